@@ -60,7 +60,7 @@ class Oracle:
         n = tx.size // frame_stride
         H = np.empty((n, NSC), np.complex128)
         fn(ptx, prx, C.c_long(frame_stride), H.ctypes.data_as(_dp), C.c_long(n))
-        return H if tx.ndim > 1 else H.reshape(NSC)
+        return H.reshape(NSC) if tx.shape == (NSC,) else H
 
     def ps_linear(self, tx, rx, frame_stride=None):
         return self._ps(self.lib.orc_ps_linear, tx, rx, frame_stride)

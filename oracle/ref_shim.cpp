@@ -58,7 +58,7 @@ void ref_mmse_as_written(const double *tx, const double *rx, double ow2, const d
 void ref_multiply(const double *M1, int r1, int c1, const double *M2, int r2, int c2, double *res)
 {
     Mat a(r1, c1), b(r2, c2), c(r1, c2);
-    a.load(M1); b.load(M2);
+    a.load(M1); b.load(M2); c.load(res);      /* copy-in/copy-out: a call that writes nothing leaves res as it was */
     multiply(a.rows, r1, c1, b.rows, r2, c2, c.rows);
     c.store(res);
 }
