@@ -1,0 +1,721 @@
+// wifi_capi.cu -- the C-ABI of include/wifi_b200.h: context, argument checking, kernel selection by dtype,
+// and the host-pointer variants (chunked H2D -> kernels -> D2H on two streams).  No CPU compute path exists
+// here: every entry point either launches the sm_100a kernels or returns an error code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "wifi_internal.h"
+
+using namespace wifi;
+
+namespace wifi {
+cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);
+cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *a, const void *rx, int64_t frame_stride,
+                                    void *H, int64_t n_frames, cudaStream_t s);
+}  // namespace wifi
+
+struct wifi_ctx {
+    int device;
+    cudaStream_t stream;
+    InterpTables tab;
+    FilterImages img;
+    int *d_info;             // device scratch: singularity flags
+    int *h_info;             // pinned mirror
+    char err[512];
+    int64_t launches;
+    int timing;
+    cudaEvent_t ev0, ev1;
+    int ev_valid;
+    // host-pointer pipeline
+    cudaStream_t hstream[2];
+    void *stage[2];
+    size_t stage_bytes[2];
+    cudaEvent_t hev[2];
+};
+
+static size_t esize(wifi_dtype dt) { return dt == WIFI_F32 ? sizeof(float2) : sizeof(double2); }
+static size_t rsize(wifi_dtype dt) { return dt == WIFI_F32 ? sizeof(float) : sizeof(double); }
+
+static int fail(wifi_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e__ = (call);                                                                                  \
+        if (e__ != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define NEED(cond)                                                                     \
+    do {                                                                               \
+        if (!(cond)) return fail(ctx, WIFI_ERR_INVALID, "invalid argument: %s", #cond); \
+    } while (0)
+#define ENTER()                                     \
+    if (!ctx) return WIFI_ERR_INVALID;              \
+    CK(cudaSetDevice(ctx->device))
+
+// bracket a launcher with the optional timing events and the launch counter
+struct Timed {
+    wifi_ctx *c; cudaStream_t s;
+    Timed(wifi_ctx *c_, cudaStream_t s_) : c(c_), s(s_) { if (c->timing) cudaEventRecord(c->ev0, s); }
+    ~Timed() { if (c->timing) { cudaEventRecord(c->ev1, s); c->ev_valid = 1; } c->launches += g_last_launches; }
+};
+
+// ---- interpolation weights (host, long double, once per context) -------------------------------
+// H_k = sum_i w[k][i] Hp_i.  Linear: main.c:86-100; Cubic: main.c:112-120 expanded (every divided
+// difference / 14, sic); Sinc: main.c:135-145 with sinc of utils.c:727-733 evaluated in double like the reference.
+static void build_tables(double *w /* [3][53][4] */)
+{
+    const int P[4] = {WIFI_P0, WIFI_P1, WIFI_P2, WIFI_P3};
+    const long double delta = WIFI_P1 - WIFI_P0;
+    for (int k = 0; k < WIFI_NSC; ++k) {
+        long double wl[4] = {0, 0, 0, 0};
+        int s = k < WIFI_P1 ? 0 : (k < WIFI_P2 ? 1 : 2);
+        long double alpha = (k - P[s]) / delta;
+        wl[s] = 1.0L - alpha; wl[s + 1] = alpha;
+        long double u = (k - WIFI_P0) / delta, v = (k - WIFI_P1) / delta, x = (k - WIFI_P2) / delta;
+        // f0 + f01 (k-P0) + f012 (k-P0)(k-P1) + f0123 (k-P0)(k-P1)(k-P2), differences all / delta
+        long double wc[4] = {1.0L - u + u * v - u * v * x, u - 2.0L * u * v + 3.0L * u * v * x, u * v - 3.0L * u * v * x, u * v * x};
+        for (int i = 0; i < 4; ++i) {
+            double a = (double)((k - P[i]) / delta);
+            double sc = a != 0 ? sin(M_PI * a) / (M_PI * a) : 1.0;
+            w[(0 * WIFI_NSC + k) * 4 + i] = (double)wl[i];
+            w[(1 * WIFI_NSC + k) * 4 + i] = (double)wc[i];
+            w[(2 * WIFI_NSC + k) * 4 + i] = sc;
+        }
+    }
+}
+
+extern "C" {
+
+const char *wifi_version(void) { return "wifi_b200 0.1 (sm_100a)"; }
+
+int wifi_create(int device, wifi_ctx **out)
+{
+    if (!out) return WIFI_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return WIFI_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return WIFI_ERR_INVALID;
+    wifi_ctx *ctx = (wifi_ctx *)calloc(1, sizeof(wifi_ctx));
+    if (!ctx) return WIFI_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return WIFI_ERR_CUDA; }
+    double w[3 * WIFI_NSC * 4];
+    float wf[3 * WIFI_NSC * 4];
+    build_tables(w);
+    for (int i = 0; i < 3 * WIFI_NSC * 4; ++i) wf[i] = (float)w[i];
+    const size_t nW = (size_t)WIFI_NSC * WIFI_NSC;
+    bool ok = cudaMalloc(&ctx->tab.w64, sizeof(w)) == cudaSuccess && cudaMalloc(&ctx->tab.w32, sizeof(wf)) == cudaSuccess &&
+              cudaMemcpy(ctx->tab.w64, w, sizeof(w), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->tab.w32, wf, sizeof(wf), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc(&ctx->img.W64, nW * sizeof(double2)) == cudaSuccess &&
+              cudaMalloc(&ctx->img.W32, nW * sizeof(float2)) == cudaSuccess &&
+              cudaMalloc(&ctx->img.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&ctx->img.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&ctx->img.B64, 112 * 112 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_info, 4096 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->hstream[0], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->hstream[1], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->hev[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->hev[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { wifi_destroy(ctx); return WIFI_ERR_CUDA; }
+    *out = ctx;
+    return WIFI_OK;
+}
+
+int wifi_destroy(wifi_ctx *ctx)
+{
+    if (!ctx) return WIFI_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->tab.w64); cudaFree(ctx->tab.w32);
+    cudaFree(ctx->img.W64); cudaFree(ctx->img.W32); cudaFree(ctx->img.Bhi); cudaFree(ctx->img.Blo); cudaFree(ctx->img.B64);
+    cudaFree(ctx->d_info);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->hstream[i]) cudaStreamDestroy(ctx->hstream[i]);
+        if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
+        cudaFree(ctx->stage[i]);
+    }
+    free(ctx);
+    return WIFI_OK;
+}
+
+int wifi_set_stream(wifi_ctx *ctx, void *s) { if (!ctx) return WIFI_ERR_INVALID; ctx->stream = (cudaStream_t)s; return WIFI_OK; }
+int wifi_synchronize(wifi_ctx *ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->stream)); return WIFI_OK; }
+const char *wifi_last_error(wifi_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+int64_t wifi_launch_count(wifi_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int wifi_enable_kernel_timing(wifi_ctx *ctx, int on) { if (!ctx) return WIFI_ERR_INVALID; ctx->timing = on; ctx->ev_valid = 0; return WIFI_OK; }
+int wifi_last_kernel_ms(wifi_ctx *ctx, float *ms)
+{
+    ENTER();
+    NEED(ms && ctx->ev_valid);
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return WIFI_OK;
+}
+
+// ---- estimators -----------------------------------------------------------------------------
+int wifi_lt_ls_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx_pre && rx_pre && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    Timed t(ctx, ctx->stream);
+    CK(launch_lt_ls(dt, tx_pre, rx_pre, H, n, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_ps_batch(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl,
+                  void *Hc, void *Hs, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && which > 0 && which < 8 && frame_stride >= WIFI_NSC);
+    NEED(n == 0 || (tx && rx));
+    NEED(n == 0 || ((!(which & WIFI_PS_LINEAR) || Hl) && (!(which & WIFI_PS_CUBIC) || Hc) && (!(which & WIFI_PS_SINC) || Hs)));
+    Timed t(ctx, ctx->stream);
+    CK(launch_ps(dt, which, tx, rx, frame_stride, Hl, Hc, Hs, n, ctx->tab, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (rx && Hlt && Hps && eq)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    Timed t(ctx, ctx->stream);
+    CK(launch_equalize(dt, rx, Hlt, Hps, eq, n, ctx->stream));
+    return WIFI_OK;
+}
+
+// ---- MMSE ---------------------------------------------------------------------------------------
+static int install_filter(wifi_ctx *ctx, cudaStream_t s)
+{
+    CK(launch_filter_install_simt(ctx->img, s));
+    ctx->launches += 1;
+    ctx->img.valid = 1;
+    return WIFI_OK;
+}
+
+int wifi_mmse_filter_form(wifi_ctx *ctx, const void *R, const double *d, void *W_out)
+{
+    ENTER();
+    NEED(R && d);
+    CK(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+    {
+        Timed t(ctx, ctx->stream);
+        CK(launch_filter_form(R, d, ctx->img.W64, ctx->d_info, ctx->stream));
+    }
+    int rc = install_filter(ctx, ctx->stream);
+    if (rc) return rc;
+    if (W_out) CK(cudaMemcpyAsync(W_out, ctx->img.W64, sizeof(double2) * WIFI_NSC * WIFI_NSC, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_info[0]) { ctx->img.valid = 0; return fail(ctx, WIFI_ERR_SINGULAR, "R + diag(d) is singular"); }
+    return WIFI_OK;
+}
+
+int wifi_mmse_filter_set(wifi_ctx *ctx, const void *W)
+{
+    ENTER();
+    NEED(W);
+    CK(cudaMemcpyAsync(ctx->img.W64, W, sizeof(double2) * WIFI_NSC * WIFI_NSC, cudaMemcpyDeviceToDevice, ctx->stream));
+    return install_filter(ctx, ctx->stream);
+}
+
+static int mmse_shared(wifi_ctx *ctx, wifi_dtype dt, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n,
+                       cudaStream_t s)
+{
+    if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
+    Timed t(ctx, s);
+    CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
+    return WIFI_OK;
+}
+
+int wifi_mmse_shared_apply_batch(wifi_ctx *ctx, wifi_dtype dt, const void *H_ls, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    return mmse_shared(ctx, dt, H_ls, nullptr, WIFI_NSC, H, n, ctx->stream);
+}
+
+int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    return mmse_shared(ctx, dt, tx, rx, frame_stride, H, n, ctx->stream);
+}
+
+static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                         const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check)
+{
+    if (check) CK(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s));
+    {
+        Timed t(ctx, s);
+        if ((flags & WIFI_SOLVE_HPD) && !hls)
+            CK(launch_mmse_perframe_hpd(dt, R, tx, rx, frame_stride, sigma2, H, n, (flags & WIFI_SOLVE_REFINE) ? 1 : 0, nullptr, s));
+        else
+            CK(launch_mmse_perframe_pivot(dt, R, tx, rx, frame_stride, sigma2, hls, H, n, check ? ctx->d_info : nullptr, s));
+    }
+    return WIFI_OK;
+}
+
+int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                             const void *sigma2, void *H, int64_t n, int flags)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (R && tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    return mmse_perframe(ctx, dt, R, tx, rx, frame_stride, sigma2, nullptr, H, n, flags, ctx->stream, false);
+}
+
+int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, const void *ow2, const void *H_ls, void *H,
+                          int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && ow2 && H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    return mmse_perframe(ctx, dt, nullptr, tx, rx, WIFI_NSC, ow2, H_ls, H, n, WIFI_SOLVE_PIVOT, ctx->stream, false);
+}
+
+// ---- utils ------------------------------------------------------------------------------------------
+static bool order_ok(int a, int b) { return a >= 0 && b >= 0 && a <= WIFI_MAX_ORDER && b <= WIFI_MAX_ORDER; }
+
+int wifi_cmatmul_batch(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && order_ok(r2, c2) && (dt == WIFI_F32 || dt == WIFI_F64));
+    if (c1 != r2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");   // utils.c:18-19: nothing written
+    NEED(batch == 0 || (A && B && C));
+    Timed t(ctx, ctx->stream);
+    CK(launch_cmatmul(dt, A, r1, c1, B, c2, C, batch, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_chermitian_batch(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(row, col) && (mode == WIFI_AS_WRITTEN || mode == WIFI_INTENDED) && (batch == 0 || (M && res)));
+    Timed t(ctx, ctx->stream);
+    CK(launch_chermitian(dt, mode, M, row, col, res, batch, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cadd_batch(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res,
+                    int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && (mode == WIFI_AS_WRITTEN || mode == WIFI_INTENDED));
+    if (r1 != r2 || c1 != c2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");   // utils.c:112-113
+    NEED(batch == 0 || (M1 && res && (mode == WIFI_AS_WRITTEN || M2)));
+    Timed t(ctx, ctx->stream);
+    CK(launch_cadd(dt, mode, M1, M2, res, batch * r1 * c1, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_couter_batch(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && order_ok(r2, c2));
+    if (c1 != r2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");   // utils.c:56-57
+    NEED(batch == 0 || (M1 && M2 && res));
+    Timed t(ctx, ctx->stream);
+    CK(launch_couter(dt, M1, r1, c1, M2, c2, res, batch, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cidentity_batch(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(size, size) && (batch == 0 || Id));
+    Timed t(ctx, ctx->stream);
+    CK(launch_cidentity(dt, Id, size, scalar, batch, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cinverse_batch(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info)
+{
+    ENTER();
+    NEED(batch >= 0 && order >= 1 && order <= WIFI_MAX_ORDER && (batch == 0 || (A && Y)));
+    Timed t(ctx, ctx->stream);
+    CK(launch_cinverse(dt, A, order, Y, batch, info, ctx->stream));
+    return WIFI_OK;
+}
+
+// ---- synthetic data / statistics ---------------------------------------------------------------------
+int wifi_synth_frames(wifi_ctx *ctx, wifi_dtype dt, uint64_t seed, int64_t first, int64_t n, int per_frame_sigma, void *tx_pre,
+                      void *rx_pre, void *tx_symb, void *rx_symb, void *H_true, void *sigma2)
+{
+    ENTER();
+    NEED(n >= 0 && first >= 0);
+    Timed t(ctx, ctx->stream);
+    CK(launch_synth(dt, seed, first, n, per_frame_sigma, tx_pre, rx_pre, tx_symb, rx_symb, H_true, sigma2, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_synth_covariance(wifi_ctx *ctx, void *R)
+{
+    ENTER();
+    NEED(R);
+    Timed t(ctx, ctx->stream);
+    CK(launch_synth_cov(R, ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_error_stats(wifi_ctx *ctx, wifi_dtype dt, const void *H, const void *Href, int64_t n_elems, double *stats)
+{
+    ENTER();
+    NEED(n_elems >= 0 && stats && (n_elems == 0 || (H && Href)));
+    Timed t(ctx, ctx->stream);
+    CK(launch_error_stats(dt, H, Href, n_elems, stats, ctx->stream));
+    return WIFI_OK;
+}
+
+// ---- host-pointer pipeline ------------------------------------------------------------------------------
+int wifi_host_alloc(void **p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? WIFI_OK : WIFI_ERR_NOMEM; }
+int wifi_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? WIFI_OK : WIFI_ERR_CUDA; }
+
+}  // extern "C"
+
+namespace {
+
+// one per-frame array crossing the PCIe boundary
+struct Arr {
+    const void *h_in;    // host source (inputs) or nullptr
+    void *h_out;         // host destination (outputs) or nullptr
+    size_t row_bytes;    // bytes per frame actually needed
+    size_t pitch_bytes;  // host distance between consecutive frames
+};
+
+constexpr size_t CHUNK_BYTES = 48u << 20;   // per-array staging target per chunk
+
+// Runs `body(dev_ptrs, n_chunk, stream)` over chunks of frames; arrays are staged compactly (pitch = row_bytes).
+template <typename Body>
+int host_pipeline(wifi_ctx *ctx, int64_t n_frames, const std::vector<Arr> &arrs, Body body)
+{
+    if (n_frames == 0) return WIFI_OK;
+    size_t max_row = 1, sum_row = 0;
+    for (auto &a : arrs) { max_row = std::max(max_row, a.row_bytes); sum_row += (a.row_bytes + 255) / 256 * 256; }
+    int64_t chunk = std::max<int64_t>(1, (int64_t)(CHUNK_BYTES / max_row));
+    chunk = std::min(chunk, n_frames);
+    if (chunk > 1 && (chunk & 1)) --chunk;                      // keep 16-byte alignment of [n][53] float2 chunks
+    std::vector<size_t> off(arrs.size());
+    size_t need = 0;
+    for (size_t i = 0; i < arrs.size(); ++i) { off[i] = need; need += (arrs[i].row_bytes * (size_t)chunk + 255) / 256 * 256; }
+    for (int b = 0; b < 2; ++b)
+        if (ctx->stage_bytes[b] < need) {
+            cudaFree(ctx->stage[b]);
+            ctx->stage[b] = nullptr; ctx->stage_bytes[b] = 0;
+            if (cudaMalloc(&ctx->stage[b], need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "staging cudaMalloc(%zu) failed", need);
+            ctx->stage_bytes[b] = need;
+        }
+    std::vector<void *> dev(arrs.size());
+    int it = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++it) {
+        const int b = it & 1;
+        const int64_t nc = std::min(chunk, n_frames - f0);
+        cudaStream_t s = ctx->hstream[b];
+        for (size_t i = 0; i < arrs.size(); ++i) {
+            dev[i] = (char *)ctx->stage[b] + off[i];
+            const Arr &a = arrs[i];
+            if (a.h_in) {
+                const char *src = (const char *)a.h_in + (size_t)f0 * a.pitch_bytes;
+                cudaError_t e = a.pitch_bytes == a.row_bytes
+                                    ? cudaMemcpyAsync(dev[i], src, a.row_bytes * (size_t)nc, cudaMemcpyHostToDevice, s)
+                                    : cudaMemcpy2DAsync(dev[i], a.row_bytes, src, a.pitch_bytes, a.row_bytes, (size_t)nc, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+            }
+        }
+        int rc = body(dev, nc, f0, s);
+        if (rc) return rc;
+        for (size_t i = 0; i < arrs.size(); ++i) {
+            const Arr &a = arrs[i];
+            if (a.h_out) {
+                char *dst = (char *)a.h_out + (size_t)f0 * a.pitch_bytes;
+                cudaError_t e = a.pitch_bytes == a.row_bytes
+                                    ? cudaMemcpyAsync(dst, dev[i], a.row_bytes * (size_t)nc, cudaMemcpyDeviceToHost, s)
+                                    : cudaMemcpy2DAsync(dst, a.pitch_bytes, dev[i], a.row_bytes, a.row_bytes, (size_t)nc, cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaStreamSynchronize(ctx->hstream[b]);
+        if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "pipeline sync: %s", cudaGetErrorString(e));
+    }
+    return WIFI_OK;
+}
+
+Arr in_arr(const void *p, size_t row, size_t pitch) { return Arr{p, nullptr, row, pitch}; }
+Arr out_arr(void *p, size_t row) { return Arr{nullptr, p, row, row}; }
+
+}  // namespace
+
+extern "C" {
+
+int wifi_lt_ls_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx_pre && rx_pre && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t row = WIFI_NSC * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx_pre, row, row), in_arr(rx_pre, row, row), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             Timed t(ctx, s);
+                             CK(launch_lt_ls(dt, d[0], d[1], d[2], nc, s));
+                             return (int)WIFI_OK;
+                         });
+}
+
+int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl, void *Hc,
+                 void *Hs, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && which > 0 && which < 8 && frame_stride >= WIFI_NSC && (n == 0 || (tx && rx)));
+    NEED(n == 0 || ((!(which & WIFI_PS_LINEAR) || Hl) && (!(which & WIFI_PS_CUBIC) || Hc) && (!(which & WIFI_PS_SINC) || Hs)));
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    std::vector<Arr> arrs = {in_arr(tx, row, pitch), in_arr(rx, row, pitch)};
+    int il = -1, ic = -1, is = -1;
+    if (which & WIFI_PS_LINEAR) { il = (int)arrs.size(); arrs.push_back(out_arr(Hl, row)); }
+    if (which & WIFI_PS_CUBIC) { ic = (int)arrs.size(); arrs.push_back(out_arr(Hc, row)); }
+    if (which & WIFI_PS_SINC) { is = (int)arrs.size(); arrs.push_back(out_arr(Hs, row)); }
+    return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+        Timed t(ctx, s);
+        CK(launch_ps(dt, which, d[0], d[1], WIFI_NSC, il >= 0 ? d[il] : nullptr, ic >= 0 ? d[ic] : nullptr, is >= 0 ? d[is] : nullptr,
+                     nc, ctx->tab, s));
+        return (int)WIFI_OK;
+    });
+}
+
+int wifi_equalize_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (rx && Hlt && Hps && eq)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t row = WIFI_NSC * esize(dt), frow = WIFI_FRAME * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(rx, frow, frow), in_arr(Hlt, row, row), in_arr(Hps, row, row), out_arr(eq, frow)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             Timed t(ctx, s);
+                             CK(launch_equalize(dt, d[0], d[1], d[2], d[3], nc, s));
+                             return (int)WIFI_OK;
+                         });
+}
+
+int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R, const double *d, void *W_out)
+{
+    ENTER();
+    NEED(R && d);
+    const size_t nW = sizeof(double2) * WIFI_NSC * WIFI_NSC;
+    const size_t need = 2 * nW + 256 * sizeof(double);
+    if (ctx->stage_bytes[0] < need) {
+        cudaFree(ctx->stage[0]); ctx->stage[0] = nullptr; ctx->stage_bytes[0] = 0;
+        CK(cudaMalloc(&ctx->stage[0], need));
+        ctx->stage_bytes[0] = need;
+    }
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base, R, nW, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + 2 * nW, d, sizeof(double) * WIFI_NSC, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_mmse_filter_form(ctx, base, (const double *)(base + 2 * nW), W_out ? base + nW : nullptr);
+    if (rc) return rc;
+    if (W_out) {
+        CK(cudaMemcpyAsync(W_out, base + nW, nW, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return WIFI_OK;
+}
+
+int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    CK(cudaStreamSynchronize(ctx->stream));   // the filter images were built on the ctx stream
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return mmse_shared(ctx, dt, d[0], d[1], WIFI_NSC, d[2], nc, s);
+                         });
+}
+
+int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                            const void *sigma2, void *H, int64_t n, int flags)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (R && tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    void *dR = nullptr;
+    const size_t nR = esize(dt) * WIFI_NSC * WIFI_NSC;
+    CK(cudaMalloc(&dR, nR));
+    cudaError_t e = cudaMemcpy(dR, R, nR, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dR); return fail(ctx, WIFI_ERR_CUDA, "H2D R: %s", cudaGetErrorString(e)); }
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    int rc = host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), in_arr(sigma2, rsize(dt), rsize(dt)), out_arr(H, row)},
+                           [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                               return mmse_perframe(ctx, dt, dR, d[0], d[1], WIFI_NSC, d[2], nullptr, d[3], nc, flags, s, false);
+                           });
+    cudaFree(dR);
+    return rc;
+}
+
+int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, const void *ow2, const void *H_ls, void *H,
+                         int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && ow2 && H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t row = WIFI_NSC * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx, row, row), in_arr(rx, row, row), in_arr(ow2, rsize(dt), rsize(dt)), in_arr(H_ls, row, row), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return mmse_perframe(ctx, dt, nullptr, d[0], d[1], WIFI_NSC, d[2], d[3], d[4], nc, WIFI_SOLVE_PIVOT, s, false);
+                         });
+}
+
+// small utils: one shot through the ctx stream
+#define UTIL_STAGE(total_bytes)                                                   \
+    if (ctx->stage_bytes[0] < (total_bytes)) {                                    \
+        cudaFree(ctx->stage[0]); ctx->stage[0] = nullptr; ctx->stage_bytes[0] = 0; \
+        CK(cudaMalloc(&ctx->stage[0], (total_bytes)));                            \
+        ctx->stage_bytes[0] = (total_bytes);                                      \
+    }
+
+int wifi_cmatmul_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && order_ok(r2, c2));
+    if (c1 != r2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");
+    if (batch == 0) return WIFI_OK;
+    NEED(A && B && C);
+    size_t na = esize(dt) * r1 * c1 * batch, nb = esize(dt) * r2 * c2 * batch, nc = esize(dt) * r1 * c2 * batch;
+    size_t oa = 0, ob = (na + 255) / 256 * 256, oc = ob + (nb + 255) / 256 * 256;
+    UTIL_STAGE(oc + nc);
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base + oa, A, na, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + ob, B, nb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_cmatmul_batch(ctx, dt, base + oa, r1, c1, base + ob, r2, c2, base + oc, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(C, base + oc, nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_chermitian_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(row, col) && (mode == WIFI_AS_WRITTEN || mode == WIFI_INTENDED));
+    if (batch == 0 || row * col == 0) return WIFI_OK;
+    NEED(M && res);
+    size_t n = esize(dt) * row * col * batch, o = (n + 255) / 256 * 256;
+    UTIL_STAGE(o + n);
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base, M, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_chermitian_batch(ctx, dt, mode, base, row, col, base + o, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(res, base + o, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cadd_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && (mode == WIFI_AS_WRITTEN || mode == WIFI_INTENDED));
+    if (r1 != r2 || c1 != c2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");
+    if (batch == 0 || r1 * c1 == 0) return WIFI_OK;
+    NEED(M1 && res && (mode == WIFI_AS_WRITTEN || M2));
+    size_t n = esize(dt) * r1 * c1 * batch, o = (n + 255) / 256 * 256;
+    UTIL_STAGE(3 * o);
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base, M1, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (M2) CK(cudaMemcpyAsync(base + o, M2, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_cadd_batch(ctx, dt, mode, base, r1, c1, base + o, r2, c2, base + 2 * o, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(res, base + 2 * o, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_couter_host(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(r1, c1) && order_ok(r2, c2));
+    if (c1 != r2) return fail(ctx, WIFI_ERR_INVALID, "Matrices dimension missmatch");
+    if (batch == 0 || r1 * c2 == 0) return WIFI_OK;
+    NEED(M1 && M2 && res);
+    size_t na = esize(dt) * r1 * c1 * batch, nb = esize(dt) * r2 * c2 * batch, nc = esize(dt) * r1 * c2 * batch;
+    size_t ob = (na + 255) / 256 * 256, oc = ob + (nb + 255) / 256 * 256;
+    UTIL_STAGE(oc + nc);
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base, M1, na, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + ob, M2, nb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_couter_batch(ctx, dt, base, r1, c1, base + ob, r2, c2, base + oc, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(res, base + oc, nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cidentity_host(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch)
+{
+    ENTER();
+    NEED(batch >= 0 && order_ok(size, size));
+    if (batch == 0 || size == 0) return WIFI_OK;
+    NEED(Id);
+    size_t n = esize(dt) * size * size * batch;
+    UTIL_STAGE(n);
+    int rc = wifi_cidentity_batch(ctx, dt, ctx->stage[0], size, scalar, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(Id, ctx->stage[0], n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WIFI_OK;
+}
+
+int wifi_cinverse_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info_host)
+{
+    ENTER();
+    NEED(batch >= 0 && order >= 1 && order <= WIFI_MAX_ORDER);
+    if (batch == 0) return WIFI_OK;
+    NEED(A && Y);
+    size_t n = esize(dt) * order * order * batch, o = (n + 255) / 256 * 256;
+    size_t oi = 2 * o;
+    UTIL_STAGE(oi + sizeof(int) * batch);
+    char *base = (char *)ctx->stage[0];
+    CK(cudaMemcpyAsync(base, A, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = wifi_cinverse_batch(ctx, dt, base, order, base + o, batch, (int *)(base + oi));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(Y, base + o, n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> info(batch);
+    CK(cudaMemcpyAsync(info.data(), base + oi, sizeof(int) * batch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int any = 0;
+    for (int64_t b = 0; b < batch; ++b) { if (info_host) info_host[b] = info[b]; any |= info[b]; }
+    return any ? fail(ctx, WIFI_ERR_SINGULAR, "singular matrix in batch") : WIFI_OK;
+}
+
+// ---- default context for the single-frame drop-ins ------------------------------------------------------
+wifi_ctx *wifi_default_ctx(void)
+{
+    static std::mutex mu;
+    static wifi_ctx *g = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!g) {
+        const char *env = getenv("WIFI_B200_DEVICE");
+        int dev = env ? atoi(env) : 0;
+        int rc = wifi_create(dev, &g);
+        if (rc != WIFI_OK) {
+            fprintf(stderr, "wifi_b200: no usable CUDA device (wifi_create(%d) -> %d); there is no CPU fallback\n", dev, rc);
+            abort();
+        }
+    }
+    return g;
+}
+
+}  // extern "C"

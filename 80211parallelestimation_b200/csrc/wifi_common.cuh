@@ -1,0 +1,58 @@
+// wifi_common.cuh -- shared device helpers of the sm_100a kernels (complex arithmetic on
+// interleaved float2/double2, streaming vector loads/stores, frame constants).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/wifi_b200.h"
+
+#define NSC WIFI_NSC
+#define NBLK WIFI_NBLK
+#define FRAME WIFI_FRAME
+#define DCBIN WIFI_DC
+
+namespace wifi {
+
+template <typename T> struct V2;
+template <> struct V2<float> { using type = float2; };
+template <> struct V2<double> { using type = double2; };
+template <typename T> using cx = typename V2<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ cx<T> mk(T re, T im) { cx<T> r; r.x = re; r.y = im; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
+// acc += a * b
+template <typename C> __device__ __forceinline__ void cfma(C &acc, C a, C b)
+{
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a * b
+template <typename C> __device__ __forceinline__ void cfms(C &acc, C a, C b)
+{
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename C> __device__ __forceinline__ auto cabs2(C a) -> decltype(a.x) { return a.x * a.x + a.y * a.y; }
+// a / b, textbook formula (what rx/tx of main.c:83 computes, up to rounding); 0/0 -> NaN like the reference
+template <typename C> __device__ __forceinline__ C cdiv(C a, C b)
+{
+    auto den = b.x * b.x + b.y * b.y;
+    C r;
+    r.x = (a.x * b.x + a.y * b.y) / den;
+    r.y = (a.y * b.x - a.x * b.y) / den;
+    return r;
+}
+template <typename C> __device__ __forceinline__ C crecip(C b)
+{
+    auto den = b.x * b.x + b.y * b.y;
+    C r; r.x = b.x / den; r.y = -b.y / den; return r;
+}
+template <typename C, typename S> __device__ __forceinline__ C cscale(C a, S s) { a.x *= s; a.y *= s; return a; }
+
+// streaming (evict-first) global accesses: every LS/interp byte is touched exactly once
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V *p, V v) { __stcs(p, v); }
+
+}  // namespace wifi

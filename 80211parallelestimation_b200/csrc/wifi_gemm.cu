@@ -1,0 +1,261 @@
+// wifi_gemm.cu -- shared-filter PS_MMSE as one GEMM over all frames, plus the small batched matrix utils.
+//
+//   H[n][53] = H_ls[n][53] * W^T          (multiply utils.c:16-31 of the 53x53 filter with every frame's LS vector)
+//
+// mmse_shared_simt_kernel: CUDA-core version (both dtypes): W^T and a 64-frame tile of H_ls (optionally formed
+// in place as rx/tx, main.c:83 arithmetic) staged in shared memory, register tile 7 rows x 2 frames per thread,
+// result staged back through shared memory so global stores are one contiguous run.
+// The FP32 tensor-core path (3xTF32 on tcgen05, accumulators in TMEM) is in wifi_gemm_tc.cu.
+#include <algorithm>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+// ------------------------------------------------------------------------------------------
+// filter images
+// ------------------------------------------------------------------------------------------
+__global__ void filter_install_kernel(const double2 *__restrict__ W, float2 *__restrict__ W32)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < NSC * NSC) W32[e] = make_float2((float)W[e].x, (float)W[e].y);
+}
+
+cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s)
+{
+    filter_install_kernel<<<(NSC * NSC + 255) / 256, 256, 0, s>>>((const double2 *)img.W64, (float2 *)img.W32);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT shared-filter kernel
+// ------------------------------------------------------------------------------------------
+constexpr int MS_THREADS = 256;
+constexpr int MS_TILE = 64;             // frames per CTA iteration
+constexpr int MS_RPW = 7;               // filter rows per warp (8 warps x 7 = 56 >= 53)
+constexpr int MS_WLD = 56;              // Wt[j][r] row length
+constexpr int MS_HLD = MS_TILE + 1;     // hT[j][f] row length (odd: conflict-light transposed stores)
+
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(MS_THREADS) mmse_shared_simt_kernel(const cx<T> *__restrict__ W, const cx<T> *__restrict__ a_in,
+                                                                      const cx<T> *__restrict__ rx, int64_t frame_stride,
+                                                                      cx<T> *__restrict__ H, int64_t n_frames)
+{
+    extern __shared__ __align__(16) unsigned char ms_smem[];
+    cx<T> *Wt = (cx<T> *)ms_smem;              // [53][56]   Wt[j][r] = W[r][j]
+    cx<T> *hT = Wt + NSC * MS_WLD;             // [53][65]   hT[j][f] = H_ls[f][j]; reused as output staging
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int e = threadIdx.x; e < NSC * MS_WLD; e += MS_THREADS) {
+        int j = e / MS_WLD, r = e - j * MS_WLD;
+        Wt[e] = r < NSC ? W[r * NSC + j] : mk<T>(0, 0);
+    }
+
+    const int64_t n_tiles = (n_frames + MS_TILE - 1) / MS_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t f0 = tile * MS_TILE;
+        const int nf = (int)min((int64_t)MS_TILE, n_frames - f0);
+        __syncthreads();   // previous tile's staging fully drained (and Wt visible on the first pass)
+        for (int e = threadIdx.x; e < MS_TILE * NSC; e += MS_THREADS) {
+            int f = e / NSC, j = e - f * NSC;
+            cx<T> v = mk<T>(0, 0);
+            if (f < nf) {
+                if (FUSED) {
+                    int64_t off = (f0 + f) * frame_stride + j;
+                    v = cdiv(ld_stream(rx + off), ld_stream(a_in + off));     // per-block LS  rx/tx
+                } else {
+                    v = ld_stream(a_in + (f0 + f) * NSC + j);
+                }
+            }
+            hT[j * MS_HLD + f] = v;
+        }
+        __syncthreads();
+
+        cx<T> acc[MS_RPW][2];
+#pragma unroll
+        for (int r = 0; r < MS_RPW; ++r) acc[r][0] = acc[r][1] = mk<T>(0, 0);
+        const int r0 = warp * MS_RPW;
+#pragma unroll 4
+        for (int j = 0; j < NSC; ++j) {
+            cx<T> h0 = hT[j * MS_HLD + lane], h1 = hT[j * MS_HLD + lane + 32];
+#pragma unroll
+            for (int r = 0; r < MS_RPW; ++r) {
+                cx<T> w = Wt[j * MS_WLD + r0 + r];           // warp-uniform address: broadcast
+                cfma(acc[r][0], w, h0);
+                cfma(acc[r][1], w, h1);
+            }
+        }
+        __syncthreads();   // everyone is done reading hT
+        // stage the result row-major [f][53] so the global write below is one contiguous run
+        cx<T> *stage = hT;
+#pragma unroll
+        for (int r = 0; r < MS_RPW; ++r)
+            if (r0 + r < NSC) {
+                stage[lane * NSC + r0 + r] = acc[r][0];
+                stage[(lane + 32) * NSC + r0 + r] = acc[r][1];
+            }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nf * NSC; e += MS_THREADS) st_stream(H + f0 * NSC + e, stage[e]);
+    }
+}
+
+template <typename T, bool FUSED>
+static cudaError_t launch_simt(const void *W, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
+                               cudaStream_t s)
+{
+    size_t smem = sizeof(cx<T>) * (NSC * MS_WLD + NSC * MS_HLD);
+    static_assert(NSC * MS_HLD >= MS_TILE * NSC, "staging must fit");
+    cudaError_t e = cudaFuncSetAttribute(mmse_shared_simt_kernel<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t n_tiles = (n_frames + MS_TILE - 1) / MS_TILE;
+    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148 * (sizeof(T) == 4 ? 4 : 2));
+    mmse_shared_simt_kernel<T, FUSED><<<grid, MS_THREADS, smem, s>>>((const cx<T> *)W, (const cx<T> *)a, (const cx<T> *)rx,
+                                                                     frame_stride, (cx<T> *)H, n_frames);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *a, const void *rx, int64_t frame_stride,
+                                    void *H, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    if (dt == WIFI_F32)
+        return rx ? launch_simt<float, true>(img.W32, a, rx, frame_stride, H, n_frames, s)
+                  : launch_simt<float, false>(img.W32, a, nullptr, NSC, H, n_frames, s);
+    return rx ? launch_simt<double, true>(img.W64, a, rx, frame_stride, H, n_frames, s)
+              : launch_simt<double, false>(img.W64, a, nullptr, NSC, H, n_frames, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// batched small-matrix utils (utils.h:38-60)
+// ------------------------------------------------------------------------------------------
+// multiply utils.c:16-31: one CTA per matrix pair, k ascending like the reference's inner loop
+template <typename T>
+__global__ void cmatmul_kernel(const cx<T> *__restrict__ A, int r1, int c1, const cx<T> *__restrict__ B, int c2, cx<T> *__restrict__ C)
+{
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    cx<T> *sa = (cx<T> *)mm_smem, *sb = sa + r1 * c1;
+    const cx<T> *Ab = A + (int64_t)blockIdx.x * r1 * c1, *Bb = B + (int64_t)blockIdx.x * c1 * c2;
+    cx<T> *Cb = C + (int64_t)blockIdx.x * r1 * c2;
+    for (int e = threadIdx.x; e < r1 * c1; e += blockDim.x) sa[e] = Ab[e];
+    for (int e = threadIdx.x; e < c1 * c2; e += blockDim.x) sb[e] = Bb[e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < r1 * c2; e += blockDim.x) {
+        int c = e / c2, d = e - c * c2;
+        cx<T> sum = mk<T>(0, 0);
+        for (int k = 0; k < c1; ++k) cfma(sum, sa[c * c1 + k], sb[k * c2 + d]);
+        Cb[e] = sum;
+    }
+}
+
+cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (batch == 0 || r1 * c2 == 0) return cudaSuccess;
+    g_last_launches = 1;
+    cudaError_t e;
+    if (dt == WIFI_F32) {
+        size_t smem = sizeof(float2) * ((size_t)r1 * c1 + (size_t)c1 * c2);
+        e = cudaFuncSetAttribute(cmatmul_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cmatmul_kernel<float><<<(unsigned)batch, 256, smem, s>>>((const float2 *)A, r1, c1, (const float2 *)B, c2, (float2 *)C);
+    } else {
+        size_t smem = sizeof(double2) * ((size_t)r1 * c1 + (size_t)c1 * c2);
+        e = cudaFuncSetAttribute(cmatmul_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cmatmul_kernel<double><<<(unsigned)batch, 256, smem, s>>>((const double2 *)A, r1, c1, (const double2 *)B, c2, (double2 *)C);
+    }
+    return cudaGetLastError();
+}
+
+// hermitian utils.c:3-7.  mode AS_WRITTEN: res[c][r] = Re(M[r][c]) - Im(M[r][c]) (real-valued, sic);
+// mode INTENDED: conjugate transpose.  Tiled through shared memory so both sides are coalesced.
+template <typename T>
+__global__ void chermitian_kernel(int mode, const cx<T> *__restrict__ M, int row, int col, cx<T> *__restrict__ res)
+{
+    __shared__ cx<T> tile[32][33];
+    const cx<T> *Mb = M + (int64_t)blockIdx.z * row * col;
+    cx<T> *Rb = res + (int64_t)blockIdx.z * row * col;
+    int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+    if (r < row && c < col) tile[threadIdx.y][threadIdx.x] = Mb[r * col + c];
+    __syncthreads();
+    int rr = blockIdx.y * 32 + threadIdx.x, cc = blockIdx.x * 32 + threadIdx.y;   // res[cc][rr]
+    if (rr < row && cc < col) {
+        cx<T> m = tile[threadIdx.x][threadIdx.y];
+        Rb[cc * row + rr] = mode == WIFI_AS_WRITTEN ? mk<T>(m.x - m.y, (T)0) : mk<T>(m.x, -m.y);
+    }
+}
+
+cudaError_t launch_chermitian(wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (batch == 0 || row * col == 0) return cudaSuccess;
+    g_last_launches = 1;
+    dim3 grid((col + 31) / 32, (row + 31) / 32, (unsigned)batch), blk(32, 32);
+    if (dt == WIFI_F32) chermitian_kernel<float><<<grid, blk, 0, s>>>(mode, (const float2 *)M, row, col, (float2 *)res);
+    else chermitian_kernel<double><<<grid, blk, 0, s>>>(mode, (const double2 *)M, row, col, (double2 *)res);
+    return cudaGetLastError();
+}
+
+// addition utils.c:111-121.  AS_WRITTEN: res = M1 + M1 (M2 ignored, sic); INTENDED: M1 + M2
+template <typename T>
+__global__ void cadd_kernel(int mode, const cx<T> *__restrict__ M1, const cx<T> *__restrict__ M2, cx<T> *__restrict__ res, int64_t n)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) { cx<T> a = M1[e]; res[e] = cadd(a, mode == WIFI_AS_WRITTEN ? a : M2[e]); }
+}
+
+cudaError_t launch_cadd(wifi_dtype dt, int mode, const void *M1, const void *M2, void *res, int64_t n, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n == 0) return cudaSuccess;
+    g_last_launches = 1;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (dt == WIFI_F32) cadd_kernel<float><<<grid, 256, 0, s>>>(mode, (const float2 *)M1, (const float2 *)M2, (float2 *)res, n);
+    else cadd_kernel<double><<<grid, 256, 0, s>>>(mode, (const double2 *)M1, (const double2 *)M2, (double2 *)res, n);
+    return cudaGetLastError();
+}
+
+// multiplyVxVeqM utils.c:55-65: res[r][c] = M1[r][0] * M2[0][c]
+template <typename T>
+__global__ void couter_kernel(const cx<T> *__restrict__ M1, int r1, int c1, const cx<T> *__restrict__ M2, int c2, int r2,
+                              cx<T> *__restrict__ res)
+{
+    const cx<T> *a = M1 + (int64_t)blockIdx.y * r1 * c1, *b = M2 + (int64_t)blockIdx.y * r2 * c2;
+    cx<T> *o = res + (int64_t)blockIdx.y * r1 * c2;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < r1 * c2) { int r = e / c2, c = e - r * c2; o[e] = cmul(a[r * c1], b[c]); }
+}
+
+cudaError_t launch_couter(wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int c2, void *res, int64_t batch, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (batch == 0 || r1 * c2 == 0) return cudaSuccess;
+    g_last_launches = 1;
+    dim3 grid((r1 * c2 + 255) / 256, (unsigned)batch);
+    if (dt == WIFI_F32) couter_kernel<float><<<grid, 256, 0, s>>>((const float2 *)M1, r1, c1, (const float2 *)M2, c2, c1, (float2 *)res);
+    else couter_kernel<double><<<grid, 256, 0, s>>>((const double2 *)M1, r1, c1, (const double2 *)M2, c2, c1, (double2 *)res);
+    return cudaGetLastError();
+}
+
+// identity utils.c:84-93
+template <typename T> __global__ void cidentity_kernel(cx<T> *Id, int size, T scalar, int64_t n)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) { int64_t w = e % ((int64_t)size * size); Id[e] = mk<T>((w / size == w % size) ? scalar : (T)0, (T)0); }
+}
+
+cudaError_t launch_cidentity(wifi_dtype dt, void *Id, int size, double scalar, int64_t batch, cudaStream_t s)
+{
+    g_last_launches = 0;
+    int64_t n = batch * size * size;
+    if (n == 0) return cudaSuccess;
+    g_last_launches = 1;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (dt == WIFI_F32) cidentity_kernel<float><<<grid, 256, 0, s>>>((float2 *)Id, size, (float)scalar, n);
+    else cidentity_kernel<double><<<grid, 256, 0, s>>>((double2 *)Id, size, scalar, n);
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

@@ -1,0 +1,62 @@
+// wifi_internal.h -- launcher prototypes shared by the .cu translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/wifi_b200.h"
+
+namespace wifi {
+
+// interpolation weight tables: H_k = sum_i w[est][k][i] * Hp_i  (est: 0 linear, 1 cubic, 2 sinc)
+struct InterpTables {
+    float *w32;   // [3][53][4]
+    double *w64;  // [3][53][4]
+};
+
+// shared MMSE filter operand images (built by filter_install from W, 53x53 double2 row-major)
+struct FilterImages {
+    double *W64;     // [53][53] double2, row-major (the FP64 truth)
+    float *W32;      // [53][53] float2 (rounded)
+    float *Bhi;      // tf32 "hi" image of the real embedding, UMMA canonical K-major no-swizzle layout [112 x 112]
+    float *Blo;      // tf32 "lo" image (W - hi)
+    double *B64;     // real embedding for the FP64 path, [112][112] row-major (n-major, k contiguous)
+    int valid;
+};
+
+cudaError_t launch_lt_ls(wifi_dtype dt, const void *tx, const void *rx, void *H, int64_t n_frames, cudaStream_t s);
+cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl, void *Hc,
+                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s);
+cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n_frames,
+                            cudaStream_t s);
+
+// dense solves (wifi_solve.cu)
+cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s);
+cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);
+cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info,
+                                       cudaStream_t s);
+cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                                     const void *sigma2, void *H, int64_t n_frames, int refine, const void *R64,
+                                     cudaStream_t s);
+
+// shared-filter GEMM + small matrix utils (wifi_gemm.cu)
+cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);   // W64 -> W32
+cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *tx_or_hls, const void *rx,
+                                    int64_t frame_stride, void *H, int64_t n_frames, cudaStream_t s);  // rx == NULL: apply only
+cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch,
+                           cudaStream_t s);
+cudaError_t launch_chermitian(wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch, cudaStream_t s);
+cudaError_t launch_cadd(wifi_dtype dt, int mode, const void *M1, const void *M2, void *res, int64_t n_elems, cudaStream_t s);
+cudaError_t launch_couter(wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int c2, void *res, int64_t batch,
+                          cudaStream_t s);
+cudaError_t launch_cidentity(wifi_dtype dt, void *Id, int size, double scalar, int64_t batch, cudaStream_t s);
+
+// synthetic frames + statistics (wifi_synth.cu)
+cudaError_t launch_synth(wifi_dtype dt, uint64_t seed, int64_t first, int64_t n, int per_frame_sigma, void *tx_pre, void *rx_pre,
+                         void *tx_symb, void *rx_symb, void *H_true, void *sigma2, cudaStream_t s);
+cudaError_t launch_synth_cov(void *R64, cudaStream_t s);
+cudaError_t launch_error_stats(wifi_dtype dt, const void *H, const void *Href, int64_t n_elems, double *stats, cudaStream_t s);
+
+// number of kernel launches the last launcher call issued (for gpu_launches accounting)
+extern thread_local int g_last_launches;
+
+}  // namespace wifi

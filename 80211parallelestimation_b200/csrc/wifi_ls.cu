@@ -1,0 +1,244 @@
+// wifi_ls.cu -- the HBM-bound estimators: LT_LS (main.c:66-75), pilot-LS + Linear/Cubic/Sinc
+// interpolation (main.c:77-146, utils.c:727-733) and the equalizer (WiFi_Equalization.m:1-9).
+//
+// All three are streaming kernels: every input byte is read once, every output byte written once.
+//   lt_ls      flat over the contiguous [n][53] arrays, 16-byte vectors per thread, 4 vectors in flight.
+//   ps_interp  a CTA owns a tile of frames; the 8 pilot values of each frame are gathered (sector-granular,
+//              the other 45 sub-carriers of the row are never fetched) and divided once into shared memory;
+//              all requested interpolators are then produced from that staged tile.  Each thread owns ONE
+//              sub-carrier k (blockDim = 6*53), so its 4 real weights per estimator live in registers and the
+//              stores of a warp are one contiguous run of the [n][53] output.
+//   equalize   one thread per (frame, sub-carrier): both channel values in registers, 15 independent
+//              loads/stores down the OFDM blocks (consecutive threads = consecutive k = coalesced).
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+thread_local int g_last_launches = 0;
+
+// ------------------------------------------------------------------------------------------
+// LT_LS
+// ------------------------------------------------------------------------------------------
+// main.c:69-72 as written: c = Re(tx) - Im(tx) (a real scalar), H = (c*rx)/(c*tx).  Re(tx) == Im(tx)
+// gives 0/0 = NaN exactly like the reference.
+template <typename T> __device__ __forceinline__ cx<T> lt_ls_one(cx<T> tx, cx<T> rx)
+{
+    T c = tx.x - tx.y;
+    return cdiv(mk<T>(c * rx.x, c * rx.y), mk<T>(c * tx.x, c * tx.y));
+}
+
+constexpr int LT_THREADS = 256;
+constexpr int LT_UNROLL = 4;
+
+__global__ void __launch_bounds__(LT_THREADS) lt_ls_f32_kernel(const float4 *__restrict__ tx, const float4 *__restrict__ rx,
+                                                               float4 *__restrict__ H, int64_t n_vec)
+{
+    // one float4 = 2 complex elements; element index e = 2*v
+    const int64_t base = (int64_t)blockIdx.x * (LT_THREADS * LT_UNROLL);
+    const int kbase = (int)((2 * base) % NSC);
+    float4 a[LT_UNROLL], b[LT_UNROLL];
+#pragma unroll
+    for (int j = 0; j < LT_UNROLL; ++j) {
+        int64_t v = base + j * LT_THREADS + threadIdx.x;
+        if (v < n_vec) { a[j] = ld_stream(tx + v); b[j] = ld_stream(rx + v); }
+    }
+#pragma unroll
+    for (int j = 0; j < LT_UNROLL; ++j) {
+        int local = j * LT_THREADS + threadIdx.x;
+        int64_t v = base + local;
+        if (v < n_vec) {
+            int k0 = (kbase + 2 * local) % NSC;
+            float2 h0 = lt_ls_one<float>(make_float2(a[j].x, a[j].y), make_float2(b[j].x, b[j].y));
+            float2 h1 = lt_ls_one<float>(make_float2(a[j].z, a[j].w), make_float2(b[j].z, b[j].w));
+            if (k0 == DCBIN) h0 = make_float2(0.f, 0.f);             // main.c:74
+            if (k0 == DCBIN - 1) h1 = make_float2(0.f, 0.f);
+            st_stream(H + v, make_float4(h0.x, h0.y, h1.x, h1.y));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LT_THREADS) lt_ls_f64_kernel(const double2 *__restrict__ tx, const double2 *__restrict__ rx,
+                                                               double2 *__restrict__ H, int64_t n_elems)
+{
+    const int64_t base = (int64_t)blockIdx.x * (LT_THREADS * LT_UNROLL);
+    const int kbase = (int)(base % NSC);
+    double2 a[LT_UNROLL], b[LT_UNROLL];
+#pragma unroll
+    for (int j = 0; j < LT_UNROLL; ++j) {
+        int64_t e = base + j * LT_THREADS + threadIdx.x;
+        if (e < n_elems) { a[j] = ld_stream(tx + e); b[j] = ld_stream(rx + e); }
+    }
+#pragma unroll
+    for (int j = 0; j < LT_UNROLL; ++j) {
+        int local = j * LT_THREADS + threadIdx.x;
+        int64_t e = base + local;
+        if (e < n_elems) {
+            double2 h = lt_ls_one<double>(a[j], b[j]);
+            if ((kbase + local) % NSC == DCBIN) h = make_double2(0.0, 0.0);
+            st_stream(H + e, h);
+        }
+    }
+}
+
+// odd tail element of the float path (n_frames odd -> 53*n odd)
+__global__ void lt_ls_f32_tail_kernel(const float2 *tx, const float2 *rx, float2 *H, int64_t e)
+{
+    float2 h = lt_ls_one<float>(tx[e], rx[e]);
+    if (e % NSC == DCBIN) h = make_float2(0.f, 0.f);
+    H[e] = h;
+}
+
+cudaError_t launch_lt_ls(wifi_dtype dt, const void *tx, const void *rx, void *H, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    const int64_t n_elems = n_frames * NSC;
+    if (n_elems == 0) return cudaSuccess;
+    const int64_t per_block = LT_THREADS * LT_UNROLL;
+    if (dt == WIFI_F32) {
+        int64_t n_vec = n_elems / 2;
+        if (n_vec) {
+            lt_ls_f32_kernel<<<(unsigned)((n_vec + per_block - 1) / per_block), LT_THREADS, 0, s>>>(
+                (const float4 *)tx, (const float4 *)rx, (float4 *)H, n_vec);
+            ++g_last_launches;
+        }
+        if (n_elems & 1) {
+            lt_ls_f32_tail_kernel<<<1, 1, 0, s>>>((const float2 *)tx, (const float2 *)rx, (float2 *)H, n_elems - 1);
+            ++g_last_launches;
+        }
+    } else {
+        lt_ls_f64_kernel<<<(unsigned)((n_elems + per_block - 1) / per_block), LT_THREADS, 0, s>>>(
+            (const double2 *)tx, (const double2 *)rx, (double2 *)H, n_elems);
+        ++g_last_launches;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// pilot LS + Linear / Cubic / Sinc
+// ------------------------------------------------------------------------------------------
+constexpr int PS_FPP = 6;                  // frames per pass
+constexpr int PS_THREADS = PS_FPP * NSC;   // 318: thread t owns sub-carrier t % 53 (2 idle lanes in 10 warps)
+constexpr int PS_PASSES = 8;
+constexpr int PS_TILE = PS_FPP * PS_PASSES;  // 48 frames per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx,
+                                                               int64_t frame_stride, cx<T> *__restrict__ Hl,
+                                                               cx<T> *__restrict__ Hc, cx<T> *__restrict__ Hs, int which,
+                                                               int64_t n_frames, const T *__restrict__ wtab)
+{
+    __shared__ cx<T> hp[PS_TILE][4];
+    const int64_t f0 = (int64_t)blockIdx.x * PS_TILE;
+    const int nf = (int)min((int64_t)PS_TILE, n_frames - f0);
+
+    // phase 1: pilot LS  Hp_i = rx[P_i] / tx[P_i]  (main.c:82-84), one (frame, pilot) pair per thread
+    for (int idx = threadIdx.x; idx < nf * 4; idx += PS_THREADS) {
+        int f = idx >> 2, p = idx & 3;
+        int64_t off = (f0 + f) * frame_stride + (WIFI_P0 + (WIFI_P1 - WIFI_P0) * p);
+        hp[f][p] = cdiv(ld_stream(rx + off), ld_stream(tx + off));
+    }
+    // this thread's sub-carrier and its weights (registers)
+    const int k = threadIdx.x % NSC, fsub = threadIdx.x / NSC;
+    T wl[4], wc[4], ws[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        wl[i] = __ldg(wtab + (0 * NSC + k) * 4 + i);
+        wc[i] = __ldg(wtab + (1 * NSC + k) * 4 + i);
+        ws[i] = __ldg(wtab + (2 * NSC + k) * 4 + i);
+    }
+    __syncthreads();
+
+    // phase 2: H_k = sum_i w[k][i] Hp_i ; a warp writes one contiguous run of the [n][53] output
+#pragma unroll
+    for (int pass = 0; pass < PS_PASSES; ++pass) {
+        int f = pass * PS_FPP + fsub;
+        if (f < nf) {
+            cx<T> h0 = hp[f][0], h1 = hp[f][1], h2 = hp[f][2], h3 = hp[f][3];
+            int64_t o = (f0 + f) * NSC + k;
+            if (which & WIFI_PS_LINEAR) {
+                cx<T> v = mk<T>(wl[0] * h0.x + wl[1] * h1.x + wl[2] * h2.x + wl[3] * h3.x,
+                                wl[0] * h0.y + wl[1] * h1.y + wl[2] * h2.y + wl[3] * h3.y);
+                st_stream(Hl + o, v);
+            }
+            if (which & WIFI_PS_CUBIC) {
+                cx<T> v = mk<T>(wc[0] * h0.x + wc[1] * h1.x + wc[2] * h2.x + wc[3] * h3.x,
+                                wc[0] * h0.y + wc[1] * h1.y + wc[2] * h2.y + wc[3] * h3.y);
+                st_stream(Hc + o, v);
+            }
+            if (which & WIFI_PS_SINC) {
+                cx<T> v = mk<T>(ws[0] * h0.x + ws[1] * h1.x + ws[2] * h2.x + ws[3] * h3.x,
+                                ws[0] * h0.y + ws[1] * h1.y + ws[2] * h2.y + ws[3] * h3.y);
+                st_stream(Hs + o, v);
+            }
+        }
+    }
+}
+
+cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl, void *Hc,
+                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    unsigned grid = (unsigned)((n_frames + PS_TILE - 1) / PS_TILE);
+    if (dt == WIFI_F32)
+        ps_interp_kernel<float><<<grid, PS_THREADS, 0, s>>>((const float2 *)tx, (const float2 *)rx, frame_stride, (float2 *)Hl,
+                                                            (float2 *)Hc, (float2 *)Hs, which, n_frames, tab.w32);
+    else
+        ps_interp_kernel<double><<<grid, PS_THREADS, 0, s>>>((const double2 *)tx, (const double2 *)rx, frame_stride,
+                                                             (double2 *)Hl, (double2 *)Hc, (double2 *)Hs, which, n_frames,
+                                                             tab.w64);
+    g_last_launches = 1;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// equalizer
+// ------------------------------------------------------------------------------------------
+constexpr int EQ_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(EQ_THREADS) equalize_kernel(const cx<T> *__restrict__ rx, const cx<T> *__restrict__ Hlt,
+                                                              const cx<T> *__restrict__ Hps, cx<T> *__restrict__ eq,
+                                                              int64_t n_fk)
+{
+    const int64_t g = (int64_t)blockIdx.x * EQ_THREADS + threadIdx.x;   // g = 53*f + k
+    if (g >= n_fk) return;
+    const int64_t f = g / NSC;
+    const int k = (int)(g - f * NSC);
+    const int64_t e0 = f * FRAME + k;                                   // element [f][0][k]
+    if (k == DCBIN) {                                                   // WiFi_Equalization.m:6-7 leaves row 27 at zero
+#pragma unroll
+        for (int b = 0; b < NBLK; ++b) st_stream(eq + e0 + b * NSC, mk<T>(0, 0));
+        return;
+    }
+    const cx<T> hl = ld_stream(Hlt + g), hpv = ld_stream(Hps + g);
+    cx<T> r[NBLK];
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) r[b] = ld_stream(rx + e0 + b * NSC);
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+        const T wl = (T)((double)(NBLK - (b + 1)) / NBLK), wp = (T)((double)(b + 1) / NBLK);   // .m:4-5, i = b+1
+        cx<T> hu = mk<T>(wl * hl.x + wp * hpv.x, wl * hl.y + wp * hpv.y);
+        st_stream(eq + e0 + b * NSC, cdiv(r[b], hu));
+    }
+}
+
+cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n_frames,
+                            cudaStream_t s)
+{
+    g_last_launches = 0;
+    const int64_t n_fk = n_frames * NSC;
+    if (n_fk == 0) return cudaSuccess;
+    unsigned grid = (unsigned)((n_fk + EQ_THREADS - 1) / EQ_THREADS);
+    if (dt == WIFI_F32)
+        equalize_kernel<float><<<grid, EQ_THREADS, 0, s>>>((const float2 *)rx, (const float2 *)Hlt, (const float2 *)Hps,
+                                                           (float2 *)eq, n_fk);
+    else
+        equalize_kernel<double><<<grid, EQ_THREADS, 0, s>>>((const double2 *)rx, (const double2 *)Hlt, (const double2 *)Hps,
+                                                            (double2 *)eq, n_fk);
+    g_last_launches = 1;
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

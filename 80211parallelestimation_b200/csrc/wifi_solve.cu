@@ -1,0 +1,244 @@
+// wifi_solve.cu -- dense complex solves that replace inverse() (utils.c:141-170, the O(n^5) un-pivoted
+// cofactor expansion) on the device:
+//   gj_solve            CTA-cooperative Gauss-Jordan with partial pivoting on [A | B] held in shared memory;
+//                       the pivot arg-max is a warp-shuffle reduction.
+//   filter_form_kernel  W = R (R + diag d)^-1 in FP64, once per batch (main.c:183-201 intent).
+//   cinverse_kernel     batched inverse, one CTA per matrix (order <= 64).
+//   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
+// The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+// Gauss-Jordan with partial pivoting on the n x ncols augmented matrix `a` (row stride ld) in shared
+// memory; on return columns n..ncols-1 hold A^-1 B.  lcol: n elements of scratch, ctl: 2 ints of scratch.
+// Every thread of the CTA must call.  Returns 1 (to all threads) if a pivot column was exactly zero.
+template <typename T>
+__device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ctl)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int singular = 0;
+    for (int k = 0; k < n; ++k) {
+        // 1. pivot search down column k (warp 0, shuffle arg-max on |a|^2)
+        if (tid < 32) {
+            T best = -1;
+            int bi = k;
+            for (int i = k + tid; i < n; i += 32) {
+                T v = cabs2(a[i * ld + k]);
+                if (v > best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                T ov = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) { ctl[0] = bi; ctl[1] = (best > (T)0) ? 0 : 1; }
+        }
+        __syncthreads();
+        const int p = ctl[0];
+        if (ctl[1]) { singular = 1; }
+        // 2. swap rows k <-> p and scale the pivot row (columns >= k)
+        const cx<T> inv = crecip(a[p * ld + k]);
+        __syncthreads();   // everyone has read the pivot before it is overwritten
+        for (int j = k + tid; j < ncols; j += nt) {
+            cx<T> top = a[k * ld + j], piv = a[p * ld + j];
+            a[k * ld + j] = cmul(piv, inv);
+            if (p != k) a[p * ld + j] = top;
+        }
+        __syncthreads();
+        // 3. multipliers
+        for (int i = tid; i < n; i += nt) lcol[i] = a[i * ld + k];
+        __syncthreads();
+        // 4. eliminate column k from every other row
+        const int w = ncols - (k + 1);
+        for (int e = tid; e < n * w; e += nt) {
+            int i = e / w, j = k + 1 + (e - i * w);
+            if (i != k) {
+                cx<T> v = a[i * ld + j];
+                cfms(v, lcol[i], a[k * ld + j]);
+                a[i * ld + j] = v;
+            }
+        }
+        __syncthreads();
+    }
+    return singular;
+}
+
+// ------------------------------------------------------------------------------------------
+// W = R (R + diag d)^-1   <=>   W^T = (R + diag d)^-T R^T : one solve with 53 right-hand sides
+// ------------------------------------------------------------------------------------------
+constexpr int FF_THREADS = 512;
+constexpr int FF_LD = 2 * NSC + 1;
+
+__global__ void __launch_bounds__(FF_THREADS) filter_form_kernel(const double2 *__restrict__ R, const double *__restrict__ d,
+                                                                 double2 *__restrict__ W, int *info)
+{
+    extern __shared__ double2 ff_smem[];
+    double2 *a = ff_smem;                 // [53][107]
+    double2 *lcol = a + NSC * FF_LD;      // [53]
+    __shared__ int ctl[2];
+    for (int e = threadIdx.x; e < NSC * NSC; e += FF_THREADS) {
+        int i = e / NSC, j = e - i * NSC;
+        double2 r = R[e];                 // R[i][j]
+        double2 at = r;
+        if (i == j) at.x += d[i];
+        a[j * FF_LD + i] = at;            // A^T
+        a[j * FF_LD + NSC + i] = r;       // R^T
+    }
+    __syncthreads();
+    int sing = gj_solve<double>(a, NSC, FF_LD, 2 * NSC, lcol, ctl);
+    for (int e = threadIdx.x; e < NSC * NSC; e += FF_THREADS) {
+        int i = e / NSC, j = e - i * NSC;
+        W[e] = a[j * FF_LD + NSC + i];    // W[i][j] = (W^T)[j][i]
+    }
+    if (threadIdx.x == 0 && info) *info = sing;
+}
+
+cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s)
+{
+    g_last_launches = 1;
+    size_t smem = sizeof(double2) * (NSC * FF_LD + NSC);
+    cudaError_t e = cudaFuncSetAttribute(filter_form_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    filter_form_kernel<<<1, FF_THREADS, smem, s>>>((const double2 *)R64, d64, (double2 *)W64, info);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// batched inverse
+// ------------------------------------------------------------------------------------------
+constexpr int INV_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
+{
+    extern __shared__ __align__(16) unsigned char inv_smem[];
+    cx<T> *a = (cx<T> *)inv_smem;
+    const int ld = 2 * n + 1;
+    cx<T> *lcol = a + n * ld;
+    __shared__ int ctl[2];
+    const cx<T> *Ab = A + (int64_t)blockIdx.x * n * n;
+    cx<T> *Yb = Y + (int64_t)blockIdx.x * n * n;
+    for (int e = threadIdx.x; e < n * n; e += INV_THREADS) {
+        int i = e / n, j = e - i * n;
+        a[i * ld + j] = Ab[e];
+        a[i * ld + n + j] = mk<T>(i == j ? (T)1 : (T)0, (T)0);
+    }
+    __syncthreads();
+    int sing = gj_solve<T>(a, n, ld, 2 * n, lcol, ctl);
+    for (int e = threadIdx.x; e < n * n; e += INV_THREADS) {
+        int i = e / n, j = e - i * n;
+        Yb[e] = a[i * ld + n + j];
+    }
+    if (threadIdx.x == 0 && info) info[blockIdx.x] = sing;
+}
+
+cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (batch == 0 || order == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const int ld = 2 * order + 1;
+    cudaError_t e;
+    if (dt == WIFI_F32) {
+        size_t smem = sizeof(float2) * ((size_t)order * ld + order);
+        e = cudaFuncSetAttribute(cinverse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cinverse_kernel<float><<<(unsigned)batch, INV_THREADS, smem, s>>>((const float2 *)A, order, (float2 *)Y, info);
+    } else {
+        size_t smem = sizeof(double2) * ((size_t)order * ld + order);
+        e = cudaFuncSetAttribute(cinverse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cinverse_kernel<double><<<(unsigned)batch, INV_THREADS, smem, s>>>((const double2 *)A, order, (double2 *)Y, info);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per-frame MMSE, general pivoted path: one CTA per frame
+//   A = R + diag(sigma2/|tx_k|^2),  y = rx/tx,  A z = y,  H = R z
+// R is shared (R != NULL) or the per-frame rank-1 H_ls H_ls^H of the C calling convention (main.c:186-189)
+// ------------------------------------------------------------------------------------------
+constexpr int PV_THREADS = 128;
+constexpr int PV_LD = NSC + 2;
+
+template <typename T>
+__global__ void __launch_bounds__(PV_THREADS) mmse_pivot_kernel(const cx<T> *__restrict__ R, const cx<T> *__restrict__ tx,
+                                                                const cx<T> *__restrict__ rx, int64_t frame_stride,
+                                                                const T *__restrict__ sigma2, const cx<T> *__restrict__ hls,
+                                                                cx<T> *__restrict__ H, int *info)
+{
+    extern __shared__ __align__(16) unsigned char pv_smem[];
+    cx<T> *a = (cx<T> *)pv_smem;          // [53][55]: A | y
+    cx<T> *lcol = a + NSC * PV_LD;        // [53]
+    cx<T> *hv = lcol + NSC;               // [53] H_ls of this frame (rank-1 mode)
+    __shared__ int ctl[2];
+    const int64_t f = blockIdx.x;
+    const cx<T> *txf = tx + f * frame_stride, *rxf = rx + f * frame_stride;
+    const T s2 = sigma2[f];
+    if (hls) {
+        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) hv[i] = hls[f * NSC + i];
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < NSC * NSC; e += PV_THREADS) {
+        int i = e / NSC, j = e - i * NSC;
+        cx<T> r = hls ? cmul(hv[i], cconj(hv[j])) : R[e];
+        if (i == j) r.x += s2 / cabs2(txf[i]);
+        a[i * PV_LD + j] = r;
+    }
+    for (int i = threadIdx.x; i < NSC; i += PV_THREADS) a[i * PV_LD + NSC] = cdiv(rxf[i], txf[i]);
+    __syncthreads();
+    int sing = gj_solve<T>(a, NSC, PV_LD, NSC + 1, lcol, ctl);
+    // z is column 53; H = R z
+    if (hls) {
+        // R z = h (h^H z)
+        if (threadIdx.x < 32) {
+            cx<T> acc = mk<T>(0, 0);
+            for (int j = threadIdx.x; j < NSC; j += 32) cfma(acc, cconj(hv[j]), a[j * PV_LD + NSC]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            }
+            if (threadIdx.x == 0) lcol[0] = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) H[f * NSC + i] = cmul(hv[i], lcol[0]);
+    } else {
+        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) {
+            cx<T> acc = mk<T>(0, 0);
+            for (int j = 0; j < NSC; ++j) cfma(acc, R[i * NSC + j], a[j * PV_LD + NSC]);
+            H[f * NSC + i] = acc;
+        }
+    }
+    if (threadIdx.x == 0 && info && sing) atomicExch(info, 1);
+}
+
+cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info,
+                                       cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    if (dt == WIFI_F32) {
+        size_t smem = sizeof(float2) * (NSC * PV_LD + 2 * NSC);
+        mmse_pivot_kernel<float><<<(unsigned)n_frames, PV_THREADS, smem, s>>>((const float2 *)R, (const float2 *)tx,
+                                                                             (const float2 *)rx, frame_stride,
+                                                                             (const float *)sigma2, (const float2 *)Hls_for_R,
+                                                                             (float2 *)H, info);
+    } else {
+        size_t smem = sizeof(double2) * (NSC * PV_LD + 2 * NSC);
+        cudaError_t e = cudaFuncSetAttribute(mmse_pivot_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mmse_pivot_kernel<double><<<(unsigned)n_frames, PV_THREADS, smem, s>>>((const double2 *)R, (const double2 *)tx,
+                                                                               (const double2 *)rx, frame_stride,
+                                                                               (const double *)sigma2, (const double2 *)Hls_for_R,
+                                                                               (double2 *)H, info);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

@@ -1,0 +1,176 @@
+/*
+ * wifi_b200.h -- C-ABI of the B200-native 802.11 channel-estimation hot path.
+ *
+ * Drop-in boundary for the hot path of usmandroid/80211ParallelEstimation: the five
+ * estimators of main.c (prototypes main.c:4-8, bodies main.c:66-212), the complex matrix
+ * routines of utils.c (prototypes utils.h:38-60) and the MATLAB equalizer
+ * (WiFi_Equalization.m:1-9).  Plain pointers and sizes only; every batched entry point
+ * returns a wifi_status.  There is NO CPU fallback: without a CUDA device wifi_create()
+ * fails with WIFI_ERR_NO_DEVICE and nothing else can be called.
+ *
+ * Layouts (kept from the reference, inputs.h:20,75,130,928 and utils.h:10-19):
+ *   - a complex element is interleaved (re, im): float2 (WIFI_F32) or double2 (WIFI_F64);
+ *   - a block vector is 53 consecutive elements, sub-carrier k at [k]; DC bin = 26,
+ *     pilots at 5, 19, 33, 47;
+ *   - a whole frame is 15 block vectors: element [53*b + k] (inputs.h tx_symb/rx_symb);
+ *   - a batch is n_frames consecutive block vectors / frames; `frame_stride` (in complex
+ *     elements) lets the pilot estimators read block b of whole frames in place
+ *     (pass ptr + 53*b and frame_stride = 795) or stacked block vectors (stride 53);
+ *   - matrices are dense row-major (what the reference's row-pointer tables point into,
+ *     utils.c:817-835), batches are consecutive matrices.
+ *
+ * Pointers named *_dev / unqualified in the `_batch` functions are DEVICE pointers on the
+ * context's GPU; the `_host` functions take HOST pointers (pinned or pageable) and run the
+ * H2D copy, the kernels and the D2H copy themselves.
+ */
+#ifndef WIFI_B200_H
+#define WIFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WIFI_NSC 53        /* SAMPUTIL, utils.h:13 */
+#define WIFI_NBLK 15       /* OFDMBLK,  utils.h:15 */
+#define WIFI_FRAME (WIFI_NSC * WIFI_NBLK) /* SIZESYMBOL, utils.h:12 */
+#define WIFI_DC 26
+#define WIFI_P0 5          /* utils.h:16-19 */
+#define WIFI_P1 19
+#define WIFI_P2 33
+#define WIFI_P3 47
+#define WIFI_MAX_ORDER 64  /* largest matrix order of the batched utils */
+
+typedef enum { WIFI_F32 = 0, WIFI_F64 = 1 } wifi_dtype;
+
+typedef enum {
+    WIFI_OK = 0,
+    WIFI_ERR_INVALID = 1,   /* bad argument / "Matrices dimension missmatch" (utils.c:18-19): nothing is written */
+    WIFI_ERR_CUDA = 2,      /* a CUDA call failed; see wifi_last_error() */
+    WIFI_ERR_NOMEM = 3,
+    WIFI_ERR_SINGULAR = 4,  /* a pivot was exactly zero (the reference silently yields NaN/Inf, utils.c:543-569) */
+    WIFI_ERR_NO_DEVICE = 5,
+    WIFI_ERR_STATE = 6      /* e.g. shared-filter apply before wifi_mmse_filter_* */
+} wifi_status;
+
+/* which-estimator bit mask for wifi_ps_batch */
+#define WIFI_PS_LINEAR 1
+#define WIFI_PS_CUBIC 2
+#define WIFI_PS_SINC 4
+
+/* flags of wifi_mmse_perframe_batch */
+#define WIFI_SOLVE_PIVOT 0      /* partial-pivoting Gauss-Jordan (any non-singular R + D) */
+#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted elimination (growth factor 1) */
+#define WIFI_SOLVE_REFINE 2     /* FP32 only: one step of iterative refinement with an FP64 residual */
+
+/* wifi_chermitian_batch / wifi_cadd_batch semantics */
+#define WIFI_AS_WRITTEN 0       /* bit-compatible with utils.c:3-7 (Re-Im, real-valued) / utils.c:111-121 (M1+M1) */
+#define WIFI_INTENDED 1         /* true conjugate transpose / M1+M2 */
+
+typedef struct wifi_ctx wifi_ctx;   /* opaque; one per GPU; calls on one ctx must not race */
+
+/* ---- context ------------------------------------------------------------------- */
+int wifi_create(int device, wifi_ctx **out);
+int wifi_destroy(wifi_ctx *ctx);
+int wifi_set_stream(wifi_ctx *ctx, void *cuda_stream);      /* cudaStream_t; NULL = default stream */
+int wifi_synchronize(wifi_ctx *ctx);
+const char *wifi_last_error(wifi_ctx *ctx);
+const char *wifi_version(void);
+/* kernels launched through this ctx since creation (bench.py's gpu_launches) */
+int64_t wifi_launch_count(wifi_ctx *ctx);
+/* elapsed device time in ms of the LAST kernel launched with timing enabled (CUDA events on the ctx stream) */
+int wifi_enable_kernel_timing(wifi_ctx *ctx, int on);
+int wifi_last_kernel_ms(wifi_ctx *ctx, float *ms);
+
+/* ---- LS / interpolation estimators (HBM-bound) ---------------------------------- */
+/* main.c:66-75  WiFi_channel_estimation_LT_LS over n_frames preambles [n][53] -> H [n][53] */
+int wifi_lt_ls_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n_frames);
+/* main.c:77-146 PS_Linear / PS_Cubic / PS_Sinc fused: one pilot-LS pass feeds every requested
+ * interpolator.  Outputs [n][53]; pointers of estimators not in `which` are ignored. */
+int wifi_ps_batch(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbols, const void *rx_symbols,
+                  int64_t frame_stride, void *H_linear, void *H_cubic, void *H_sinc, int64_t n_frames);
+/* WiFi_Equalization.m:1-9: rx [n][15][53], H_lt/H_ps [n][53] -> eq [n][15][53] */
+int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
+                        void *eq, int64_t n_frames);
+
+/* ---- PS_MMSE, intended formula  H = R (R + s2 (X X^H)^-1)^-1 (rx/tx) ------------- */
+/* Shared-filter case.  Form W = R (R + diag(d))^-1 once in FP64 on the device
+ * (R: 53x53 double2 row-major, d: 53 doubles = s2/|x_k|^2, W_out: optional 53x53 double2)
+ * and install it in the context as the operand of wifi_mmse_shared_*. */
+int wifi_mmse_filter_form(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);
+/* install an externally formed filter (53x53 double2, device) */
+int wifi_mmse_filter_set(wifi_ctx *ctx, const void *W_f64);
+/* H[n][53] = H_ls[n][53] W^T   (multiply utils.c:16-31 over all frames as one GEMM) */
+int wifi_mmse_shared_apply_batch(wifi_ctx *ctx, wifi_dtype dt, const void *H_ls, void *H, int64_t n_frames);
+/* fused: per-block LS divide rx/tx (main.c:83 arithmetic on all 53 bins) + the GEMM */
+int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                           int64_t frame_stride, void *H, int64_t n_frames);
+/* Per-frame case: A_f = R + diag(sigma2[f]/|tx_k|^2); solve A_f z = rx/tx; H = R z.
+ * R in the compute dtype (53x53), sigma2 real [n] in the compute dtype. */
+int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols,
+                             const void *rx_symbols, int64_t frame_stride, const void *sigma2, void *H,
+                             int64_t n_frames, int flags);
+/* C calling convention of main.c:148 batched: R_f = H_ls,f H_ls,f^H (main.c:186-189 intent),
+ * tx/rx block vectors [n][53], ow2 [n] real, H_ls [n][53] -> H [n][53] */
+int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                          const void *ow2, const void *H_ls, void *H, int64_t n_frames);
+
+/* ---- batched complex matrix utils (utils.h:38-60), order <= WIFI_MAX_ORDER --------- */
+/* multiply utils.c:16-31: C[b] = A[b] (r1 x c1) * B[b] (r2 x c2); c1 != r2 -> WIFI_ERR_INVALID, nothing written */
+int wifi_cmatmul_batch(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2,
+                       void *C, int64_t batch);
+/* hermitian utils.c:3-7 (mode WIFI_AS_WRITTEN: res[c][r] = Re - Im) or conjugate transpose (WIFI_INTENDED) */
+int wifi_chermitian_batch(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch);
+/* addition utils.c:111-121 (WIFI_AS_WRITTEN: M1+M1) or M1+M2 (WIFI_INTENDED) */
+int wifi_cadd_batch(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r1, int c1, const void *M2, int r2, int c2,
+                    void *res, int64_t batch);
+/* multiplyVxVeqM utils.c:55-65: res[r][c] = M1[r][0] * M2[0][c] */
+int wifi_couter_batch(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int r2, int c2,
+                      void *res, int64_t batch);
+/* identity utils.c:84-93 */
+int wifi_cidentity_batch(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch);
+/* inverse utils.c:141-170 replaced by partial-pivoting Gauss-Jordan; info[b] (device int, may be NULL) = 1 if singular */
+int wifi_cinverse_batch(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info);
+
+/* ---- synthetic frames of the inputs.h shape, generated on the device ---- */
+/* per_frame_sigma: 0 -> sigma2 = 9.6172e-08 for every frame, 1 -> log-uniform [1e-8, 1e-5].
+ * Any output pointer may be NULL.  tx_pre/rx_pre/H_true [n][53], tx_symb/rx_symb [n][15][53], sigma2 [n] real. */
+int wifi_synth_frames(wifi_ctx *ctx, wifi_dtype dt, uint64_t seed, int64_t first_frame, int64_t n_frames, int per_frame_sigma,
+                      void *tx_pre, void *rx_pre, void *tx_symb, void *rx_symb, void *H_true, void *sigma2);
+/* theoretical channel covariance of the generator: 53x53 double2 (device) */
+int wifi_synth_covariance(wifi_ctx *ctx, void *R_f64);
+/* per-shard error statistics, stats[4] (device doubles): sum|H-Href|^2, sum|Href|^2, count, max|H-Href| */
+int wifi_error_stats(wifi_ctx *ctx, wifi_dtype dt, const void *H, const void *H_ref, int64_t n_elems, double *stats);
+
+/* ---- host-pointer variants: H2D + kernels + D2H inside, chunked and double-buffered ---- */
+int wifi_lt_ls_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n_frames);
+int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbols, const void *rx_symbols,
+                 int64_t frame_stride, void *H_linear, void *H_cubic, void *H_sinc, int64_t n_frames);
+int wifi_equalize_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
+                       void *eq, int64_t n_frames);
+int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);
+int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                          int64_t frame_stride, void *H, int64_t n_frames);
+int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols, const void *rx_symbols,
+                            int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames, int flags);
+int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                         const void *ow2, const void *H_ls, void *H, int64_t n_frames);
+int wifi_cmatmul_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch);
+int wifi_chermitian_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch);
+int wifi_cadd_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch);
+int wifi_couter_host(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch);
+int wifi_cidentity_host(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch);
+int wifi_cinverse_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info_host);
+/* pinned host memory for the `_host` calls (cudaHostAlloc / cudaFreeHost) */
+int wifi_host_alloc(void **p, size_t bytes);
+int wifi_host_free(void *p);
+
+/* ---- process-global default context used by the single-frame drop-ins (wifi_dropin.h) ---- */
+wifi_ctx *wifi_default_ctx(void);   /* created on first use on device $WIFI_B200_DEVICE (default 0); aborts loudly if no GPU */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WIFI_B200_H */

@@ -1,0 +1,323 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): every call goes through the C-ABI of libwifi_b200.so and is
+compared with the CPU oracle (oracle/wifi_oracle.c) on the same inputs and with the committed golden vectors
+produced by the reference's own code (tests/golden/).
+
+Tolerances (north star): FP64 mode <= 1e-10, FP32 mode <= 1e-4, relative per sub-carrier with the survey's floor
+|d| / max(|ref_k|, 1e-3 max_k|ref|)  (synth.rel_err).  FP32 inputs are rounded to FP32 BEFORE the oracle sees them,
+so both sides work on the same numbers.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import synth
+from synth import rel_err
+
+pytestmark = pytest.mark.gpu
+
+NSC, NBLK = 53, 15
+TOL = {"f64": 1e-10, "f32": 1e-4}
+CDT = {"f64": np.complex128, "f32": np.complex64}
+
+
+@pytest.fixture(scope="module")
+def wifi():
+    return importlib.import_module("80211parallelestimation_b200")
+
+
+@pytest.fixture(scope="module")
+def ctx(wifi):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return wifi.WifiContext(0)
+
+
+def dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def r32(x, prec):
+    """round to the precision under test, return as complex128 for the oracle"""
+    return np.asarray(x).astype(CDT[prec]).astype(np.complex128)
+
+
+# ------------------------------------------------------------------ LT_LS
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lt_ls_inputs_h_and_golden(ctx, oracle, gold, prec):
+    g, r = gold["inputs_h"], gold["ref_c_outputs"]
+    tx, rx = g["tx_preamble_fft"].astype(CDT[prec]), g["rx_preamble_fft"].astype(CDT[prec])
+    got = host(ctx.lt_ls(dev(tx), dev(rx)))
+    assert rel_err(got, oracle.lt_ls(r32(tx, prec), r32(rx, prec))) < TOL[prec]
+    if prec == "f64":
+        assert rel_err(got, r["lt_ls"]) < TOL[prec]          # the reference's own output
+    assert got[26] == 0
+    tx, rx = r["syn_tx_pre"].astype(CDT[prec]), r["syn_rx_pre"].astype(CDT[prec])
+    got = host(ctx.lt_ls(dev(tx), dev(rx)))
+    assert rel_err(got, oracle.lt_ls(r32(tx, prec), r32(rx, prec))) < TOL[prec]
+    if prec == "f64":
+        assert rel_err(got, r["syn_lt_ls"]) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 19, 1024, 4097])
+def test_lt_ls_ragged(ctx, oracle, prec, n):
+    fr = synth.make_frames(max(n, 1), seed=n + 1)
+    tx, rx = fr["tx_pre"][:n].astype(CDT[prec]), fr["rx_pre"][:n].astype(CDT[prec])
+    got = host(ctx.lt_ls(dev(tx), dev(rx)))
+    assert got.shape == (n, NSC)
+    if n:
+        assert rel_err(got, oracle.lt_ls(r32(tx, prec), r32(rx, prec))) < TOL[prec]
+
+
+def test_lt_ls_nan_bug_compat(ctx, gold):
+    r, g = gold["ref_c_outputs"], gold["inputs_h"]
+    got = host(ctx.lt_ls(dev(r["nan_tx_pre"]), dev(g["rx_preamble_fft"])))
+    assert np.isnan(got[3]) and np.isnan(r["nan_lt_ls"][3])       # Re(tx) == Im(tx): main.c:69-72 yields 0/0
+    assert rel_err(got, r["nan_lt_ls"]) < 1e-10
+
+
+# ------------------------------------------------------------------ PS estimators
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_ps_inputs_h(ctx, oracle, gold, prec):
+    g, r = gold["inputs_h"], gold["ref_c_outputs"]
+    tx = g["tx_symb"].reshape(NBLK, NSC).astype(CDT[prec]); rx = g["rx_symb"].reshape(NBLK, NSC).astype(CDT[prec])
+    out = ctx.ps(dev(tx), dev(rx))                      # every OFDM block as its own "frame"
+    for name in ("linear", "cubic", "sinc"):
+        got = host(out[name])
+        assert rel_err(got, getattr(oracle, "ps_" + name)(r32(tx, prec), r32(rx, prec))) < TOL[prec], name
+        if prec == "f64":
+            assert rel_err(got, r["ps_%s_blocks" % name]) < TOL[prec], name
+    # whole frame in place, block 0 (main.c:30-33): frame_stride 795
+    out = ctx.ps(dev(tx.reshape(1, NBLK, NSC)), dev(rx.reshape(1, NBLK, NSC)))
+    if prec == "f64":
+        assert rel_err(host(out["cubic"])[0], r["ps_cubic_blocks"][0]) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [0, 1, 5, 47, 48, 49, 1000])
+def test_ps_ragged_and_strided(ctx, oracle, prec, n):
+    fr = synth.make_frames(max(n, 1), seed=100 + n)
+    tx, rx = fr["tx_symb"][:n].astype(CDT[prec]), fr["rx_symb"][:n].astype(CDT[prec])
+    out = ctx.ps(dev(tx), dev(rx))                      # [n][15][53] -> stride 795
+    for name in ("linear", "cubic", "sinc"):
+        assert out[name].shape == (n, NSC)
+        if n:
+            ref = getattr(oracle, "ps_" + name)(r32(tx[:, 0, :], prec), r32(rx[:, 0, :], prec))
+            assert rel_err(host(out[name]), ref) < TOL[prec], name
+    if n:   # a single estimator, another block, via pointer offset semantics: pass block 3 vectors stacked
+        got = host(ctx.ps_sinc(dev(tx[:, 3, :].copy()), dev(rx[:, 3, :].copy())))
+        assert rel_err(got, oracle.ps_sinc(r32(tx[:, 3, :], prec), r32(rx[:, 3, :], prec))) < TOL[prec]
+
+
+def test_ps_golden_synthetic_reference(ctx, gold):
+    r = gold["ref_c_outputs"]
+    out = ctx.ps(dev(r["syn_tx_blk0"]), dev(r["syn_rx_blk0"]))
+    for name in ("linear", "cubic", "sinc"):
+        assert rel_err(host(out[name]), r["syn_ps_" + name]) < 1e-10, name
+
+
+# ------------------------------------------------------------------ equalizer
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_equalize(ctx, oracle, gold, prec):
+    m = gold["matlab_mat"]
+    rx = m["rx_symb"].T.reshape(1, NBLK, NSC).astype(CDT[prec])
+    hl, hp = m["H_EST_LT_LS"].ravel().astype(CDT[prec]), m["H_EST_PS_Linear"].ravel().astype(CDT[prec])
+    got = host(ctx.equalize(dev(rx), dev(hl.reshape(1, NSC)), dev(hp.reshape(1, NSC))))
+    assert rel_err(got, oracle.equalize(r32(rx, prec), r32(hl, prec), r32(hp, prec)), floor=1e-6) < TOL[prec]
+    if prec == "f64":
+        assert rel_err(got[0], m["eq_symbols"].T, floor=1e-6) < TOL[prec]     # MATLAB golden
+    assert np.all(got[0][:, 26] == 0)
+    for n in (2, 37):
+        fr = synth.make_frames(n, seed=n)
+        rxs = fr["rx_symb"].astype(CDT[prec])
+        a = oracle.lt_ls(fr["tx_pre"], fr["rx_pre"]).astype(CDT[prec])
+        b = oracle.ps_linear(fr["tx_symb"][:, 0, :], fr["rx_symb"][:, 0, :]).astype(CDT[prec])
+        a[:, 26] = 1.0      # the DC value of H is never used (eq[26] = 0) but must not produce NaN/garbage
+        got = host(ctx.equalize(dev(rxs), dev(a), dev(b)))
+        assert rel_err(got, oracle.equalize(r32(rxs, prec), r32(a, prec), r32(b, prec)), floor=1e-6) < TOL[prec]
+
+
+# ------------------------------------------------------------------ MMSE, shared filter
+def test_mmse_filter_form(ctx, oracle):
+    R = synth.channel_covariance()
+    d = np.full(NSC, synth.OW2 / synth.AMP ** 2); d[26] = synth.OW2 / 1e-8
+    W = host(ctx.mmse_filter_form(dev(R), dev(d)))
+    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-9
+    rng = np.random.default_rng(3)
+    Rg = synth.random_hpd(rng)
+    W = host(ctx.mmse_filter_form(dev(Rg), dev(d)))
+    assert rel_err(W, oracle.mmse_filter(Rg, d), floor=1e-3) < 1e-10
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 777])
+def test_mmse_shared(ctx, oracle, prec, n):
+    fr = synth.make_frames(n, seed=n)
+    tx, rx = fr["tx_symb"][:, 0, :].astype(CDT[prec]), fr["rx_symb"][:, 0, :].astype(CDT[prec])
+    R = synth.channel_covariance()
+    d = synth.OW2 / np.abs(fr["tx_symb"][0, 0, :]) ** 2
+    W = host(ctx.mmse_filter_form(dev(R), dev(d)))
+    hls = (r32(rx, prec) / r32(tx, prec))
+    ref = oracle.mmse_apply(W, hls)
+    got = host(ctx.mmse_shared(dev(tx), dev(rx)))
+    assert rel_err(got, ref) < TOL[prec]
+    got2 = host(ctx.mmse_shared_apply(dev(hls.astype(CDT[prec]))))
+    assert rel_err(got2, oracle.mmse_apply(W, r32(hls.astype(CDT[prec]), prec))) < TOL[prec]
+    # the shared filter reproduces the per-frame formula when sigma2 and |x|^2 are shared
+    if prec == "f64":
+        assert rel_err(got, oracle.mmse_perframe(R, tx, rx, synth.OW2)) < 1e-9
+
+
+def test_mmse_shared_needs_filter(wifi):
+    c = wifi.WifiContext(0)
+    with pytest.raises(wifi.WifiError):
+        c.mmse_shared_apply(dev(np.zeros((4, NSC), np.complex64)))
+    c.close()
+
+
+# ------------------------------------------------------------------ MMSE, per frame
+@pytest.mark.parametrize("flags", ["pivot", "hpd"])
+@pytest.mark.parametrize("n", [1, 3, 8, 61])
+def test_mmse_perframe_f64(ctx, wifi, oracle, flags, n):
+    fr = synth.make_frames(n, seed=10 + n, sigma2="perframe")
+    tx, rx, s2 = fr["tx_symb"][:, 0, :], fr["rx_symb"][:, 0, :], fr["sigma2"]
+    for R in (synth.channel_covariance(), synth.random_hpd(np.random.default_rng(n))):
+        ref = oracle.mmse_perframe(R, tx, rx, s2)
+        fl = wifi.SOLVE_PIVOT if flags == "pivot" else wifi.SOLVE_HPD
+        got = host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2), flags=fl))
+        assert rel_err(got, ref) < 1e-10
+
+
+def test_mmse_perframe_kat(ctx, wifi, gold):
+    k = gold["mmse_kat"]
+    for fl in (wifi.SOLVE_PIVOT, wifi.SOLVE_HPD):
+        got = host(ctx.mmse_perframe(dev(k["gen_R"]), dev(k["gen_tx"]), dev(k["gen_rx"]), dev(k["gen_sigma2"]), flags=fl))
+        assert rel_err(got, k["gen_H"]) < 1e-10              # 40-digit mpmath
+
+
+def test_mmse_cconv_inputs_h(ctx, gold):
+    g, r, k = gold["inputs_h"], gold["ref_c_outputs"], gold["mmse_kat"]
+    tx0, rx0 = g["tx_symb"][:53].reshape(1, NSC), g["rx_symb"][:53].reshape(1, NSC)
+    got = host(ctx.mmse_cconv(dev(tx0), dev(rx0), float(g["ow2"]), dev(r["lt_ls"].reshape(1, NSC))))
+    assert rel_err(got[0], k["inputs_h_full"]) < 1e-10      # mpmath known answer
+    assert got[0][26] == 0
+
+
+@pytest.mark.parametrize("flags", ["pivot", "hpd"])
+def test_mmse_perframe_f32_stated_accuracy(ctx, wifi, oracle, flags):
+    """FP32 elimination of R + D loses the sigma2/|x|^2 diagonal against R at high SNR (DESIGN.md 'FP32 per-frame'):
+    the stated bound for the plain FP32 solve is 5e-2 over sigma2 in [1e-8, 1e-5]."""
+    fr = synth.make_frames(32, seed=77, sigma2="perframe", dtype=np.complex64)
+    tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
+    s2 = fr["sigma2"].astype(np.float32)
+    R = synth.channel_covariance().astype(np.complex64)
+    ref = oracle.mmse_perframe(R.astype(np.complex128), tx.astype(np.complex128), rx.astype(np.complex128), s2.astype(np.float64))
+    fl = wifi.SOLVE_PIVOT if flags == "pivot" else wifi.SOLVE_HPD
+    got = host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2), flags=fl))
+    assert rel_err(got, ref) < 5e-2
+
+
+# ------------------------------------------------------------------ utils.h
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_utils_vs_reference(ctx, wifi, gold, prec):
+    u = gold["ref_utils"]
+    tol = TOL[prec] if prec == "f64" else 2e-5
+    c = lambda k: u[k].astype(CDT[prec])
+    assert rel_err(host(ctx.multiply(dev(c("A53")), dev(c("B53")))), u["mul_53x53"]) < tol
+    assert rel_err(host(ctx.multiply(dev(c("A53")), dev(c("v53")))), u["mul_53x1"]) < tol
+    assert rel_err(host(ctx.multiply(dev(c("A7x5")), dev(c("B5x3")))), u["mul_7x5x3"]) < tol
+    with pytest.raises(wifi.WifiError, match="missmatch"):
+        ctx.multiply(dev(c("A7x5")), dev(c("A7x5")))
+    assert rel_err(host(ctx.hermitian(dev(c("A53")))), u["herm_53"]) < tol            # as written: Re - Im
+    assert rel_err(host(ctx.hermitian(dev(c("A7x5")))), u["herm_7x5"]) < tol
+    assert np.array_equal(host(ctx.hermitian(dev(c("A7x5")), wifi.INTENDED)), c("A7x5").conj().T)
+    assert rel_err(host(ctx.multiplyVxVeqM(dev(c("A53")), dev(c("B53")))), u["outer_53"]) < tol
+    assert rel_err(host(ctx.addition(dev(c("A53")), dev(c("B53")))), u["add_53"]) < tol  # as written: M1 + M1
+    assert np.array_equal(host(ctx.addition(dev(c("A53")), dev(c("B53")), wifi.INTENDED)), c("A53") + c("B53"))
+    idn = host(ctx.identity(53, 9.6172e-08, like=dev(c("A53"))))
+    assert rel_err(idn, u["ident_53"]) < tol
+    for n in (2, 3, 6, 10):
+        assert rel_err(host(ctx.inverse(dev(c("inv_in_%d" % n)))), u["inv_out_%d" % n]) < (1e-10 if prec == "f64" else 1e-4)
+
+
+def test_inverse_53(ctx, wifi, gold, oracle):
+    u = gold["ref_utils"]
+    a = u["inv_in_53pd"]
+    y = host(ctx.inverse(dev(a)))
+    assert np.abs(y @ a - np.eye(53)).max() < 1e-8
+    assert rel_err(y, oracle.inverse_gj(a), floor=1e-2) < 1e-8
+    # F = 53-point DFT (main.c:22-26): inverse(F) == conj(F)/53 analytically
+    t = np.arange(53)
+    F = np.exp(-2j * np.pi * np.outer(t, t) / 53)
+    assert rel_err(host(ctx.inverse(dev(F))), F.conj() / 53) < 1e-12
+    # batch + singular detection
+    batch = np.stack([F, np.zeros((53, 53), complex)])
+    with pytest.raises(wifi.WifiError):
+        ctx.inverse(dev(batch))
+
+
+# ------------------------------------------------------------------ host-pointer entry points (numpy in, numpy out)
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_host_entry_points(ctx, wifi, oracle, prec):
+    n = 333
+    fr = synth.make_frames(n, seed=9, sigma2="perframe")
+    txp, rxp = fr["tx_pre"].astype(CDT[prec]), fr["rx_pre"].astype(CDT[prec])
+    txs, rxs = fr["tx_symb"].astype(CDT[prec]), fr["rx_symb"].astype(CDT[prec])
+    lt = ctx.lt_ls(txp, rxp)
+    assert isinstance(lt, np.ndarray) and rel_err(lt, oracle.lt_ls(r32(txp, prec), r32(rxp, prec))) < TOL[prec]
+    out = ctx.ps(txs, rxs)                                                 # strided host frames (795)
+    assert rel_err(out["cubic"], oracle.ps_cubic(r32(txs[:, 0, :], prec), r32(rxs[:, 0, :], prec))) < TOL[prec]
+    eq = ctx.equalize(rxs, lt, out["linear"])
+    lt2 = lt.copy(); lt2[:, 26] = 1
+    assert rel_err(eq, oracle.equalize(r32(rxs, prec), r32(lt, prec), r32(out["linear"], prec)), floor=1e-6) < TOL[prec]
+    R = synth.channel_covariance()
+    d = synth.OW2 / np.abs(fr["tx_symb"][0, 0, :]) ** 2
+    W = ctx.mmse_filter_form(R, d)
+    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-9
+    H = ctx.mmse_shared(txs[:, 0, :].copy(), rxs[:, 0, :].copy())
+    assert rel_err(H, oracle.mmse_apply(W, r32(rxs[:, 0, :], prec) / r32(txs[:, 0, :], prec))) < TOL[prec]
+    if prec == "f64":
+        Hp = ctx.mmse_perframe(R, txs[:, 0, :].copy(), rxs[:, 0, :].copy(), fr["sigma2"])
+        assert rel_err(Hp, oracle.mmse_perframe(R, txs[:, 0, :], rxs[:, 0, :], fr["sigma2"])) < 1e-10
+        a = np.random.default_rng(0).standard_normal((4, 9, 9)) + 1j * np.eye(9)
+        assert np.abs(ctx.inverse(a) @ a - np.eye(9)).max() < 1e-12
+        assert np.allclose(ctx.multiply(a, a), a @ a)
+
+
+def test_reference_named_wrappers(wifi, gold):
+    g, r = gold["inputs_h"], gold["ref_c_outputs"]
+    H = wifi.WiFi_channel_estimation_LT_LS(g["tx_preamble_fft"], g["rx_preamble_fft"])
+    assert rel_err(H, r["lt_ls"]) < 1e-10
+    tx0, rx0 = g["tx_symb"][:53], g["rx_symb"][:53]
+    assert rel_err(wifi.WiFi_channel_estimation_PS_Linear(tx0, rx0), r["ps_linear_blocks"][0]) < 1e-10
+    assert rel_err(wifi.WiFi_channel_estimation_PS_Cubic(tx0, rx0), r["ps_cubic_blocks"][0]) < 1e-10
+    assert rel_err(wifi.WiFi_channel_estimation_PS_Sinc(tx0, rx0), r["ps_sinc_blocks"][0]) < 1e-10
+    Hm = wifi.WiFi_channel_estimation_PS_MMSE(tx0, rx0, None, float(g["ow2"]), r["lt_ls"])
+    assert rel_err(Hm, gold["mmse_kat"]["inputs_h_full"]) < 1e-10
+
+
+# ------------------------------------------------------------------ on-device generator + statistics
+def test_synth_and_stats(ctx):
+    import torch
+    fr = ctx.synth_frames(4096, "f64", per_frame_sigma=True)
+    tx, rx, Ht, s2 = (host(fr[k]) for k in ("tx_symb", "rx_symb", "H_true", "sigma2"))
+    assert np.all(np.abs(np.abs(tx[:, :, np.arange(53) != 26]) - 8.875) < 1e-12) and np.all(tx[:, :, 26] == -1e-4)
+    assert np.all((s2 >= 1e-8) & (s2 <= 1e-5))
+    noise = rx - Ht[:, None, :] * tx
+    est = (np.abs(noise) ** 2).mean(axis=(1, 2))
+    assert np.abs(np.log(est / s2)).mean() < 0.05                     # noise power matches sigma2 per frame
+    R = host(ctx.synth_covariance())
+    emp = (Ht[:, :, None] * Ht[:, None, :].conj()).mean(axis=0)
+    assert np.abs(emp - R).max() < 0.1 * np.abs(R).max()
+    assert np.abs(R - synth.channel_covariance()).max() < 1e-18
+    # same frames from a different shard origin
+    fr2 = ctx.synth_frames(100, "f64", first_frame=1000, per_frame_sigma=True)
+    assert np.array_equal(host(fr2["rx_pre"]), host(fr["rx_pre"])[1000:1100])
+    st = host(ctx.error_stats(fr["H_true"], fr["H_true"] * 1.001))
+    assert abs(st[0] / st[1] - 1e-6 / 1.001 ** 2) < 1e-9 and st[2] == 4096 * 53
