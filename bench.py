@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the 802.11 channel-estimation hot path on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                # our arm (sm_100a kernels through the C-ABI)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference's own CPU code on the host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU, frame-sharded, no collective
+
+Headline workload (config.workload): BASELINE.json configs[2] -- shared-filter PS_MMSE over 1 Mi synthetic frames of the
+inputs.h shape per GPU, FP32 I/O: one step = one pass  H[n][53] = (rx/tx)[n][53] W^T  over every local frame (LS divide
+fused into the GEMM kernel).  `value` = frames all ranks processed / max-over-ranks device time (inputs resident in HBM);
+`e2e` = the same call with HOST buffers (pinned), H2D and D2H inside the timed region.  Inputs (1.27 GB per pass) are
+10x larger than L2, so no flush is needed between iterations.  `extras` carries the secondary kernels (LT_LS, fused
+PS_Linear/Cubic/Sinc, equalizer, per-frame solves), each with its own roofline fraction.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+NSC, NBLK = 53, 15
+METRIC = "MMSE channel estimates/sec (53-subcarrier frames)"
+UNIT = "frames/s"
+OW2 = 9.6172e-08
+AMP = 8.875
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def time_steps(fn, steps, warmup, torch, dist=None):
+    """W untimed + K timed steps; device time from CUDA events per step; returns (total_ms, per_step_ms list)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), per
+
+
+def pinned(wifi, shape, dtype):
+    lib = wifi._lib.load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    if lib.wifi_host_alloc(ctypes.byref(p), n) != 0:
+        raise MemoryError("wifi_host_alloc(%d)" % n)
+    buf = (ctypes.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def cpu_reference_rate(sample_frames, seconds_target=12.0):
+    """The reference's own routines (oracle/_ref: multiply utils.c:16-31 + the LS divide), frame-parallel over all host
+    threads, on a bounded sample of the same workload.  Falls back to the oracle port when _ref is not built."""
+    import synth
+    from oracle.pyoracle import Oracle, Reference
+    o = Oracle()
+    cores = os.cpu_count() or 1
+    R = synth.channel_covariance()
+    d = np.full(NSC, OW2 / AMP ** 2); d[26] = OW2 / 1e-8
+    W = o.mmse_filter(R, d)
+    fr = synth.make_frames(4096, seed=5)
+    tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
+    if Reference.available():
+        ref = Reference()
+        run = lambda t, r: ref.mmse_shared_omp(W, t, r)
+        kind = "reference"
+    else:
+        run = lambda t, r: o.mmse_apply(W, r / t)
+        kind, cores = "port", 1
+    t0 = time.perf_counter(); run(tx, rx); dt = time.perf_counter() - t0
+    n = int(min(sample_frames, max(4096, 4096 * seconds_target / max(dt, 1e-6))))
+    reps = -(-n // 4096)
+    txb, rxb = np.tile(tx, (reps, 1))[:n], np.tile(rx, (reps, 1))[:n]
+    t0 = time.perf_counter(); run(txb, rxb); dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d frames of the shared-filter MMSE workload (LS divide + 53x53 filter), %.1f s, %s" %
+                      (n, dt, "oracle/_ref ref_mmse_shared_omp (reference multiply(), OpenMP over frames)" if kind == "reference"
+                       else "oracle port, single thread")}, (run, txb, rxb)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, (run, txb, rxb) = cpu_reference_rate(1 << 22, seconds_target=max(1.0, min(12.0, 90.0 / (args.steps + args.warmup))))
+    n = len(txb)
+    for _ in range(args.warmup):
+        run(txb[: n // 4], rxb[: n // 4])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(txb, rxb)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    cb["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f80 (x87 long double)",
+        "data": "synthetic", "config": {"workload": "configs[2]: shared-filter PS_MMSE, bounded sample of %d frames per step on the host cores" % n},
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def extras_block(wifi, ctx, torch, peaks, n_frames, steps, warmup):
+    """Secondary kernels: frames/s + roofline fraction each (algorithmic bytes/flops per frame from SURVEY 8(d))."""
+    out = {}
+    hbm = peaks["hbm_gbs"]
+
+    def rate(fn, n, bytes_per_frame=None, flops_per_frame=None, peak_tflops=None):
+        total, per = time_steps(fn, steps, warmup, torch)
+        ms = float(np.median(per))
+        r = {"frames_per_s": n / (ms * 1e-3), "ms": ms, "n_frames": n}
+        if bytes_per_frame:
+            r["GBps"] = n * bytes_per_frame / (ms * 1e-3) / 1e9
+            r["hbm_frac"] = r["GBps"] / hbm
+            r["bytes_per_frame"] = bytes_per_frame
+        if flops_per_frame:
+            r["TFLOPs"] = n * flops_per_frame / (ms * 1e-3) / 1e12
+            r["flops_per_frame"] = flops_per_frame
+            if peak_tflops:
+                r["peak_tflops_nominal"] = peak_tflops
+                r["flop_frac_of_nominal"] = r["TFLOPs"] / peak_tflops
+        return r
+
+    for prec, cbytes in (("f32", 8), ("f64", 16)):
+        n = n_frames
+        fr = ctx.synth_frames(n, prec, want=("tx_pre", "rx_pre", "tx_symb", "rx_symb"))
+        H = torch.empty_like(fr["tx_pre"])
+        out["lt_ls_" + prec] = rate(lambda: ctx.lt_ls(fr["tx_pre"], fr["rx_pre"], out=H), n, 159 * cbytes)
+        outs = {k: torch.empty_like(fr["tx_pre"]) for k in ("linear", "cubic", "sinc")}
+        out["ps_fused3_" + prec] = rate(lambda: ctx.ps(fr["tx_symb"], fr["rx_symb"], out=outs), n, 167 * cbytes)
+        o1 = {"linear": outs["linear"]}
+        out["ps_linear_" + prec] = rate(lambda: ctx.ps(fr["tx_symb"], fr["rx_symb"], ("linear",), out=o1), n, 61 * cbytes)
+        eq = torch.empty_like(fr["rx_symb"])
+        out["equalize_" + prec] = rate(lambda: ctx.equalize(fr["rx_symb"], H, outs["linear"], out=eq), n, 1696 * cbytes)
+        del eq
+        tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
+        del fr
+        Hm = torch.empty_like(tx0)
+        if prec == "f64":
+            out["mmse_shared_f64"] = rate(lambda: ctx.mmse_shared(tx0, rx0, out=Hm), n, 159 * cbytes, 22472, 37.0)
+        # per-frame solve: 256 Ki frames (configs[3])
+        npf = min(n, 1 << 18)
+        s2 = ctx.synth_frames(npf, prec, per_frame_sigma=True, want=("sigma2",))["sigma2"]
+        R = ctx.synth_covariance()
+        Rp = R if prec == "f64" else R.to(torch.complex64)
+        Hp = torch.empty_like(tx0[:npf])
+        out["mmse_perframe_hpd_" + prec] = rate(
+            lambda: ctx.mmse_perframe(Rp, tx0[:npf], rx0[:npf], s2, flags=wifi.SOLVE_HPD, out=Hp), npf, 159 * cbytes, 441949,
+            74.0 if prec == "f32" else 37.0)
+        npv = min(npf, 1 << 15)
+        out["mmse_perframe_pivot_" + prec] = rate(
+            lambda: ctx.mmse_perframe(Rp, tx0[:npv], rx0[:npv], s2[:npv], flags=wifi.SOLVE_PIVOT, out=Hp[:npv]), npv, 159 * cbytes, 441949,
+            74.0 if prec == "f32" else 37.0)
+        del tx0, rx0, Hm, Hp
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    wifi = importlib.import_module("80211parallelestimation_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    ctx = wifi.WifiContext(local)
+    peaks = measured_peaks()
+    n_local = args.frames
+    n_total = n_local * world
+    shard = wifi.ShardedEstimator(n_total, rank, world)
+    assert shard.n_local == n_local
+
+    # ---- data resident in HBM: this rank's contiguous shard of the global synthetic sequence ----
+    fr = ctx.synth_frames(n_local, "f32", first_frame=shard.lo, want=("tx_symb", "rx_symb", "H_true"))
+    tx = fr["tx_symb"][:, 0, :].contiguous(); rx = fr["rx_symb"][:, 0, :].contiguous(); Htrue = fr["H_true"]
+    del fr
+    torch.cuda.empty_cache()
+    H = torch.empty_like(tx)
+    # shared filter: formed once on the device in FP64 (not part of the step)
+    R = ctx.synth_covariance()
+    d = torch.full((NSC,), OW2 / AMP ** 2, dtype=torch.float64, device=tx.device); d[26] = OW2 / 1e-8
+    t0 = time.perf_counter(); ctx.mmse_filter_form(R, d, want_W=False); torch.cuda.synchronize(); filter_ms = 1e3 * (time.perf_counter() - t0)
+
+    step = lambda: ctx.mmse_shared(tx, rx, out=H)
+    sampler = ClockSampler(local); sampler.start()
+    l0 = ctx.launches
+    total_ms, per = time_steps(step, args.steps, args.warmup, torch, dist)
+    launches = (ctx.launches - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.result()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=tx.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    value = n_total * args.steps / (total_ms * 1e-3)
+    kernel_ms = float(np.mean(per))
+
+    # ---- statistics: the only (optional) collective, after the timed region ----
+    stats = shard.reduce_stats(ctx.error_stats(H, Htrue))
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----
+    htx = pinned(wifi, (n_local, NSC), np.complex64); hrx = pinned(wifi, (n_local, NSC), np.complex64); hH = pinned(wifi, (n_local, NSC), np.complex64)
+    htx[:] = tx.cpu().numpy(); hrx[:] = rx.cpu().numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        ctx.mmse_shared(htx, hrx, out=hH)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.mmse_shared(htx, hrx, out=hH)          # returns after the D2H of the result has completed
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=tx.device)
+    if dist is not None:
+        dist.barrier()
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = n_total * e2e_steps / float(te[0])
+    e2e_ok = bool(np.allclose(hH[:1024], H[:1024].cpu().numpy(), rtol=1e-5, atol=1e-8))
+
+    if rank == 0:
+        bytes_per_frame = 159 * 8          # read tx 53c + rx 53c, write H 53c, FP32 complex (fused LS + filter)
+        achieved = n_local * bytes_per_frame / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core products, FP32 accumulate; filter formed in f64)" if os.environ.get("WIFI_B200_GEMM", "tc") == "tc" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: batched PS_MMSE, shared Rhh/sigma2, %d frames per GPU as one complex GEMM (LS divide fused), FP32 I/O" % n_local,
+                       "frames_per_gpu": n_local, "frames_total": n_total, "l2_policy": "inputs per pass (%.2f GB) >> 126 MB L2, no flush" % (n_local * bytes_per_frame / 1e9),
+                       "parallelism": "frame-sharded x%d, no data-path collective" % world, "filter_form_ms": filter_ms},
+            "roofline": {"bound": "hbm", "kernel": "mmse_shared (fused LS divide + 53x53 complex filter GEMM)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_frame": bytes_per_frame, "kernel_ms": kernel_ms,
+                         "tensor_TFLOPs_3xTF32": n_local * 3 * 2 * 112 * 112 / (kernel_ms * 1e-3) / 1e12},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_local * NSC * 8), "d2h_bytes_per_step": int(n_local * NSC * 8),
+                    "steps": e2e_steps, "matches_device_result": e2e_ok, "api": "WifiContext.mmse_shared(numpy pinned) -> wifi_mmse_shared_host"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "accuracy": {"nmse_vs_true_channel": stats["nmse"], "max_abs_err": stats["max_abs_err"], "count": stats["count"]},
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_reference_rate(1 << 21)
+            line["cpu_baseline"] = cb
+        if world == 1 and not args.no_extras:
+            del htx, hrx, hH
+            line["extras"] = extras_block(wifi, ctx, torch, peaks, min(n_local, 1 << 20), max(3, min(args.steps, 10)), 3)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

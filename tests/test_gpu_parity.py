@@ -148,7 +148,12 @@ def test_mmse_filter_form(ctx, oracle):
     R = synth.channel_covariance()
     d = np.full(NSC, synth.OW2 / synth.AMP ** 2); d[26] = synth.OW2 / 1e-8
     W = host(ctx.mmse_filter_form(dev(R), dev(d)))
-    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-9
+    # entries of W = R (R+D)^-1 are individually ill-determined at cond(R+D) ~ 1e7 (the oracle's own long-double W is
+    # only ~1e-12 accurate); what the estimator needs is the ACTION of W on LS vectors, checked to 1e-10 below
+    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-6
+    fr = synth.make_frames(64, seed=4)
+    tx, rx = fr["tx_symb"][:, 0, :], fr["rx_symb"][:, 0, :]
+    assert rel_err(oracle.mmse_apply(W, rx / tx), oracle.mmse_perframe(R, tx, rx, synth.OW2)) < 1e-10
     rng = np.random.default_rng(3)
     Rg = synth.random_hpd(rng)
     W = host(ctx.mmse_filter_form(dev(Rg), dev(d)))
@@ -171,7 +176,7 @@ def test_mmse_shared(ctx, oracle, prec, n):
     assert rel_err(got2, oracle.mmse_apply(W, r32(hls.astype(CDT[prec]), prec))) < TOL[prec]
     # the shared filter reproduces the per-frame formula when sigma2 and |x|^2 are shared
     if prec == "f64":
-        assert rel_err(got, oracle.mmse_perframe(R, tx, rx, synth.OW2)) < 1e-9
+        assert rel_err(got, oracle.mmse_perframe(R, tx, rx, synth.OW2)) < 1e-10
 
 
 def test_mmse_shared_needs_filter(wifi):
@@ -279,7 +284,7 @@ def test_host_entry_points(ctx, wifi, oracle, prec):
     R = synth.channel_covariance()
     d = synth.OW2 / np.abs(fr["tx_symb"][0, 0, :]) ** 2
     W = ctx.mmse_filter_form(R, d)
-    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-9
+    assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-6
     H = ctx.mmse_shared(txs[:, 0, :].copy(), rxs[:, 0, :].copy())
     assert rel_err(H, oracle.mmse_apply(W, r32(rxs[:, 0, :], prec) / r32(txs[:, 0, :], prec))) < TOL[prec]
     if prec == "f64":
