@@ -79,19 +79,36 @@ __global__ void __launch_bounds__(FF_THREADS) filter_form_kernel(const double2 *
     double2 *a = ff_smem;                 // [53][107]
     double2 *lcol = a + NSC * FF_LD;      // [53]
     __shared__ int ctl[2];
+    __shared__ double sc[NSC];            // s_i = d_i^-1/2 (symmetric equilibration), 1 if some d_i <= 0
+    __shared__ int all_pos;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        for (int i = 0; i < NSC; ++i) ok &= (d[i] > 0.0);
+        all_pos = ok;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NSC; i += FF_THREADS) sc[i] = all_pos ? rsqrt(d[i]) : 1.0;
+    __syncthreads();
+    // With S = diag(s): R + D = S^-1 (B + I) S^-1, B = S R S, so W = R (R+D)^-1 = S^-1 [B (B+I)^-1] S.
+    // B + I is equilibrated (unit noise floor on every bin, including the DC bin whose d is 1e10 x larger),
+    // which keeps the relative accuracy of every column of W.  X^T = (B+I)^-T B^T is one solve with 53 rhs.
     for (int e = threadIdx.x; e < NSC * NSC; e += FF_THREADS) {
         int i = e / NSC, j = e - i * NSC;
         double2 r = R[e];                 // R[i][j]
-        double2 at = r;
-        if (i == j) at.x += d[i];
-        a[j * FF_LD + i] = at;            // A^T
-        a[j * FF_LD + NSC + i] = r;       // R^T
+        double sij = sc[i] * sc[j];
+        double2 b = make_double2(r.x * sij, r.y * sij);
+        double2 at = b;
+        if (i == j) at.x += all_pos ? 1.0 : d[i];
+        a[j * FF_LD + i] = at;            // (B + I)^T
+        a[j * FF_LD + NSC + i] = b;       // B^T
     }
     __syncthreads();
     int sing = gj_solve<double>(a, NSC, FF_LD, 2 * NSC, lcol, ctl);
     for (int e = threadIdx.x; e < NSC * NSC; e += FF_THREADS) {
         int i = e / NSC, j = e - i * NSC;
-        W[e] = a[j * FF_LD + NSC + i];    // W[i][j] = (W^T)[j][i]
+        double2 x = a[j * FF_LD + NSC + i];    // X[i][j] = (X^T)[j][i]
+        double f = sc[j] / sc[i];
+        W[e] = make_double2(x.x * f, x.y * f);
     }
     if (threadIdx.x == 0 && info) *info = sing;
 }
