@@ -16,11 +16,6 @@
 
 using namespace wifi;
 
-namespace wifi {
-cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);
-cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *a, const void *rx, int64_t frame_stride,
-                                    void *H, int64_t n_frames, cudaStream_t s);
-}  // namespace wifi
 
 struct wifi_ctx {
     int device;
@@ -32,6 +27,7 @@ struct wifi_ctx {
     char err[512];
     int64_t launches;
     int timing;
+    int force_simt;
     cudaEvent_t ev0, ev1;
     int ev_valid;
     // host-pointer pipeline
@@ -113,6 +109,7 @@ int wifi_create(int device, wifi_ctx **out)
     wifi_ctx *ctx = (wifi_ctx *)calloc(1, sizeof(wifi_ctx));
     if (!ctx) return WIFI_ERR_NOMEM;
     ctx->device = device;
+    { const char *g = getenv("WIFI_B200_GEMM"); ctx->force_simt = (g && strcmp(g, "simt") == 0); }
     if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return WIFI_ERR_CUDA; }
     double w[3 * WIFI_NSC * 4];
     float wf[3 * WIFI_NSC * 4];
@@ -208,7 +205,8 @@ int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx, const void
 static int install_filter(wifi_ctx *ctx, cudaStream_t s)
 {
     CK(launch_filter_install_simt(ctx->img, s));
-    ctx->launches += 1;
+    CK(launch_filter_install_tc(ctx->img, s));
+    ctx->launches += 2;
     ctx->img.valid = 1;
     return WIFI_OK;
 }
@@ -244,7 +242,10 @@ static int mmse_shared(wifi_ctx *ctx, wifi_dtype dt, const void *a, const void *
 {
     if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
     Timed t(ctx, s);
-    CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
+    // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: CUDA-core kernel (tcgen05 has no FP64 kind).
+    // WIFI_B200_GEMM=simt selects the CUDA-core FP32 kernel for A/B measurements (both are sm_100a kernels).
+    if (dt == WIFI_F32 && !ctx->force_simt) CK(launch_mmse_shared_tc(ctx->img, a, rx, frame_stride, H, n, s));
+    else CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
     return WIFI_OK;
 }
 

@@ -1,0 +1,363 @@
+// wifi_gemm_tc.cu -- shared-filter PS_MMSE on the 5th-generation tensor cores (FP32 mode).
+//
+//   H[n][53] = (rx/tx)[n][53] * W^T        complex, as the real product  [n x 106] * [106 x 106]   (K, N padded to 112)
+//
+// 3xTF32: every FP32 operand is split into a TF32 "hi" part and a residual "lo" part and the product is accumulated as
+// A_hi*B_hi + A_lo*B_hi + A_hi*B_lo in FP32 (error ~2^-21 per term), so FP32-level accuracy comes out of kind::tf32 MMAs.
+//
+// One persistent CTA per SM, 128-frame tiles:
+//   warps 0-3 (one thread per frame = one TMEM lane):
+//       a. coalesced LDG.128 of the warp's 32-frame chunk of tx and rx (contiguous 13.5 KB each), LS divide rx/tx
+//          (main.c:83 arithmetic on all 53 bins), result staged row-major in the warp's private shared-memory buffer;
+//       b. each thread re-reads ITS frame, splits hi/lo and writes both operand images straight into TENSOR MEMORY
+//          (tcgen05.st) -- the A operand never exists in shared memory;
+//       c. epilogue of the previous tile: tcgen05.ld of the FP32 accumulators (TMEM, double buffered), staged through the
+//          same private buffer so the global store is one contiguous 13.5 KB run per warp.
+//   warp 4, one elected thread: 14 K-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=112, K=8; A from TMEM, B = the filter's
+//       hi/lo images resident in shared memory in the canonical K-major no-swizzle UMMA layout), tcgen05.commit -> mbarrier.
+// The MMA of tile t overlaps the epilogue of tile t-1 and the loads of tile t+1.  HBM traffic is exactly the algorithmic
+// 159 complex values per frame.
+#include <algorithm>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+constexpr int TC_M = 128;                 // frames per tile
+constexpr int TC_K = 112;                 // 106 padded to a multiple of 8
+constexpr int TC_N = 112;                 // 106 padded to a multiple of 16
+constexpr int TC_CONV_WARPS = 4;
+constexpr int TC_THREADS = (TC_CONV_WARPS + 1) * 32;
+constexpr int TC_ROWF = 2 * NSC;          // 106 floats per frame
+constexpr int TC_CHUNK_F = 32 * TC_ROWF;  // 3392 floats per warp chunk
+constexpr int TC_B_BYTES = TC_N * TC_K * 4;       // 50176
+constexpr int TC_B_SBO = (TC_K / 4) * 128;        // 3584: byte distance between 8-row groups
+constexpr int TC_B_LBO = 128;                     // byte distance between adjacent 16-byte K chunks
+// TMEM columns
+constexpr int TC_COL_D0 = 0, TC_COL_D1 = 128, TC_COL_AHI = 256, TC_COL_ALO = 384;
+
+// canonical K-major SWIZZLE_NONE layout: element (n, k) of B -> float index
+__host__ __device__ __forceinline__ int b_canon_index(int n, int k)
+{
+    return ((n >> 3) * TC_B_SBO + (k >> 2) * TC_B_LBO + (n & 7) * 16 + (k & 3) * 4) >> 2;
+}
+
+// ---- filter images: W (53x53 double2) -> real embedding B[n][k] = Wembed[k][n], split hi/lo, canonical layout ----
+__global__ void filter_install_tc_kernel(const double2 *__restrict__ W, float *__restrict__ Bhi, float *__restrict__ Blo)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= TC_N * TC_K) return;
+    int n = e / TC_K, k = e - n * TC_K;
+    double v = 0.0;
+    if (n < TC_ROWF && k < TC_ROWF) {
+        double2 w = W[(n >> 1) * NSC + (k >> 1)];        // W[j][i], j = n/2 (output), i = k/2 (input)
+        // out[2j] = sum Wr in[2i] - Wi in[2i+1];  out[2j+1] = sum Wi in[2i] + Wr in[2i+1]
+        v = (n & 1) ? ((k & 1) ? w.x : w.y) : ((k & 1) ? -w.y : w.x);
+    }
+    float f = (float)v;
+    float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);     // exact TF32
+    float lo = (float)(v - (double)hi);
+    int idx = b_canon_index(n, k);
+    Bhi[idx] = hi;
+    Blo[idx] = lo;
+}
+
+cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s)
+{
+    filter_install_tc_kernel<<<(TC_N * TC_K + 255) / 256, 256, 0, s>>>((const double2 *)img.W64, img.Bhi, img.Blo);
+    return cudaGetLastError();
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar), done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 "version 1")
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                 // start address
+    d |= (uint64_t)((TC_B_LBO >> 4) & 0x3FFF) << 16;        // leading (K-chunk) byte offset
+    d |= (uint64_t)((TC_B_SBO >> 4) & 0x3FFF) << 32;        // stride (8-row group) byte offset
+    d |= (uint64_t)1 << 46;                                 // descriptor version
+    return d;                                               // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+
+constexpr uint32_t TC_IDESC = (1u << 4)            // D format F32
+                              | (2u << 7)          // A format TF32
+                              | (2u << 10)         // B format TF32
+                              | (0u << 15)         // A K-major
+                              | (0u << 16)         // B K-major
+                              | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct TcSmem {
+    float bhi[TC_B_BYTES / 4];
+    float blo[TC_B_BYTES / 4];
+    float chunk[TC_CONV_WARPS][TC_CHUNK_F];        // per-warp private staging (input H_ls chunk, then output chunk)
+    uint64_t bar_a_ready;                          // 128 converter arrivals per tile
+    uint64_t bar_mma_done[2];                      // tcgen05.commit per accumulator buffer
+    uint32_t tmem_base;
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
+                          const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16)
+{
+    extern __shared__ unsigned char tc_smem_raw[];
+    TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 127) & ~(uintptr_t)127);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup: filter images -> smem, barriers, TMEM ----
+    {
+        const uint4 *gh = reinterpret_cast<const uint4 *>(Bhi_g), *gl = reinterpret_cast<const uint4 *>(Blo_g);
+        uint4 *sh = reinterpret_cast<uint4 *>(sm.bhi), *sl = reinterpret_cast<uint4 *>(sm.blo);
+        for (int i = threadIdx.x; i < TC_B_BYTES / 16; i += TC_THREADS) { sh[i] = __ldg(gh + i); sl[i] = __ldg(gl + i); }
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar_a_ready, TC_CONV_WARPS * 32);
+        mbar_init(&sm.bar_mma_done[0], 1);
+        mbar_init(&sm.bar_mma_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_CONV_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // B images (generic-proxy writes) -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles blockIdx.x, +gridDim.x, ...
+
+    if (warp == TC_CONV_WARPS) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint64_t dhi = make_b_desc(smem_u32(sm.bhi)), dlo = make_b_desc(smem_u32(sm.blo));
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(&sm.bar_a_ready, it & 1);
+                tc_fence_after();
+                const uint32_t d = tmem + ((it & 1) ? TC_COL_D1 : TC_COL_D0);
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 256 >> 4);             // two 128-byte core matrices per K-step
+                    umma_tf32_ts(d, tmem + TC_COL_AHI + 8 * ks, dhi + adv, TC_IDESC, ks > 0);
+                    umma_tf32_ts(d, tmem + TC_COL_ALO + 8 * ks, dhi + adv, TC_IDESC, 1);
+                    umma_tf32_ts(d, tmem + TC_COL_AHI + 8 * ks, dlo + adv, TC_IDESC, 1);
+                }
+                umma_commit(&sm.bar_mma_done[it & 1]);
+            }
+        }
+    } else {
+        // ================= converter / epilogue warps: thread = frame = TMEM lane =================
+        float *buf = sm.chunk[warp];
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool vec_ok = (frame_stride == NSC) && aligned16;
+        for (int it = 0; it <= my_tiles; ++it) {
+            if (it < my_tiles) {
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                const int64_t f0 = tile * TC_M + warp * 32;                       // first frame of this warp's chunk
+                const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
+                // ---- a. chunk -> private buffer (row-major [32][106] floats), LS divide fused ----
+                if (vec_ok && valid == 32) {
+                    const float4 *pa = reinterpret_cast<const float4 *>(a_in + f0 * NSC);
+                    const float4 *pr = FUSED ? reinterpret_cast<const float4 *>(rx + f0 * NSC) : nullptr;
+                    float4 *b4 = reinterpret_cast<float4 *>(buf);
+#pragma unroll
+                    for (int i0 = 0; i0 < 27; i0 += 9) {
+                        float4 va[9], vr[9];
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            int q = (i0 + j) * 32 + lane;
+                            if (q < TC_CHUNK_F / 4) { va[j] = ld_stream(pa + q); if (FUSED) vr[j] = ld_stream(pr + q); }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            int q = (i0 + j) * 32 + lane;
+                            if (q < TC_CHUNK_F / 4) {
+                                float4 o = va[j];
+                                if (FUSED) {
+                                    float2 h0 = cdiv(make_float2(vr[j].x, vr[j].y), make_float2(va[j].x, va[j].y));
+                                    float2 h1 = cdiv(make_float2(vr[j].z, vr[j].w), make_float2(va[j].z, va[j].w));
+                                    o = make_float4(h0.x, h0.y, h1.x, h1.y);
+                                }
+                                b4[q] = o;
+                            }
+                        }
+                    }
+                } else {
+                    float2 *b2 = reinterpret_cast<float2 *>(buf);
+                    for (int e = lane; e < 32 * NSC; e += 32) {
+                        int r = e / NSC, c = e - r * NSC;
+                        float2 o = make_float2(0.f, 0.f);
+                        if (r < valid) {
+                            int64_t off = (f0 + r) * frame_stride + c;
+                            o = ld_stream(a_in + off);
+                            if (FUSED) o = cdiv(ld_stream(rx + off), o);
+                        }
+                        b2[e] = o;
+                    }
+                }
+                __syncwarp();
+                // ---- b. my frame -> hi/lo -> TMEM (A operand), after the previous tile's MMAs have released it ----
+                if (it > 0) { mbar_wait(&sm.bar_mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
+                const float2 *row = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
+#pragma unroll
+                for (int g = 0; g < TC_K / 16; ++g) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        int cc = g * 8 + c;
+                        float2 v = (cc < NSC) ? row[cc] : make_float2(0.f, 0.f);
+                        uint32_t hx, hy;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
+                        hi[2 * c] = hx; hi[2 * c + 1] = hy;
+                        lo[2 * c] = __float_as_uint(v.x - __uint_as_float(hx));
+                        lo[2 * c + 1] = __float_as_uint(v.y - __uint_as_float(hy));
+                    }
+                    tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
+                    tmem_st16(lane_base + TC_COL_ALO + 16 * g, lo);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&sm.bar_a_ready);
+            }
+            // ---- c. epilogue of the previous tile ----
+            if (it > 0) {
+                const int pt = it - 1;
+                if (it == my_tiles) { mbar_wait(&sm.bar_mma_done[pt & 1], (pt >> 1) & 1); tc_fence_after(); }
+                const int64_t tile = blockIdx.x + (int64_t)pt * gridDim.x;
+                const int64_t f0 = tile * TC_M + warp * 32;
+                const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
+                const uint32_t dcol = lane_base + ((pt & 1) ? TC_COL_D1 : TC_COL_D0);
+                __syncwarp();      // everyone finished reading buf as input
+                float2 *rowo = reinterpret_cast<float2 *>(buf + lane * TC_ROWF);
+#pragma unroll
+                for (int g = 0; g < TC_N / 16; ++g) {
+                    uint32_t v[16];
+                    tmem_ld16(dcol + 16 * g, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        int cc = g * 8 + c;
+                        if (cc < NSC) rowo[cc] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (valid == 32) {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(buf);
+                    float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
+#pragma unroll 9
+                    for (int i = 0; i < 27; ++i) {
+                        int q = i * 32 + lane;
+                        if (q < TC_CHUNK_F / 4) st_stream(po + q, b4[q]);
+                    }
+                } else {
+                    const float2 *b2 = reinterpret_cast<const float2 *>(buf);
+                    for (int e = lane; e < valid * NSC; e += 32) H[f0 * NSC + e] = b2[e];
+                }
+                __syncwarp();      // buf is free for the next chunk
+            }
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_CONV_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
+                                  int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const size_t smem = sizeof(TcSmem) + 128;
+    const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
+    const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;
+    cudaError_t e;
+    if (rx) {
+        e = cudaFuncSetAttribute(mmse_shared_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mmse_shared_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
+                                                                   (float2 *)H, n_frames, aligned16);
+    } else {
+        e = cudaFuncSetAttribute(mmse_shared_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mmse_shared_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, nullptr, NSC, (float2 *)H,
+                                                                    n_frames, aligned16);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

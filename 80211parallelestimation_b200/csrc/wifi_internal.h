@@ -42,6 +42,9 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
 cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);   // W64 -> W32
 cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *tx_or_hls, const void *rx,
                                     int64_t frame_stride, void *H, int64_t n_frames, cudaStream_t s);  // rx == NULL: apply only
+cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // W64 -> Bhi/Blo (UMMA canonical layout)
+cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
+                                  int64_t n_frames, cudaStream_t s);             // FP32 I/O, 3xTF32 on tcgen05
 cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch,
                            cudaStream_t s);
 cudaError_t launch_chermitian(wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch, cudaStream_t s);

@@ -161,7 +161,7 @@ def test_mmse_filter_form(ctx, oracle):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("n", [1, 63, 64, 65, 777])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 777, 18949])
 def test_mmse_shared(ctx, oracle, prec, n):
     fr = synth.make_frames(n, seed=n)
     tx, rx = fr["tx_symb"][:, 0, :].astype(CDT[prec]), fr["rx_symb"][:, 0, :].astype(CDT[prec])
