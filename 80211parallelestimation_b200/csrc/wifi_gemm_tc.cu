@@ -54,9 +54,12 @@ __global__ void filter_install_tc_kernel(const double2 *__restrict__ W, float *_
         // out[2j] = sum Wr in[2i] - Wi in[2i+1];  out[2j+1] = sum Wi in[2i] + Wr in[2i+1]
         v = (n & 1) ? ((k & 1) ? w.x : w.y) : ((k & 1) ? -w.y : w.x);
     }
-    float f = (float)v;
-    float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);     // exact TF32
-    float lo = (float)(v - (double)hi);
+    // hi = TF32 round-to-nearest of v, lo = TF32 round-to-nearest of the remainder: hi + lo = v (1 + 2^-22)
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"((float)v));
+    float hi = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"((float)(v - (double)hi)));
+    float lo = __uint_as_float(lb);
     int idx = b_canon_index(n, k);
     Bhi[idx] = hi;
     Blo[idx] = lo;
@@ -276,8 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
                         hi[2 * c] = hx; hi[2 * c + 1] = hy;
-                        lo[2 * c] = __float_as_uint(v.x - __uint_as_float(hx));
-                        lo[2 * c + 1] = __float_as_uint(v.y - __uint_as_float(hy));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c]) : "f"(v.x - __uint_as_float(hx)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c + 1]) : "f"(v.y - __uint_as_float(hy)));
                     }
                     tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
                     tmem_st16(lane_base + TC_COL_ALO + 16 * g, lo);

