@@ -6,14 +6,14 @@
 // A_hi*B_hi + A_lo*B_hi + A_hi*B_lo in FP32 (error ~2^-21 per term), so FP32-level accuracy comes out of kind::tf32 MMAs.
 //
 // One persistent CTA per SM, 128-frame tiles:
-//   warps 0-3 (one thread per frame = one TMEM lane):
+//   warps 0-7 = two groups of four that alternate tiles (one thread per frame = one TMEM lane):
 //       a. coalesced LDG.128 of the warp's 32-frame chunk of tx and rx (contiguous 13.5 KB each), LS divide rx/tx
 //          (main.c:83 arithmetic on all 53 bins), result staged row-major in the warp's private shared-memory buffer;
 //       b. each thread re-reads ITS frame, splits hi/lo and writes both operand images straight into TENSOR MEMORY
 //          (tcgen05.st) -- the A operand never exists in shared memory;
 //       c. epilogue of the previous tile: tcgen05.ld of the FP32 accumulators (TMEM, double buffered), staged through the
 //          same private buffer so the global store is one contiguous 13.5 KB run per warp.
-//   warp 4, one elected thread: 14 K-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=112, K=8; A from TMEM, B = the filter's
+//   warp 8, one elected thread: 14 K-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=112, K=8; A from TMEM, B = the filter's
 //       hi/lo images resident in shared memory in the canonical K-major no-swizzle UMMA layout), tcgen05.commit -> mbarrier.
 // The MMA of tile t overlaps the epilogue of tile t-1 and the loads of tile t+1.  HBM traffic is exactly the algorithmic
 // 159 complex values per frame.
@@ -26,7 +26,7 @@ namespace wifi {
 constexpr int TC_M = 128;                 // frames per tile
 constexpr int TC_K = 112;                 // 106 padded to a multiple of 8
 constexpr int TC_N = 112;                 // 106 padded to a multiple of 16
-constexpr int TC_CONV_WARPS = 4;
+constexpr int TC_CONV_WARPS = 8;          // two groups of 4 (one warp per TMEM lane quarter and group)
 constexpr int TC_THREADS = (TC_CONV_WARPS + 1) * 32;
 constexpr int TC_ROWF = 2 * NSC;          // 106 floats per frame
 constexpr int TC_CHUNK_F = 32 * TC_ROWF;  // 3392 floats per warp chunk
@@ -162,13 +162,33 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
+// rx/tx with ONE reciprocal: MUFU.RCP + a Newton step (relative error ~1e-7, branch-free; 0/0 still yields NaN like
+// the reference).  The IEEE '/' expands to ~12 instructions and a slow-path branch per real divide, which made the LS
+// divide two thirds of this kernel's instruction count.
+__device__ __forceinline__ float2 cdiv_fast(float2 a, float2 b)
+{
+    const float den = fmaf(b.x, b.x, b.y * b.y);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+    r = fmaf(r, fmaf(-den, r, 1.0f), r);
+    return make_float2(fmaf(a.x, b.x, a.y * b.y) * r, fmaf(a.y, b.x, -a.x * b.y) * r);
+}
+// LS divide of one float4 (two complex bins) when FUSED, identity otherwise
+template <bool FUSED> __device__ __forceinline__ float4 ls_pair(float4 a, float4 r)
+{
+    if (!FUSED) return a;
+    float2 h0 = cdiv_fast(make_float2(r.x, r.y), make_float2(a.x, a.y));
+    float2 h1 = cdiv_fast(make_float2(r.z, r.w), make_float2(a.z, a.w));
+    return make_float4(h0.x, h0.y, h1.x, h1.y);
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
                           const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16)
 {
-    extern __shared__ unsigned char tc_smem_raw[];
-    TcSmem &sm = *reinterpret_cast<TcSmem *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    TcSmem &sm = *reinterpret_cast<TcSmem *>(tc_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: filter images -> smem, barriers, TMEM ----
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int i = threadIdx.x; i < TC_B_BYTES / 16; i += TC_THREADS) { sh[i] = __ldg(gh + i); sl[i] = __ldg(gl + i); }
     }
     if (threadIdx.x == 0) {
-        mbar_init(&sm.bar_a_ready, TC_CONV_WARPS * 32);
+        mbar_init(&sm.bar_a_ready, 128);
         mbar_init(&sm.bar_mma_done[0], 1);
         mbar_init(&sm.bar_mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -216,88 +236,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else {
         // ================= converter / epilogue warps: thread = frame = TMEM lane =================
+        // Two groups of 4 warps alternate tiles (group g owns the CTA's tiles g, g+2, ...), so the latency-bound load /
+        // divide / stage phase of one tile overlaps the TMEM write, MMA and epilogue of the other group's tile.
+        const int group = warp >> 2, quarter = warp & 3;
         float *buf = sm.chunk[warp];
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
         const bool vec_ok = (frame_stride == NSC) && aligned16;
-        for (int it = 0; it <= my_tiles; ++it) {
-            if (it < my_tiles) {
-                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-                const int64_t f0 = tile * TC_M + warp * 32;                       // first frame of this warp's chunk
-                const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
-                // ---- a. chunk -> private buffer (row-major [32][106] floats), LS divide fused ----
-                if (vec_ok && valid == 32) {
-                    const float4 *pa = reinterpret_cast<const float4 *>(a_in + f0 * NSC);
-                    const float4 *pr = FUSED ? reinterpret_cast<const float4 *>(rx + f0 * NSC) : nullptr;
-                    float4 *b4 = reinterpret_cast<float4 *>(buf);
-#pragma unroll
-                    for (int i0 = 0; i0 < 27; i0 += 9) {
-                        float4 va[9], vr[9];
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) {
-                            int q = (i0 + j) * 32 + lane;
-                            if (q < TC_CHUNK_F / 4) { va[j] = ld_stream(pa + q); if (FUSED) vr[j] = ld_stream(pr + q); }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) {
-                            int q = (i0 + j) * 32 + lane;
-                            if (q < TC_CHUNK_F / 4) {
-                                float4 o = va[j];
-                                if (FUSED) {
-                                    float2 h0 = cdiv(make_float2(vr[j].x, vr[j].y), make_float2(va[j].x, va[j].y));
-                                    float2 h1 = cdiv(make_float2(vr[j].z, vr[j].w), make_float2(va[j].z, va[j].w));
-                                    o = make_float4(h0.x, h0.y, h1.x, h1.y);
-                                }
-                                b4[q] = o;
-                            }
-                        }
-                    }
-                } else {
-                    float2 *b2 = reinterpret_cast<float2 *>(buf);
-                    for (int e = lane; e < 32 * NSC; e += 32) {
-                        int r = e / NSC, c = e - r * NSC;
-                        float2 o = make_float2(0.f, 0.f);
-                        if (r < valid) {
-                            int64_t off = (f0 + r) * frame_stride + c;
-                            o = ld_stream(a_in + off);
-                            if (FUSED) o = cdiv(ld_stream(rx + off), o);
-                        }
-                        b2[e] = o;
-                    }
-                }
-                __syncwarp();
-                // ---- b. my frame -> hi/lo -> TMEM (A operand), after the previous tile's MMAs have released it ----
-                if (it > 0) { mbar_wait(&sm.bar_mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
-                const float2 *row = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
-#pragma unroll
-                for (int g = 0; g < TC_K / 16; ++g) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        int cc = g * 8 + c;
-                        float2 v = (cc < NSC) ? row[cc] : make_float2(0.f, 0.f);
-                        uint32_t hx, hy;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
-                        hi[2 * c] = hx; hi[2 * c + 1] = hy;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c]) : "f"(v.x - __uint_as_float(hx)));
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c + 1]) : "f"(v.y - __uint_as_float(hy)));
-                    }
-                    tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
-                    tmem_st16(lane_base + TC_COL_ALO + 16 * g, lo);
-                }
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&sm.bar_a_ready);
-            }
-            // ---- c. epilogue of the previous tile ----
-            if (it > 0) {
-                const int pt = it - 1;
-                if (it == my_tiles) { mbar_wait(&sm.bar_mma_done[pt & 1], (pt >> 1) & 1); tc_fence_after(); }
+        for (int it = group; it < my_tiles + 2; it += 2) {
+            // ---- c. epilogue of this group's previous tile (it-2); must precede this iteration's a_ready arrival ----
+            if (it >= 2) {
+                const int pt = it - 2;
+                mbar_wait(&sm.bar_mma_done[pt & 1], (pt >> 1) & 1);
+                tc_fence_after();
                 const int64_t tile = blockIdx.x + (int64_t)pt * gridDim.x;
-                const int64_t f0 = tile * TC_M + warp * 32;
+                const int64_t f0 = tile * TC_M + quarter * 32;
                 const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
                 const uint32_t dcol = lane_base + ((pt & 1) ? TC_COL_D1 : TC_COL_D0);
-                __syncwarp();      // everyone finished reading buf as input
                 float2 *rowo = reinterpret_cast<float2 *>(buf + lane * TC_ROWF);
 #pragma unroll
                 for (int g = 0; g < TC_N / 16; ++g) {
@@ -312,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (valid == 32) {
+                if (valid == 32 && aligned16) {
                     const float4 *b4 = reinterpret_cast<const float4 *>(buf);
                     float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
 #pragma unroll 9
@@ -326,6 +280,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 __syncwarp();      // buf is free for the next chunk
             }
+            if (it >= my_tiles) continue;
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t f0 = tile * TC_M + quarter * 32;                       // first frame of this warp's chunk
+            const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
+            // ---- a. chunk -> private buffer (row-major [32][106] floats), LS divide fused; loads software-pipelined ----
+            if (vec_ok && valid == 32) {
+                const float4 *pa = reinterpret_cast<const float4 *>(a_in + f0 * NSC) + lane;
+                const float4 *pr = FUSED ? reinterpret_cast<const float4 *>(rx + f0 * NSC) + lane : nullptr;
+                float4 *b4 = reinterpret_cast<float4 *>(buf) + lane;
+                constexpr int NB = 7;                                             // 4 batches of 7 vectors (27 used)
+                float4 va[2][NB], vr[2][NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) { va[0][j] = ld_stream(pa + 32 * j); if (FUSED) vr[0][j] = ld_stream(pr + 32 * j); }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (b < 3) {
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) {
+                            const int i = (b + 1) * NB + j;
+                            if (i < 26 || (i == 26 && lane < 16)) {
+                                va[(b + 1) & 1][j] = ld_stream(pa + 32 * i);
+                                if (FUSED) vr[(b + 1) & 1][j] = ld_stream(pr + 32 * i);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int i = b * NB + j;
+                        if (i < 26 || (i == 26 && lane < 16)) b4[32 * i] = ls_pair<FUSED>(va[b & 1][j], vr[b & 1][j]);
+                    }
+                }
+            } else {
+                float2 *b2 = reinterpret_cast<float2 *>(buf);
+                for (int e = lane; e < 32 * NSC; e += 32) {
+                    int r = e / NSC, c = e - r * NSC;
+                    float2 o = make_float2(0.f, 0.f);
+                    if (r < valid) {
+                        int64_t off = (f0 + r) * frame_stride + c;
+                        o = ld_stream(a_in + off);
+                        if (FUSED) o = cdiv_fast(ld_stream(rx + off), o);
+                    }
+                    b2[e] = o;
+                }
+            }
+            __syncwarp();
+            // ---- b. my frame -> hi/lo -> TMEM (A operand), after the previous tile's MMAs have released it ----
+            if (it > 0) { mbar_wait(&sm.bar_mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
+            const float2 *row = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
+#pragma unroll
+            for (int g = 0; g < TC_K / 16; ++g) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    int cc = g * 8 + c;
+                    float2 v = (cc < NSC) ? row[cc] : make_float2(0.f, 0.f);
+                    uint32_t hx, hy;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
+                    hi[2 * c] = hx; hi[2 * c + 1] = hy;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c]) : "f"(v.x - __uint_as_float(hx)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c + 1]) : "f"(v.y - __uint_as_float(hy)));
+                }
+                tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
+                tmem_st16(lane_base + TC_COL_ALO + 16 * g, lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&sm.bar_a_ready);
+            __syncwarp();          // everyone has read its row before the buffer is reused
         }
     }
 
@@ -344,7 +367,7 @@ cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const 
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const size_t smem = sizeof(TcSmem) + 128;
+    const size_t smem = sizeof(TcSmem);
     const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;

@@ -1,0 +1,37 @@
+"""Launches every hot kernel twice at its benchmark size (for `ncu`; numbers printed under a profiler are not bench values).
+    python profiles/run_profile.py [kernel-name-substring ...]
+"""
+import importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+def main():
+    sel = sys.argv[1:]
+    want = lambda name: (not sel) or any(s in name for s in sel)
+    wifi = importlib.import_module("80211parallelestimation_b200")
+    ctx = wifi.WifiContext(0)
+    n = 1 << 20
+    R = ctx.synth_covariance()
+    d = torch.full((53,), 9.6172e-08 / 8.875 ** 2, dtype=torch.float64, device="cuda"); d[26] = 9.6172e-08 / 1e-8
+    ctx.mmse_filter_form(R, d, want_W=False)
+    for prec in ("f32", "f64"):
+        fr = ctx.synth_frames(n if prec == "f32" else n // 2, prec, per_frame_sigma=True, want=("tx_pre", "rx_pre", "tx_symb", "rx_symb", "sigma2"))
+        tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
+        H = torch.empty_like(tx0)
+        outs = {k: torch.empty_like(tx0) for k in ("linear", "cubic", "sinc")}
+        eq = torch.empty_like(fr["rx_symb"][: n // 8])
+        Rp = R if prec == "f64" else R.to(torch.complex64)
+        for rep in range(2):
+            if want("lt_ls"): ctx.lt_ls(fr["tx_pre"], fr["rx_pre"], out=H)
+            if want("ps_interp"): ctx.ps(fr["tx_symb"], fr["rx_symb"], out=outs)
+            if want("equalize"): ctx.equalize(fr["rx_symb"][: n // 8], H[: n // 8], outs["linear"][: n // 8], out=eq)
+            if want("mmse_shared"): ctx.mmse_shared(tx0, rx0, out=H)
+            if want("mmse_hpd"): ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD, out=H[: 1 << 16])
+        torch.cuda.synchronize()
+        del fr, tx0, rx0, H, outs, eq
+        torch.cuda.empty_cache()
+    print("profile run ok, launches:", ctx.launches)
+
+if __name__ == "__main__":
+    main()
