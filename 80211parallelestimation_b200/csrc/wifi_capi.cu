@@ -111,6 +111,13 @@ int wifi_create(int device, wifi_ctx **out)
     ctx->device = device;
     { const char *g = getenv("WIFI_B200_GEMM"); ctx->force_simt = (g && strcmp(g, "simt") == 0); }
     if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return WIFI_ERR_CUDA; }
+    {
+        // The pilot gather of the PS estimators touches 8 isolated complex values per frame; with the default L2 fetch
+        // granularity every one of them drags a 128-byte line out of HBM (measured 929 B/frame instead of 256).
+        const char *g = getenv("WIFI_B200_L2FETCH");
+        int gran = g ? atoi(g) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    }
     double w[3 * WIFI_NSC * 4];
     float wf[3 * WIFI_NSC * 4];
     build_tables(w);

@@ -55,4 +55,19 @@ template <typename C, typename S> __device__ __forceinline__ C cscale(C a, S s) 
 template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V *p, V v) { __stcs(p, v); }
 
+// isolated gather load (pilot sub-carriers): streaming, and ask L2 to fetch only the 64-byte half-line that holds the
+// value -- by default every touched sector promotes to a full 128-byte line from HBM (ncu: 929 B/frame for 8 pilots)
+__device__ __forceinline__ float2 ld_gather(const float2 *p)
+{
+    float2 v;
+    asm volatile("ld.global.cs.L2::64B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_gather(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cs.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 }  // namespace wifi

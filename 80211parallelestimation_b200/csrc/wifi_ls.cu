@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__re
     for (int idx = threadIdx.x; idx < nf * 4; idx += PS_THREADS) {
         int f = idx >> 2, p = idx & 3;
         int64_t off = (f0 + f) * frame_stride + (WIFI_P0 + (WIFI_P1 - WIFI_P0) * p);
-        hp[f][p] = cdiv(ld_stream(rx + off), ld_stream(tx + off));
+        hp[f][p] = cdiv(ld_gather(rx + off), ld_gather(tx + off));
     }
     // this thread's sub-carrier and its weights (registers)
     const int k = threadIdx.x % NSC, fsub = threadIdx.x / NSC;
