@@ -36,6 +36,10 @@ def main():
     # ---- 1. inputs.h ----
     inp = ref.inputs()
     np.savez(os.path.join(HERE, "inputs_h.npz"), **inp)
+    with open(os.path.join(HERE, "inputs_h_frame.f64"), "wb") as f:      # raw doubles for the C host driver (host/)
+        np.array([float(inp["ow2"])]).tofile(f)
+        for key in ("tx_preamble_fft", "rx_preamble_fft", "tx_symb", "rx_symb"):
+            np.ascontiguousarray(inp[key]).view(np.float64).tofile(f)
     txs = inp["tx_symb"].reshape(NBLK, NSC)
     rxs = inp["rx_symb"].reshape(NBLK, NSC)
 
