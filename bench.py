@@ -126,6 +126,7 @@ def cpu_reference_rate(sample_frames, seconds_target=12.0):
     tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
     if Reference.available():
         ref = Reference()
+        cores = ref.set_threads(cores)           # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
         run = lambda t, r: ref.mmse_shared_omp(W, t, r)
         kind = "reference"
     else:

@@ -174,6 +174,15 @@ class Oracle:
         assert rc == 0
         return H
 
+    def mmse_cconv_batch(self, tx, rx, ow2, H_ls):
+        t, pt = _c(tx); x, px = _c(rx); h, ph = _c(H_ls)
+        n = t.size // NSC
+        s, ps = _d(np.broadcast_to(np.asarray(ow2, np.float64), (n,)))
+        H = np.empty((n, NSC), np.complex128)
+        rc = self.lib.orc_mmse_cconv_batch(pt, px, ps, ph, H.ctypes.data_as(_dp), C.c_long(n))
+        assert rc == 0
+        return H
+
     def mmse_cconv(self, tx, rx, ow2, H_ls):
         t, pt = _c(tx); x, px = _c(rx); h, ph = _c(H_ls)
         H = np.empty(NSC, np.complex128)
@@ -212,6 +221,11 @@ class Reference:
         self.lib = C.CDLL(self.path)
         self.lib.ref_ow2.restype = C.c_double
         self.lib.ref_sinc.restype = C.c_double
+
+    def set_threads(self, n):
+        """OpenMP team size of the *_omp timing loops; returns the size in effect."""
+        self.lib.ref_set_threads(C.c_int(int(n)))
+        return int(self.lib.ref_get_max_threads())
 
     def estimate(self, which, a, b, omp=False):
         code = {"lt_ls": 0, "ps_linear": 1, "ps_cubic": 2, "ps_sinc": 3}[which]

@@ -100,6 +100,10 @@ void ref_inputs(double *tx_pre, double *rx_pre, double *txs, double *rxs)
     from_ld(tx_symb, txs, SIZESYMBOL); from_ld(rx_symb, rxs, SIZESYMBOL);
 }
 
+/* OpenMP team size of the timing loops below (torchrun exports OMP_NUM_THREADS=1; the bench overrides it here) */
+void ref_set_threads(int n) { omp_set_num_threads(n); }
+int ref_get_max_threads(void) { return omp_get_max_threads(); }
+
 /* ---- timing loops for bench.py's CPU arm: the reference functions, frame-parallel
  * over all host threads (the fair multi-core number, survey 8(d)-iii) ---- */
 void ref_estimate_omp(int which, const double *a, const double *b, double *H, long n_frames)
