@@ -9,6 +9,7 @@ F32, F64 = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_SINGULAR, ERR_NO_DEVICE, ERR_STATE = range(7)
 PS_LINEAR, PS_CUBIC, PS_SINC = 1, 2, 4
 SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE = 0, 1, 2
+SOLVE_WIDE = SOLVE_REFINE
 AS_WRITTEN, INTENDED = 0, 1
 
 _vp, _i, _i64, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint64

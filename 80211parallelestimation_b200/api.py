@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, AS_WRITTEN, INTENDED)
+from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, AS_WRITTEN, INTENDED)
 
 NSC, NBLK, FRAME = 53, 15, 795
 

@@ -277,7 +277,7 @@ static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void
     {
         Timed t(ctx, s);
         if ((flags & WIFI_SOLVE_HPD) && !hls)
-            CK(launch_mmse_perframe_hpd(dt, R, tx, rx, frame_stride, sigma2, H, n, (flags & WIFI_SOLVE_REFINE) ? 1 : 0, nullptr, s));
+            CK(launch_mmse_perframe_hpd(dt, R, tx, rx, frame_stride, sigma2, H, n, (flags & WIFI_SOLVE_WIDE) ? 1 : 0, s));
         else
             CK(launch_mmse_perframe_pivot(dt, R, tx, rx, frame_stride, sigma2, hls, H, n, check ? ctx->d_info : nullptr, s));
     }

@@ -35,8 +35,7 @@ cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void 
                                        const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info,
                                        cudaStream_t s);
 cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                     const void *sigma2, void *H, int64_t n_frames, int refine, const void *R64,
-                                     cudaStream_t s);
+                                     const void *sigma2, void *H, int64_t n_frames, int wide, cudaStream_t s);
 
 // shared-filter GEMM + small matrix utils (wifi_gemm.cu)
 cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);   // W64 -> W32

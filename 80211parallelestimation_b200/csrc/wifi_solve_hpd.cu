@@ -1,26 +1,36 @@
-// wifi_solve_hpd.cu -- per-frame PS_MMSE solve, register-resident fast path (WIFI_SOLVE_HPD).
+// wifi_solve_hpd.cu -- per-frame PS_MMSE for Hermitian PSD R (WIFI_SOLVE_HPD):
 //
-//   A_f = R + diag(sigma2_f / |tx_k|^2)   (Hermitian positive definite when R is Hermitian PSD)
-//   A_f z = rx/tx,   H = R z
+//   A_f = R + diag(d_f),  d_fk = sigma2_f / |tx_k|^2   (Hermitian positive definite when R is Hermitian PSD)
+//   A_f z = y = rx/tx,    H = R z = (A_f - D_f) z = y - D_f z
+//
+// The last identity replaces the 53 x 53 product R z of the formula by 53 multiplies, and it is the better-conditioned
+// evaluation: an error dz enters H as D dz (D ~ 1e-10 .. 1e-7) instead of R dz (measured in FP64: 4.6e-12 vs 9.9e-12).
 //
 // A frame is owned by a PR x 8 grid of lanes (PR = 8: two warps, PR = 4: one warp).  Lane (pr, pc) keeps the
 // 2-D-cyclic slice  a[li][lj] = M[PR li + pr][8 lj + pc]  of the bordered Hermitian matrix
 //        M = [ A   . ]      (row 53 = y^H carries the right-hand side through the elimination)
 //            [ y^H . ]
-// in REGISTERS, and only the local positions that can lie on or below the diagonal (28 of 49 for PR = 8).
-// Elimination is the symmetric (L D L^H) form without pivoting -- for a Hermitian positive-definite matrix the growth
-// factor is 1 -- and is fully unrolled over the 53 steps so every register index is static.  Step k:
-//   * the lanes of lane-column k%8 publish the raw column  c_i = a_ik  (i >= k) to a double-buffered 56-entry scratch;
-//   * one sync (named 64-thread barrier or __syncwarp);
-//   * every lane reads c for its rows and its columns and the pivot, forms t_j = conj(c_j)/a_kk and updates
-//     a_ij -= c_i t_j  on its lower local positions (4 FMAs each, ~40 % fewer than the unsymmetric update);
-//   * conj(c_i)/a_kk = U'_ki is stored (one entry per lane) into a packed triangle that later serves the
-//     back-substitution; the entry of row 53 is the forward-substituted right-hand side.
-// The cyclic distribution keeps all lanes busy as the active sub-matrix shrinks.  Back-substitution (unit-diagonal U',
-// columns contiguous in shared memory) runs on one warp with shuffle broadcasts; H = R z reads R^T from shared memory.
+// in REGISTERS, and only the local positions that can lie on or below the diagonal (28 of 49 for PR = 8, 56 of 98 for
+// PR = 4).  Elimination is the symmetric (L D L^H) form without pivoting -- for a Hermitian positive-definite matrix
+// the growth factor is 1 -- and is fully unrolled over the 53 steps so every register index is static.  Step k:
+//   * the lanes of lane-column k%8 publish the raw column  c_i = a_ik  to a double-buffered 64-entry scratch, permuted
+//     so that the entries one lane needs afterwards (its rows, its columns) are contiguous 64-byte runs;
+//   * one sync (named barrier for two warps, __syncwarp for one);
+//   * every lane reads the runs of its rows and its columns and the pivot, forms t_j = conj(c_j)/a_kk for its columns
+//     and updates  a_ij -= c_i t_j  on its lower local positions (4 FMAs each).  Positions that are already finished
+//     (row or column <= k) are NOT masked: they receive garbage that is never read again;
+//   * row k of U' = D^-1 L^H, U'_ki = conj(c_i)/a_kk, goes to shared memory (one contiguous run per step, rows k and
+//     52-k folded into one 54-entry line); its entry 53 is the forward-substituted right-hand side.
+// The cyclic distribution keeps all lanes busy as the active sub-matrix shrinks.  Back-substitution with the
+// unit-diagonal U' runs on one warp (column axpys, z_j broadcast by shuffle) and finishes with H = y - D z from
+// registers.  tx/rx of the group's next frame are prefetched into registers during the elimination.
+//
+// TIO is the storage type of R/tx/rx/sigma2/H and T the arithmetic type: <float,float>, <double,double>, and
+// <double,float> = WIFI_SOLVE_WIDE (FP32 I/O, FP64 arithmetic: d_f is below the FP32 resolution of R).
 //
 // Replaces the two inverse() calls of main.c:186,201 (utils.c:141-170, O(n^5)) for the intended formula.
 #include <algorithm>
+#include <cstdlib>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -28,23 +38,24 @@ namespace wifi {
 
 constexpr int H_N1 = NSC + 1;                   // 54 rows of the bordered matrix
 constexpr int H_NLC = 7;                        // local columns (53 columns / 8)
-constexpr int H_UT = 1432;                      // packed strict upper triangle incl. rhs: sum_{i=1..53} i = 1431
-constexpr int H_RT = NSC * NSC + 7;             // 2816
+constexpr int H_US = 27 * 54 + 2;               // folded U' store: line m = row m (53-m entries) ++ row 52-m (m+1 entries)
+constexpr int H_RT = (NSC * NSC + 7) & ~7;      // 2816: keeps the per-group runs 64-byte aligned
 
-__device__ __forceinline__ int ut_off(int j) { return (j * (j - 1)) >> 1; }   // column j of U' holds rows 0..j-1
+// The published column is stored as 8 runs (run r = rows/columns i with i%8 == r, position i/8).  Runs are RS entries
+// apart with RS * sizeof(cx<T>) / 16 odd, so the 8 runs start in 8 different 16-byte bank groups and a 16-byte shared
+// load that touches the same position of all 8 runs is conflict-free (RS = 8 would be an 8-way conflict).
+template <typename T> struct RunStride { static constexpr int v = sizeof(T) == 4 ? 10 : 9; };
 
 // per-group shared-memory layout, in units of cx<T>
 struct HpdSmem {
-    static constexpr int UT = 0;
-    static constexpr int LB = UT + H_UT;        // [2][56]
-    static constexpr int YB = LB + 112;         // [56]
-    static constexpr int ZB = YB + 56;          // [56]
-    static constexpr int DB = ZB + 56;          // T[56] <= 28 cx
-    static constexpr int GROUP = DB + 28;       // 1684
+    static constexpr int US = 0;
+    static constexpr int LB = US + H_US;        // [2][80]
+    static constexpr int YB = LB + 160;         // [56]
+    static constexpr int DB = YB + 56;          // T[56] <= 28 cx
+    static constexpr int GROUP = DB + 28;       // 1704 (multiple of 8: every run stays 16-byte aligned)
 };
-
-// frames per CTA / lane-grid height per precision (tuned on B200)
-constexpr int HPD_F32_PR = 8, HPD_F32_FPC = 8, HPD_F64_FPC = 4;
+// offset of U'_ki (i > k) in the folded store
+__host__ __device__ constexpr int us_off(int k, int i) { return k <= 26 ? k * 54 + i - k - 1 : (52 - k) * 54 + i; }
 
 template <int LANES> __device__ __forceinline__ void group_sync(int id)
 {
@@ -52,10 +63,110 @@ template <int LANES> __device__ __forceinline__ void group_sync(int id)
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(LANES) : "memory");
 }
 
-template <typename T, int PR, int FPC>
-__global__ void __launch_bounds__(PR * 8 * FPC, 1)
-    mmse_hpd_kernel(const cx<T> *__restrict__ R, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx, int64_t frame_stride,
-                    const T *__restrict__ sigma2, cx<T> *__restrict__ H, int64_t n_frames)
+// 1/x for a positive pivot without the IEEE slow path: hardware approximation + Newton steps
+__device__ __forceinline__ float pivot_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ double pivot_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));      // MUFU.RCP64H: ~20 bits
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
+// entries [lo, 8) of a 64-byte-aligned run of 8 complex values, with 16-byte shared loads
+template <int LO> __device__ __forceinline__ void load_run(const float2 *p, float2 (&v)[8])
+{
+#pragma unroll
+    for (int m = LO / 2; m < 4; ++m) {
+        float4 q = *reinterpret_cast<const float4 *>(p + 2 * m);
+        v[2 * m] = make_float2(q.x, q.y);
+        v[2 * m + 1] = make_float2(q.z, q.w);
+    }
+}
+template <int LO> __device__ __forceinline__ void load_run(const double2 *p, double2 (&v)[8])
+{
+#pragma unroll
+    for (int m = LO; m < 7; ++m) v[m] = p[m];
+}
+
+template <typename T, typename TIO, int PR, int FPC, int MINB, int K>
+struct HpdStep {
+    static constexpr int LANES = PR * 8;
+    static constexpr int NLR = (H_N1 + PR - 1) / PR;
+    static __device__ __forceinline__ bool live(int li, int lj) { return PR * li + PR - 1 >= 8 * lj; }
+
+    static __device__ __forceinline__ void run(cx<T> (&a)[NLR][H_NLC], cx<T> *lb, cx<T> *Us, int lane, int pr, int pc, int bar_id)
+    {
+        constexpr int kc = K & 7, klc = K >> 3;        // owner lane-column and local column of column K
+        constexpr int klr = K / PR;                    // first local row that can hold a row >= K
+        constexpr int RS = RunStride<T>::v;
+        cx<T> *lbk = lb + (K & 1) * 80;
+        if (pc == kc) {
+#pragma unroll
+            for (int li = klr; li < NLR; ++li)
+                if (live(li, klc)) lbk[PR == 8 ? pr * RS + li : (pr + 4 * (li & 1)) * RS + (li >> 1)] = a[li][klc];   // row PR li + pr
+        }
+        group_sync<LANES>(bar_id);
+        const T inv = pivot_rcp(lbk[(K & 7) * RS + (K >> 3)].x);       // the pivot a_KK of a Hermitian matrix is real
+        // my columns: class pc, local columns klc..6
+        cx<T> cc[8], t[H_NLC];
+        load_run<klc>(lbk + pc * RS, cc);
+#pragma unroll
+        for (int lj = klc; lj < H_NLC; ++lj) t[lj] = mk<T>(cc[lj].x * inv, -cc[lj].y * inv);
+        // row K of U' (entries i = K+1 .. 53), one contiguous run
+#pragma unroll
+        for (int i0 = 0; i0 < H_N1; i0 += LANES) {
+            if (i0 + LANES - 1 > K) {
+                const int i = i0 + lane;
+                if (i > K && i < H_N1) {
+                    cx<T> c = lbk[(i & 7) * RS + (i >> 3)];
+                    Us[us_off(K, i)] = mk<T>(c.x * inv, -c.y * inv);
+                }
+            }
+        }
+        // my rows
+        if (PR == 8) {
+            cx<T> cr[8];
+            load_run<klr>(lbk + pr * RS, cr);
+#pragma unroll
+            for (int li = klr; li < NLR; ++li)
+#pragma unroll
+                for (int lj = klc; lj < H_NLC; ++lj)
+                    if (live(li, lj)) cfms(a[li][lj], cr[li], t[lj]);
+        } else {
+            // PR == 4: rows 4 li + pr -> class pr (li even) and class pr + 4 (li odd), run position li / 2
+            cx<T> ce[8], co[8];
+            load_run<(klr + 1) / 2>(lbk + pr * RS, ce);
+            load_run<klr / 2>(lbk + (pr + 4) * RS, co);
+#pragma unroll
+            for (int li = klr; li < NLR; ++li) {
+                const cx<T> c = (li & 1) ? co[li >> 1] : ce[li >> 1];
+#pragma unroll
+                for (int lj = klc; lj < H_NLC; ++lj)
+                    if (live(li, lj)) cfms(a[li][lj], c, t[lj]);
+            }
+        }
+        HpdStep<T, TIO, PR, FPC, MINB, K + 1>::run(a, lb, Us, lane, pr, pc, bar_id);
+    }
+};
+template <typename T, typename TIO, int PR, int FPC, int MINB>
+struct HpdStep<T, TIO, PR, FPC, MINB, NSC> {
+    static constexpr int NLR = (H_N1 + PR - 1) / PR;
+    static __device__ __forceinline__ void run(cx<T> (&)[NLR][H_NLC], cx<T> *, cx<T> *, int, int, int, int) {}
+};
+
+template <typename T, typename TIO> __device__ __forceinline__ cx<T> widen(cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); }
+
+template <typename T, typename TIO, int PR, int FPC, int MINB>
+__global__ void __launch_bounds__(PR * 8 * FPC, MINB)
+    mmse_hpd_kernel(const cx<TIO> *__restrict__ R, const cx<TIO> *__restrict__ tx, const cx<TIO> *__restrict__ rx, int64_t frame_stride,
+                    const TIO *__restrict__ sigma2, cx<TIO> *__restrict__ H, int64_t n_frames)
 {
     constexpr int LANES = PR * 8;
     constexpr int NLR = (H_N1 + PR - 1) / PR;              // local rows: 7 (PR = 8) or 14 (PR = 4)
@@ -65,22 +176,51 @@ __global__ void __launch_bounds__(PR * 8 * FPC, 1)
     const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
     const int pr = lane >> 3, pc = lane & 7;
     cx<T> *gs = Rt + H_RT + grp * S::GROUP;
-    cx<T> *Ut = gs + S::UT, *lb = gs + S::LB, *yb = gs + S::YB, *zb = gs + S::ZB;
+    cx<T> *Us = gs + S::US, *lb = gs + S::LB, *yb = gs + S::YB;
     T *db = (T *)(gs + S::DB);
     const int bar_id = grp + 1;
 
     for (int e = threadIdx.x; e < NSC * NSC; e += LANES * FPC) {
         int i = e / NSC, j = e - i * NSC;
-        Rt[j * NSC + i] = R[e];
+        Rt[j * NSC + i] = widen<T, TIO>(R[e]);
     }
     __syncthreads();
 
-    for (int64_t f = (int64_t)blockIdx.x * FPC + grp; f < n_frames; f += (int64_t)gridDim.x * FPC) {
+    const int64_t fstep = (int64_t)gridDim.x * FPC;
+    int64_t f = (int64_t)blockIdx.x * FPC + grp;
+    // prefetched inputs of the current frame: lane k (and k + 32 for one-warp groups) holds sub-carrier k
+    constexpr int NIN = (NSC + LANES - 1) / LANES;
+    cx<TIO> tin[NIN], rin[NIN];
+    TIO sin = (TIO)0;
+    if (f < n_frames) {
+#pragma unroll
+        for (int q = 0; q < NIN; ++q) {
+            const int k = lane + q * LANES;
+            if (k < NSC) { tin[q] = ld_stream(tx + f * frame_stride + k); rin[q] = ld_stream(rx + f * frame_stride + k); }
+        }
+        sin = sigma2[f];
+    }
+    for (; f < n_frames; f += fstep) {
         // ---- per-frame inputs: y = rx/tx, d = sigma2/|tx|^2 ----
-        for (int k = lane; k < NSC; k += LANES) {
-            cx<T> t = ld_stream(tx + f * frame_stride + k), r = ld_stream(rx + f * frame_stride + k);
-            yb[k] = cdiv(r, t);
-            db[k] = sigma2[f] / cabs2(t);
+#pragma unroll
+        for (int q = 0; q < NIN; ++q) {
+            const int k = lane + q * LANES;
+            if (k < NSC) {
+                cx<T> t = widen<T, TIO>(tin[q]), r = widen<T, TIO>(rin[q]);
+                yb[k] = cdiv(r, t);
+                db[k] = (T)sin / cabs2(t);
+            }
+        }
+        {
+            const int64_t fn = f + fstep;
+            if (fn < n_frames) {
+#pragma unroll
+                for (int q = 0; q < NIN; ++q) {
+                    const int k = lane + q * LANES;
+                    if (k < NSC) { tin[q] = ld_stream(tx + fn * frame_stride + k); rin[q] = ld_stream(rx + fn * frame_stride + k); }
+                }
+                sin = sigma2[fn];
+            }
         }
         group_sync<LANES>(bar_id);
         // local slice of the bordered matrix; only positions that can be on/below the diagonal are ever touched
@@ -102,92 +242,93 @@ __global__ void __launch_bounds__(PR * 8 * FPC, 1)
             }
         }
 
-        // ---- symmetric elimination, fully unrolled ----
-#pragma unroll
-        for (int K = 0; K < NSC; ++K) {
-            const int kc = K & 7, klc = K >> 3;            // owner lane-column and local column of column K
-            const int klr = K / PR;                        // first local row that can hold a row >= K
-            cx<T> *lbk = lb + (K & 1) * 56;
-            if (pc == kc) {
-#pragma unroll
-                for (int li = klr; li < NLR; ++li)
-                    if (PR * li + PR - 1 >= 8 * klc) lbk[PR * li + pr] = a[li][klc];
-            }
-            group_sync<LANES>(bar_id);
-            const T inv = (T)1 / lbk[K].x;                 // pivot a_KK is real for a Hermitian matrix
-            cx<T> t[H_NLC];
-#pragma unroll
-            for (int lj = klc; lj < H_NLC; ++lj) {
-                const int j = 8 * lj + pc;
-                cx<T> c = lbk[j];
-                t[lj] = (j > K && j < NSC) ? mk<T>(c.x * inv, -c.y * inv) : mk<T>(0, 0);
-            }
-#pragma unroll
-            for (int li = klr; li < NLR; ++li) {
-                const int i = PR * li + pr;
-                cx<T> c = lbk[i];
-                if (!(i > K && i < H_N1)) c = mk<T>(0, 0);           // rows <= K are finished, rows >= 54 do not exist
-                if (pc == (li & 7) && i > K && i < H_N1) Ut[ut_off(i) + K] = mk<T>(c.x * inv, -c.y * inv);   // U'_Ki
-#pragma unroll
-                for (int lj = klc; lj < H_NLC; ++lj)
-                    if (PR * li + PR - 1 >= 8 * lj) cfms(a[li][lj], c, t[lj]);
-            }
-        }
+        // ---- symmetric elimination, fully unrolled (compile-time recursion: every index is static) ----
+        HpdStep<T, TIO, PR, FPC, MINB, 0>::run(a, lb, Us, lane, pr, pc, bar_id);
         group_sync<LANES>(bar_id);
 
-        // ---- back-substitution on the first warp of the group: U' has unit diagonal, column j = rows 0..j-1 contiguous ----
+        // ---- back-substitution on the first warp of the group, then H = y - D z from registers ----
         if (lane < 32) {
-            const cx<T> *ycol = Ut + ut_off(NSC);
-            cx<T> y0 = ycol[lane], y1 = (lane + 32 < NSC) ? ycol[lane + 32] : mk<T>(0, 0);
+            // lane owns rows i0 = lane and i1 = lane + 32; U'_ij lives at ub + j
+            const cx<T> *ub0 = Us + (lane <= 26 ? lane * 53 - 1 : (52 - lane) * 54);
+            const cx<T> *ub1 = Us + (lane <= 20 ? (20 - lane) * 54 : 0);
+            cx<T> y0 = ub0[NSC], y1 = (lane + 32 < NSC) ? ub1[NSC] : mk<T>(0, 0);
+#pragma unroll 4
             for (int j = NSC - 1; j >= 32; --j) {
                 cx<T> zj = mk<T>(__shfl_sync(0xffffffffu, y1.x, j - 32), __shfl_sync(0xffffffffu, y1.y, j - 32));
-                const cx<T> *col = Ut + ut_off(j);
-                cfms(y0, col[lane], zj);
-                if (lane + 32 < j) cfms(y1, col[lane + 32], zj);
+                cfms(y0, ub0[j], zj);
+                if (lane + 32 < j) cfms(y1, ub1[j], zj);
             }
+#pragma unroll 4
             for (int j = 31; j >= 1; --j) {
                 cx<T> zj = mk<T>(__shfl_sync(0xffffffffu, y0.x, j), __shfl_sync(0xffffffffu, y0.y, j));
-                if (lane < j) cfms(y0, (Ut + ut_off(j))[lane], zj);
+                if (lane < j) cfms(y0, ub0[j], zj);
             }
-            zb[lane] = y0;
-            if (lane + 32 < NSC) zb[lane + 32] = y1;
+            {
+                const cx<T> y = yb[lane]; const T d = db[lane];
+                st_stream(H + f * NSC + lane, mk<TIO>((TIO)(y.x - d * y0.x), (TIO)(y.y - d * y0.y)));
+            }
+            if (lane + 32 < NSC) {
+                const cx<T> y = yb[lane + 32]; const T d = db[lane + 32];
+                st_stream(H + f * NSC + lane + 32, mk<TIO>((TIO)(y.x - d * y1.x), (TIO)(y.y - d * y1.y)));
+            }
         }
         group_sync<LANES>(bar_id);
-        // ---- H = R z ----
-        for (int i = lane; i < NSC; i += LANES) {
-            cx<T> acc = mk<T>(0, 0);
-#pragma unroll 4
-            for (int j = 0; j < NSC; ++j) cfma(acc, Rt[j * NSC + i], zb[j]);
-            st_stream(H + f * NSC + i, acc);
-        }
     }
 }
 
-template <typename T, int PR, int FPC>
+template <typename T, typename TIO, int PR, int FPC, int MINB>
 static cudaError_t launch_hpd(const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H,
                               int64_t n_frames, cudaStream_t s)
 {
     using S = HpdSmem;
     size_t smem = sizeof(cx<T>) * (H_RT + FPC * S::GROUP);
-    cudaError_t e = cudaFuncSetAttribute(mmse_hpd_kernel<T, PR, FPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = mmse_hpd_kernel<T, TIO, PR, FPC, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t need = (n_frames + FPC - 1) / FPC;
-    unsigned grid = (unsigned)std::min<int64_t>(need, 148);
-    mmse_hpd_kernel<T, PR, FPC><<<grid, PR * 8 * FPC, smem, s>>>((const cx<T> *)R, (const cx<T> *)tx, (const cx<T> *)rx, frame_stride,
-                                                               (const T *)sigma2, (cx<T> *)H, n_frames);
+    unsigned grid = (unsigned)std::min<int64_t>(need, 148 * MINB);
+    kern<<<grid, PR * 8 * FPC, smem, s>>>((const cx<TIO> *)R, (const cx<TIO> *)tx, (const cx<TIO> *)rx, frame_stride,
+                                          (const TIO *)sigma2, (cx<TIO> *)H, n_frames);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                     const void *sigma2, void *H, int64_t n_frames, int refine, const void *R64, cudaStream_t s)
+// tuning variants (WIFI_HPD_CFG=<n> selects one at run time for the probes; the defaults were measured on B200)
+static int hpd_cfg()
 {
-    (void)R64;
+    static int v = -2;
+    if (v == -2) { const char *e = getenv("WIFI_HPD_CFG"); v = e ? atoi(e) : -1; }
+    return v;
+}
+
+cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                                     const void *sigma2, void *H, int64_t n_frames, int wide, cudaStream_t s)
+{
     g_last_launches = 0;
-    if (refine) return cudaErrorNotSupported;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    if (dt == WIFI_F32) return launch_hpd<float, HPD_F32_PR, HPD_F32_FPC>(R, tx, rx, frame_stride, sigma2, H, n_frames, s);
-    return launch_hpd<double, 8, HPD_F64_FPC>(R, tx, rx, frame_stride, sigma2, H, n_frames, s);
+    const int cfg = hpd_cfg();
+#define HPD_ARGS R, tx, rx, frame_stride, sigma2, H, n_frames, s
+    if (dt == WIFI_F32 && wide) {
+        switch (cfg) {
+        case 1: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
+        default: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
+        }
+    }
+    if (dt == WIFI_F32) {
+        switch (cfg) {
+        case 1: return launch_hpd<float, float, 4, 8, 1>(HPD_ARGS);
+        case 2: return launch_hpd<float, float, 4, 6, 2>(HPD_ARGS);
+        case 3: return launch_hpd<float, float, 4, 12, 1>(HPD_ARGS);
+        case 4: return launch_hpd<float, float, 8, 4, 2>(HPD_ARGS);
+        default: return launch_hpd<float, float, 8, 8, 1>(HPD_ARGS);
+        }
+    }
+    switch (cfg) {
+    case 1: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
+    case 2: return launch_hpd<double, double, 8, 3, 1>(HPD_ARGS);
+    default: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
+    }
+#undef HPD_ARGS
 }
 
 }  // namespace wifi

@@ -63,7 +63,9 @@ typedef enum {
 /* flags of wifi_mmse_perframe_batch */
 #define WIFI_SOLVE_PIVOT 0      /* partial-pivoting Gauss-Jordan (any non-singular R + D) */
 #define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted elimination (growth factor 1) */
-#define WIFI_SOLVE_REFINE 2     /* FP32 only: one step of iterative refinement with an FP64 residual */
+#define WIFI_SOLVE_WIDE 2       /* with WIFI_SOLVE_HPD and WIFI_F32: FP32 storage, FP64 arithmetic inside the solve (sigma2/|x|^2
+                                 * is below the FP32 resolution of R; the plain FP32 solve is only accurate to ~1e-1) */
+#define WIFI_SOLVE_REFINE WIFI_SOLVE_WIDE   /* former name */
 
 /* wifi_chermitian_batch / wifi_cadd_batch semantics */
 #define WIFI_AS_WRITTEN 0       /* bit-compatible with utils.c:3-7 (Re-Im, real-valued) / utils.c:111-121 (M1+M1) */
