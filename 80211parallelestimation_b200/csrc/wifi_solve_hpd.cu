@@ -12,7 +12,7 @@
 //            [ y^H . ]
 // in REGISTERS, and only the local positions that can lie on or below the diagonal (28 of 49 for PR = 8, 56 of 98 for
 // PR = 4).  Elimination is the symmetric (L D L^H) form without pivoting -- for a Hermitian positive-definite matrix
-// the growth factor is 1 -- and is fully unrolled over the 53 steps so every register index is static.  Step k:
+// the growth factor is 1 -- and is unrolled over groups of PR steps so every register index is static.  Step k:
 //   * the lanes of lane-column k%8 publish the raw column  c_i = a_ik  to a double-buffered 64-entry scratch, permuted
 //     so that the entries one lane needs afterwards (its rows, its columns) are contiguous 64-byte runs;
 //   * one sync (named barrier for two warps, __syncwarp for one);
@@ -95,70 +95,91 @@ template <int LO> __device__ __forceinline__ void load_run(const double2 *p, dou
     for (int m = LO; m < 7; ++m) v[m] = p[m];
 }
 
-template <typename T, typename TIO, int PR, int FPC, int MINB, int K>
-struct HpdStep {
+// Per-lane addresses into the published-column scratch (buffer 0; the live buffer is `+ bo`, bo in {0, 80})
+template <typename T> struct HpdLane {
+    cx<T> *lb;      // scratch base
+    cx<T> *rowp;    // run of my rows (run pr; for one-warp groups the odd local rows are in run pr + 4)
+    cx<T> *colp;    // run of my columns (run pc)
+    cx<T> *usl;     // entry of row i = lane (row lane + 32 is 4 positions further)
+    cx<T> *Us;      // folded U' store
+    int lane, pr, pc, bar_id;
+};
+
+// Elimination steps are grouped by the local row / column block they start in: the PR steps K = PR*G .. PR*G + PR-1
+// touch the same register positions (local rows >= G, local columns >= PR*G/8), so one compiled body per group runs as a
+// rolled loop over the steps of the group -- the step index only enters through the publisher predicate, the scratch
+// buffer parity and the U' row offset.  (A fully unrolled 53-step elimination is 75-120 KB of straight-line code per
+// frame and misses in the instruction cache: ncu no_instruction stalls.)
+// (Forming the reciprocal of the next pivot on its owner lane at the end of a step and publishing it with the column
+// was measured slower: f64 31.2 -> 28.1 M frames/s; every lane recomputes it after the sync instead.)
+template <typename T, int PR, int G>
+struct HpdGroup {
     static constexpr int LANES = PR * 8;
     static constexpr int NLR = (H_N1 + PR - 1) / PR;
+    static constexpr int K0 = PR * G, NQ = (NSC - K0 < PR) ? NSC - K0 : PR;
+    static constexpr int klr = G, klc = K0 >> 3;       // first local row / column that can still be live
+    static constexpr int RS = RunStride<T>::v;
     static __device__ __forceinline__ bool live(int li, int lj) { return PR * li + PR - 1 >= 8 * lj; }
+    static __device__ __forceinline__ int rowpos(int li) { return PR == 8 ? li : (li & 1) * 4 * RS + (li >> 1); }
 
-    static __device__ __forceinline__ void run(cx<T> (&a)[NLR][H_NLC], cx<T> *lb, cx<T> *Us, int lane, int pr, int pc, int bar_id)
+    static __device__ __forceinline__ void run(cx<T> (&a)[NLR][H_NLC], const HpdLane<T> &L, int &bo)
     {
-        constexpr int kc = K & 7, klc = K >> 3;        // owner lane-column and local column of column K
-        constexpr int klr = K / PR;                    // first local row that can hold a row >= K
-        constexpr int RS = RunStride<T>::v;
-        cx<T> *lbk = lb + (K & 1) * 80;
-        if (pc == kc) {
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+            const int K = K0 + q, kc = K & 7;              // kc: owner lane-column of column K
+            if (L.pc == kc) {
 #pragma unroll
-            for (int li = klr; li < NLR; ++li)
-                if (live(li, klc)) lbk[PR == 8 ? pr * RS + li : (pr + 4 * (li & 1)) * RS + (li >> 1)] = a[li][klc];   // row PR li + pr
-        }
-        group_sync<LANES>(bar_id);
-        const T inv = pivot_rcp(lbk[(K & 7) * RS + (K >> 3)].x);       // the pivot a_KK of a Hermitian matrix is real
-        // my columns: class pc, local columns klc..6
-        cx<T> cc[8], t[H_NLC];
-        load_run<klc>(lbk + pc * RS, cc);
+                for (int li = klr; li < NLR; ++li)
+                    if (live(li, klc)) L.rowp[bo + rowpos(li)] = a[li][klc];          // row PR li + pr
+            }
+            group_sync<LANES>(L.bar_id);
+            const T inv = pivot_rcp(L.lb[bo + kc * RS + klc].x);   // the pivot a_KK of a Hermitian matrix is real
+            // my columns: run pc, local columns klc..6
+            cx<T> cc[8], t[H_NLC];
+            load_run<klc>(L.colp + bo, cc);
 #pragma unroll
-        for (int lj = klc; lj < H_NLC; ++lj) t[lj] = mk<T>(cc[lj].x * inv, -cc[lj].y * inv);
-        // row K of U' (entries i = K+1 .. 53), one contiguous run
+            for (int lj = klc; lj < H_NLC; ++lj) t[lj] = mk<T>(cc[lj].x * inv, -cc[lj].y * inv);
+            // row K of U' (entries i = K+1 .. 53), one contiguous run of the folded store
+            cx<T> *urow = L.Us + (K <= 26 ? K * 53 - 1 : (52 - K) * 54) + L.lane;
 #pragma unroll
-        for (int i0 = 0; i0 < H_N1; i0 += LANES) {
-            if (i0 + LANES - 1 > K) {
-                const int i = i0 + lane;
-                if (i > K && i < H_N1) {
-                    cx<T> c = lbk[(i & 7) * RS + (i >> 3)];
-                    Us[us_off(K, i)] = mk<T>(c.x * inv, -c.y * inv);
+            for (int i0 = 0; i0 < H_N1; i0 += LANES) {
+                if (i0 + LANES - 1 > K0) {
+                    const cx<T> c = L.usl[bo + (i0 >> 3)];
+                    if (i0 + L.lane > K && i0 + L.lane < H_N1) urow[i0] = mk<T>(c.x * inv, -c.y * inv);
                 }
             }
-        }
-        // my rows
-        if (PR == 8) {
-            cx<T> cr[8];
-            load_run<klr>(lbk + pr * RS, cr);
+            // my rows
+            if (PR == 8) {
+                cx<T> cr[8];
+                load_run<klr>(L.rowp + bo, cr);
 #pragma unroll
-            for (int li = klr; li < NLR; ++li)
+                for (int li = klr; li < NLR; ++li)
 #pragma unroll
-                for (int lj = klc; lj < H_NLC; ++lj)
-                    if (live(li, lj)) cfms(a[li][lj], cr[li], t[lj]);
-        } else {
-            // PR == 4: rows 4 li + pr -> class pr (li even) and class pr + 4 (li odd), run position li / 2
-            cx<T> ce[8], co[8];
-            load_run<(klr + 1) / 2>(lbk + pr * RS, ce);
-            load_run<klr / 2>(lbk + (pr + 4) * RS, co);
+                    for (int lj = klc; lj < H_NLC; ++lj)
+                        if (live(li, lj)) cfms(a[li][lj], cr[li], t[lj]);
+            } else {
+                // PR == 4: rows 4 li + pr -> run pr (li even) and run pr + 4 (li odd), position li / 2
+                cx<T> ce[8], co[8];
+                load_run<(klr + 1) / 2>(L.rowp + bo, ce);
+                load_run<klr / 2>(L.rowp + bo + 4 * RS, co);
 #pragma unroll
-            for (int li = klr; li < NLR; ++li) {
-                const cx<T> c = (li & 1) ? co[li >> 1] : ce[li >> 1];
+                for (int li = klr; li < NLR; ++li) {
+                    const cx<T> c = (li & 1) ? co[li >> 1] : ce[li >> 1];
 #pragma unroll
-                for (int lj = klc; lj < H_NLC; ++lj)
-                    if (live(li, lj)) cfms(a[li][lj], c, t[lj]);
+                    for (int lj = klc; lj < H_NLC; ++lj)
+                        if (live(li, lj)) cfms(a[li][lj], c, t[lj]);
+                }
             }
+            bo ^= 80;
         }
-        HpdStep<T, TIO, PR, FPC, MINB, K + 1>::run(a, lb, Us, lane, pr, pc, bar_id);
+        HpdGroup<T, PR, G + 1>::run(a, L, bo);
     }
 };
-template <typename T, typename TIO, int PR, int FPC, int MINB>
-struct HpdStep<T, TIO, PR, FPC, MINB, NSC> {
-    static constexpr int NLR = (H_N1 + PR - 1) / PR;
-    static __device__ __forceinline__ void run(cx<T> (&)[NLR][H_NLC], cx<T> *, cx<T> *, int, int, int, int) {}
+template <typename T> struct HpdGroup<T, 8, 7> {
+    static __device__ __forceinline__ void run(cx<T> (&)[7][H_NLC], const HpdLane<T> &, int &) {}
+};
+template <typename T> struct HpdGroup<T, 4, 14> {
+    static __device__ __forceinline__ void run(cx<T> (&)[14][H_NLC], const HpdLane<T> &, int &) {}
 };
 
 template <typename T, typename TIO> __device__ __forceinline__ cx<T> widen(cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); }
@@ -179,6 +200,8 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     cx<T> *Us = gs + S::US, *lb = gs + S::LB, *yb = gs + S::YB;
     T *db = (T *)(gs + S::DB);
     const int bar_id = grp + 1;
+    constexpr int RS = RunStride<T>::v;
+    const HpdLane<T> L = {lb, lb + pr * RS, lb + pc * RS, lb + (lane & 7) * RS + (lane >> 3), Us, lane, pr, pc, bar_id};
 
     for (int e = threadIdx.x; e < NSC * NSC; e += LANES * FPC) {
         int i = e / NSC, j = e - i * NSC;
@@ -242,8 +265,11 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
             }
         }
 
-        // ---- symmetric elimination, fully unrolled (compile-time recursion: every index is static) ----
-        HpdStep<T, TIO, PR, FPC, MINB, 0>::run(a, lb, Us, lane, pr, pc, bar_id);
+        // ---- symmetric elimination: compile-time recursion over the step groups (every register index is static) ----
+        {
+            int bo = 0;
+            HpdGroup<T, PR, 0>::run(a, L, bo);
+        }
         group_sync<LANES>(bar_id);
 
         // ---- back-substitution on the first warp of the group, then H = y - D z from registers ----
@@ -308,25 +334,24 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
     g_last_launches = 1;
     const int cfg = hpd_cfg();
 #define HPD_ARGS R, tx, rx, frame_stride, sigma2, H, n_frames, s
+    // measured on B200, 256 Ki frames (gpurun_out/hpd_probe6.log): f32 <4,12> 77.9 M frames/s (<8,8> 60.2, <4,8> 68.9);
+    // f64 <8,6> 34.1 M (<8,4> 31.7); FP32 storage + FP64 arithmetic <8,6> 35.4 M
     if (dt == WIFI_F32 && wide) {
         switch (cfg) {
-        case 1: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
-        default: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
+        case 1: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
+        default: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
         }
     }
     if (dt == WIFI_F32) {
         switch (cfg) {
         case 1: return launch_hpd<float, float, 4, 8, 1>(HPD_ARGS);
-        case 2: return launch_hpd<float, float, 4, 6, 2>(HPD_ARGS);
-        case 3: return launch_hpd<float, float, 4, 12, 1>(HPD_ARGS);
-        case 4: return launch_hpd<float, float, 8, 4, 2>(HPD_ARGS);
-        default: return launch_hpd<float, float, 8, 8, 1>(HPD_ARGS);
+        case 2: return launch_hpd<float, float, 8, 8, 1>(HPD_ARGS);
+        default: return launch_hpd<float, float, 4, 12, 1>(HPD_ARGS);
         }
     }
     switch (cfg) {
-    case 1: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
-    case 2: return launch_hpd<double, double, 8, 3, 1>(HPD_ARGS);
-    default: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
+    case 1: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
+    default: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
     }
 #undef HPD_ARGS
 }
