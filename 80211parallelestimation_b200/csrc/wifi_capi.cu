@@ -130,7 +130,7 @@ int wifi_create(int device, wifi_ctx **out)
               cudaMalloc(&ctx->img.W32, nW * sizeof(float2)) == cudaSuccess &&
               cudaMalloc(&ctx->img.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&ctx->img.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&ctx->img.B64, 112 * 112 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->img.B64, 112 * WIFI_DMMA_BS * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
               cudaHostAlloc(&ctx->h_info, 4096 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
@@ -213,6 +213,7 @@ static int install_filter(wifi_ctx *ctx, cudaStream_t s)
 {
     CK(launch_filter_install_simt(ctx->img, s));
     CK(launch_filter_install_tc(ctx->img, s));
+    CK(launch_filter_install_dmma(ctx->img, s));
     ctx->launches += 2;
     ctx->img.valid = 1;
     return WIFI_OK;
@@ -249,10 +250,11 @@ static int mmse_shared(wifi_ctx *ctx, wifi_dtype dt, const void *a, const void *
 {
     if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
     Timed t(ctx, s);
-    // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: CUDA-core kernel (tcgen05 has no FP64 kind).
-    // WIFI_B200_GEMM=simt selects the CUDA-core FP32 kernel for A/B measurements (both are sm_100a kernels).
-    if (dt == WIFI_F32 && !ctx->force_simt) CK(launch_mmse_shared_tc(ctx->img, a, rx, frame_stride, H, n, s));
-    else CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
+    // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: DMMA (tcgen05 has no FP64 kind).
+    // WIFI_B200_GEMM=simt selects the CUDA-core kernels for A/B measurements (all are sm_100a kernels).
+    if (ctx->force_simt) CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
+    else if (dt == WIFI_F32) CK(launch_mmse_shared_tc(ctx->img, a, rx, frame_stride, H, n, s));
+    else CK(launch_mmse_shared_dmma(ctx->img, a, rx, frame_stride, H, n, s));
     return WIFI_OK;
 }
 

@@ -1,0 +1,169 @@
+// wifi_gemm_dmma.cu -- FP64 shared-filter PS_MMSE on the FP64 tensor-core path (DMMA, mma.sync m8n8k4 f64).
+//
+//   H[n][53] = (rx/tx)[n][53] * W^T     as the real product  [n x 106] * [106 x 106],  K padded to 108, N to 112.
+//
+// tcgen05 has no FP64 kind, so the FP64 mode of the shared-filter estimator uses the warp-level DMMA.  Measured on B200
+// (profiles/microbench/dmma_peak.cu): every f64 mma shape lowers to DMMA.8x8x4 and sustains 37.0 TFLOP/s = 64 FMA/clk/SM,
+// the same ceiling as DFMA -- but one warp instruction carries 256 FMAs with two operand registers per lane, so the
+// pipe is fed without the LDS/issue pressure that held the CUDA-core kernel at 9.8 TFLOP/s.
+//
+// One persistent CTA per SM, 8 warps.  The filter image Bt[n][k] (n-major, row stride 116 doubles so the 8 rows a
+// fragment load touches fall in different bank groups) is copied to shared memory once.  Every warp owns tiles of 16
+// frames end to end -- there is no CTA-wide barrier after start-up, so the warps drift apart and one warp's global loads
+// overlap the other warps' DMMAs:
+//   * load tx/rx (16 x 53 complex, contiguous when frames are dense), LS divide, write the interleaved (re, im) row --
+//     which IS the real embedding of the A operand -- into the warp's private A buffer (row stride 108, k = 106, 107 zero);
+//   * 27 k-steps x (2 m8 tiles x 14 n8 tiles) DMMA.8x8x4, accumulators (56 doubles) in registers;
+//   * a lane's accumulator pair is one complex output (re, im): 16-byte streaming stores straight from registers.
+// Replaces multiply() utils.c:16-31 applied per frame (main.c:201-207 intent) in the FP64 mode.
+#include <algorithm>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+constexpr int DM_K = 108;               // 106 padded to a multiple of 4
+constexpr int DM_N = 112;               // 106 padded to a multiple of 8
+constexpr int DM_BS = WIFI_DMMA_BS;     // Bt row stride (doubles): 116 = 4 mod 16
+constexpr int DM_AS = 108;              // A row stride (doubles): 12 mod 16
+constexpr int DM_WARPS = 8;
+constexpr int DM_ROWS = 16;             // frames per warp tile
+constexpr int DM_NT = DM_N / 8;         // 14
+constexpr int DM_KT = DM_K / 4;         // 27
+
+// W (53 x 53 double2, row-major) -> Bt[n][k] = B[k][n], B = real embedding of W^T acting on interleaved (re, im) rows:
+//   out[2r] = sum_j Wre[r][j] y[2j] - Wim[r][j] y[2j+1],   out[2r+1] = sum_j Wim[r][j] y[2j] + Wre[r][j] y[2j+1]
+__global__ void filter_install_dmma_kernel(const double2 *__restrict__ W, double *__restrict__ Bt)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= DM_N * DM_BS) return;
+    int n = e / DM_BS, k = e - n * DM_BS;
+    double v = 0.0;
+    if (n < 2 * NSC && k < 2 * NSC) {
+        const double2 w = W[(n >> 1) * NSC + (k >> 1)];
+        v = (n & 1) ? ((k & 1) ? w.x : w.y) : ((k & 1) ? -w.y : w.x);
+    }
+    Bt[e] = v;
+}
+
+cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s)
+{
+    filter_install_dmma_kernel<<<(DM_N * DM_BS + 255) / 256, 256, 0, s>>>((const double2 *)img.W64, img.B64);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(DM_WARPS * 32, 1)
+    mmse_shared_dmma_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
+                            int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames)
+{
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    double *Bt = (double *)dm_smem;                                   // [112][116]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *As = Bt + DM_N * DM_BS + warp * (DM_ROWS * DM_AS);        // [16][108], private to the warp
+    const int g = lane >> 2, q = lane & 3;                            // fragment row group / position in group
+
+    {
+        const double2 *src = (const double2 *)Bt_g;
+        double2 *dst = (double2 *)Bt;
+        for (int e = threadIdx.x; e < DM_N * DM_BS / 2; e += DM_WARPS * 32) dst[e] = src[e];
+        if (lane < DM_ROWS) { As[lane * DM_AS + 106] = 0.0; As[lane * DM_AS + 107] = 0.0; }
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
+    for (int64_t tile = (int64_t)blockIdx.x * DM_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * DM_WARPS) {
+        const int64_t f0 = tile * DM_ROWS;
+        const int nf = (int)min((int64_t)DM_ROWS, n_frames - f0);
+        // ---- stage the warp's 16 rows: y = rx/tx (or H_ls) as interleaved doubles ----
+        __syncwarp();
+        constexpr int NEL = DM_ROWS * NSC;                            // 848 complex values
+#pragma unroll 1
+        for (int e0 = 0; e0 < NEL; e0 += 32 * 9) {
+            double2 tv[9], rv[9];
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int e = e0 + u * 32 + lane;
+                const int f = e / NSC, k = e - f * NSC;
+                tv[u] = make_double2(1.0, 0.0); rv[u] = make_double2(0.0, 0.0);
+                if (e < NEL && f < nf) {
+                    const int64_t off = (f0 + f) * frame_stride + k;
+                    tv[u] = ld_stream(a_in + off);
+                    if (FUSED) rv[u] = ld_stream(rx + off);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int e = e0 + u * 32 + lane;
+                const int f = e / NSC, k = e - f * NSC;
+                if (e < NEL) {
+                    double2 y = tv[u];
+                    if (FUSED) {
+                        if (f < nf) y = cdiv(rv[u], tv[u]); else y = make_double2(0.0, 0.0);     // per-block LS rx/tx (main.c:83)
+                    } else if (f >= nf) y = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2 *>(As + f * DM_AS + 2 * k) = y;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- 16 x 112 x 108 product on the FP64 tensor path ----
+        double c[2][DM_NT][2];
+#pragma unroll
+        for (int j = 0; j < DM_NT; ++j) c[0][j][0] = c[0][j][1] = c[1][j][0] = c[1][j][1] = 0.0;
+        const double *ap = As + g * DM_AS + q;
+        const double *bp = Bt + g * DM_BS + q;
+#pragma unroll 3
+        for (int kt = 0; kt < DM_KT; ++kt) {
+            const double a0 = ap[kt * 4], a1 = ap[8 * DM_AS + kt * 4];
+#pragma unroll
+            for (int j = 0; j < DM_NT; ++j) {
+                const double b = bp[j * 8 * DM_BS + kt * 4];
+                dmma884(c[0][j][0], c[0][j][1], a0, b);
+                dmma884(c[1][j][0], c[1][j][1], a1, b);
+            }
+        }
+
+        // ---- a lane's accumulator pair = one complex output: H[f][4 j + q] ----
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int f = mt * 8 + g;
+            if (f < nf) {
+                double2 *out = H + (f0 + f) * NSC + q;
+#pragma unroll
+                for (int j = 0; j < DM_NT; ++j)
+                    if (4 * j + q < NSC) st_stream(out + 4 * j, make_double2(c[mt][j][0], c[mt][j][1]));
+            }
+        }
+    }
+}
+
+cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
+                                    int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const size_t smem = sizeof(double) * (DM_N * DM_BS + DM_WARPS * DM_ROWS * DM_AS);
+    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DM_WARPS - 1) / DM_WARPS, 148);
+    cudaError_t e;
+    if (rx) {
+        e = cudaFuncSetAttribute(mmse_shared_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mmse_shared_dmma_kernel<true><<<grid, DM_WARPS * 32, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
+                                                                        (double2 *)H, n_frames);
+    } else {
+        e = cudaFuncSetAttribute(mmse_shared_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mmse_shared_dmma_kernel<false><<<grid, DM_WARPS * 32, smem, s>>>(img.B64, (const double2 *)a, nullptr, NSC, (double2 *)H, n_frames);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include "../../include/wifi_b200.h"
 
+#define WIFI_DMMA_BS 116   /* row stride of the FP64 filter image in doubles (4 mod 16: conflict-free fragment loads) */
+
 namespace wifi {
 
 // interpolation weight tables: H_k = sum_i w[est][k][i] * Hp_i  (est: 0 linear, 1 cubic, 2 sinc)
@@ -18,7 +20,7 @@ struct FilterImages {
     float *W32;      // [53][53] float2 (rounded)
     float *Bhi;      // tf32 "hi" image of the real embedding, UMMA canonical K-major no-swizzle layout [112 x 112]
     float *Blo;      // tf32 "lo" image (W - hi)
-    double *B64;     // real embedding for the FP64 path, [112][112] row-major (n-major, k contiguous)
+    double *B64;     // real embedding for the FP64 DMMA path, Bt[112][WIFI_DMMA_BS] (n-major, k contiguous, rows padded)
     int valid;
 };
 
@@ -44,6 +46,9 @@ cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, cons
 cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // W64 -> Bhi/Blo (UMMA canonical layout)
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                   int64_t n_frames, cudaStream_t s);             // FP32 I/O, 3xTF32 on tcgen05
+cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s);   // W64 -> B64
+cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
+                                    int64_t n_frames, cudaStream_t s);           // FP64 I/O, DMMA m8n8k4
 cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch,
                            cudaStream_t s);
 cudaError_t launch_chermitian(wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch, cudaStream_t s);
