@@ -8,12 +8,14 @@
 // pipe is fed without the LDS/issue pressure that held the CUDA-core kernel at 9.8 TFLOP/s.
 //
 // One persistent CTA per SM, 8 warps.  The filter image Bt[n][k] (n-major, row stride 116 doubles so the 8 rows a
-// fragment load touches fall in different bank groups) is copied to shared memory once.  Every warp owns tiles of 16
+// fragment load touches fall in different bank groups) is copied to shared memory once.  Every warp owns tiles of 8
 // frames end to end -- there is no CTA-wide barrier after start-up, so the warps drift apart and one warp's global loads
 // overlap the other warps' DMMAs:
-//   * load tx/rx (16 x 53 complex, contiguous when frames are dense), LS divide, write the interleaved (re, im) row --
-//     which IS the real embedding of the A operand -- into the warp's private A buffer (row stride 108, k = 106, 107 zero);
-//   * 27 k-steps x (2 m8 tiles x 14 n8 tiles) DMMA.8x8x4, accumulators (56 doubles) in registers;
+//   * tx/rx of the warp's NEXT tile (8 x 53 complex each, contiguous when frames are dense) are loaded into registers
+//     before the DMMA loop of the current tile and consumed after it, so HBM latency hides behind ~380 DMMAs;
+//   * LS divide, write the interleaved (re, im) row -- which IS the real embedding of the A operand -- into the warp's
+//     private A buffer (row stride 108, k = 106, 107 zero);
+//   * 27 k-steps x 14 n8 tiles DMMA.8x8x4, accumulators (28 doubles) in registers;
 //   * a lane's accumulator pair is one complex output (re, im): 16-byte streaming stores straight from registers.
 // Replaces multiply() utils.c:16-31 applied per frame (main.c:201-207 intent) in the FP64 mode.
 #include <algorithm>
@@ -27,7 +29,8 @@ constexpr int DM_N = 112;               // 106 padded to a multiple of 8
 constexpr int DM_BS = WIFI_DMMA_BS;     // Bt row stride (doubles): 116 = 4 mod 16
 constexpr int DM_AS = 108;              // A row stride (doubles): 12 mod 16
 constexpr int DM_WARPS = 8;
-constexpr int DM_ROWS = 16;             // frames per warp tile
+constexpr int DM_ROWS = 8;              // frames per warp tile (one m8 fragment)
+constexpr int DM_NLD = (DM_ROWS * NSC + 31) / 32;   // 14 complex values per lane and input
 constexpr int DM_NT = DM_N / 8;         // 14
 constexpr int DM_KT = DM_K / 4;         // 27
 
@@ -57,6 +60,30 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// raw inputs of one 8-frame tile, spread over the warp: element e = 32 u + lane  ->  frame e / 53, sub-carrier e % 53
+template <bool FUSED> struct DmRaw {
+    double2 t[DM_NLD];
+    double2 r[FUSED ? DM_NLD : 1];
+};
+
+template <bool FUSED>
+__device__ __forceinline__ void dm_load_raw(DmRaw<FUSED> &raw, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
+                                            int64_t frame_stride, int64_t f0, int nf, int lane)
+{
+#pragma unroll
+    for (int u = 0; u < DM_NLD; ++u) {
+        const int e = u * 32 + lane;
+        const int f = e / NSC, k = e - f * NSC;
+        raw.t[u] = make_double2(FUSED ? 1.0 : 0.0, 0.0);
+        if (FUSED) raw.r[u] = make_double2(0.0, 0.0);
+        if (e < DM_ROWS * NSC && f < nf) {
+            const int64_t off = (f0 + f) * frame_stride + k;
+            raw.t[u] = ld_stream(a_in + off);
+            if (FUSED) raw.r[u] = ld_stream(rx + off);
+        }
+    }
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(DM_WARPS * 32, 1)
     mmse_shared_dmma_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
@@ -65,9 +92,14 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 1)
     extern __shared__ __align__(16) unsigned char dm_smem[];
     double *Bt = (double *)dm_smem;                                   // [112][116]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *As = Bt + DM_N * DM_BS + warp * (DM_ROWS * DM_AS);        // [16][108], private to the warp
-    const int g = lane >> 2, q = lane & 3;                            // fragment row group / position in group
+    double *As = Bt + DM_N * DM_BS + warp * (DM_ROWS * DM_AS);        // [8][108], private to the warp
+    const int g = lane >> 2, q = lane & 3;                            // fragment row / position in the group of 4
 
+    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
+    const int64_t tstep = (int64_t)gridDim.x * DM_WARPS;
+    int64_t tile = (int64_t)blockIdx.x * DM_WARPS + warp;
+    DmRaw<FUSED> raw;
+    if (tile < n_tiles) dm_load_raw<FUSED>(raw, a_in, rx, frame_stride, tile * DM_ROWS, (int)min((int64_t)DM_ROWS, n_frames - tile * DM_ROWS), lane);
     {
         const double2 *src = (const double2 *)Bt_g;
         double2 *dst = (double2 *)Bt;
@@ -75,70 +107,53 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 1)
         if (lane < DM_ROWS) { As[lane * DM_AS + 106] = 0.0; As[lane * DM_AS + 107] = 0.0; }
     }
     __syncthreads();
+    // Warps w and w + 4 share a scheduler and its FP64 pipe.  Started together they stay in lockstep (both convert, then
+    // both issue DMMAs); offset by about half a tile period they alternate and the pipe never waits for a conversion.
+    if (warp >= 4 && tile + tstep < n_tiles) __nanosleep(2500);
 
-    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
-    for (int64_t tile = (int64_t)blockIdx.x * DM_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * DM_WARPS) {
+    for (; tile < n_tiles; tile += tstep) {
         const int64_t f0 = tile * DM_ROWS;
         const int nf = (int)min((int64_t)DM_ROWS, n_frames - f0);
-        // ---- stage the warp's 16 rows: y = rx/tx (or H_ls) as interleaved doubles ----
-        __syncwarp();
-        constexpr int NEL = DM_ROWS * NSC;                            // 848 complex values
-#pragma unroll 1
-        for (int e0 = 0; e0 < NEL; e0 += 32 * 9) {
-            double2 tv[9], rv[9];
+        // ---- y = rx/tx (or H_ls) of this tile, held in registers since the previous iteration -> A rows ----
 #pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int e = e0 + u * 32 + lane;
-                const int f = e / NSC, k = e - f * NSC;
-                tv[u] = make_double2(1.0, 0.0); rv[u] = make_double2(0.0, 0.0);
-                if (e < NEL && f < nf) {
-                    const int64_t off = (f0 + f) * frame_stride + k;
-                    tv[u] = ld_stream(a_in + off);
-                    if (FUSED) rv[u] = ld_stream(rx + off);
+        for (int u = 0; u < DM_NLD; ++u) {
+            const int e = u * 32 + lane;
+            const int f = e / NSC, k = e - f * NSC;
+            if (e < DM_ROWS * NSC) {
+                double2 y = raw.t[u];
+                if (FUSED) {                                          // per-block LS rx/tx (main.c:83); rows >= nf: 0/1 = 0
+                    const double2 t = raw.t[u], r = raw.r[u];
+                    const double inv = 1.0 / (t.x * t.x + t.y * t.y);  // one division: the FP64 pipe is the DMMA pipe
+                    y = make_double2((r.x * t.x + r.y * t.y) * inv, (r.y * t.x - r.x * t.y) * inv);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int e = e0 + u * 32 + lane;
-                const int f = e / NSC, k = e - f * NSC;
-                if (e < NEL) {
-                    double2 y = tv[u];
-                    if (FUSED) {
-                        if (f < nf) y = cdiv(rv[u], tv[u]); else y = make_double2(0.0, 0.0);     // per-block LS rx/tx (main.c:83)
-                    } else if (f >= nf) y = make_double2(0.0, 0.0);
-                    *reinterpret_cast<double2 *>(As + f * DM_AS + 2 * k) = y;
-                }
+                *reinterpret_cast<double2 *>(As + f * DM_AS + 2 * k) = y;
             }
         }
         __syncwarp();
+        // ---- next tile's inputs: in flight during the DMMA loop below ----
+        if (tile + tstep < n_tiles)
+            dm_load_raw<FUSED>(raw, a_in, rx, frame_stride, (tile + tstep) * DM_ROWS, (int)min((int64_t)DM_ROWS, n_frames - (tile + tstep) * DM_ROWS), lane);
 
-        // ---- 16 x 112 x 108 product on the FP64 tensor path ----
-        double c[2][DM_NT][2];
+        // ---- 8 x 112 x 108 product on the FP64 tensor path ----
+        double c[DM_NT][2];
 #pragma unroll
-        for (int j = 0; j < DM_NT; ++j) c[0][j][0] = c[0][j][1] = c[1][j][0] = c[1][j][1] = 0.0;
+        for (int j = 0; j < DM_NT; ++j) c[j][0] = c[j][1] = 0.0;
         const double *ap = As + g * DM_AS + q;
         const double *bp = Bt + g * DM_BS + q;
 #pragma unroll 3
         for (int kt = 0; kt < DM_KT; ++kt) {
-            const double a0 = ap[kt * 4], a1 = ap[8 * DM_AS + kt * 4];
+            const double a0 = ap[kt * 4];
 #pragma unroll
-            for (int j = 0; j < DM_NT; ++j) {
-                const double b = bp[j * 8 * DM_BS + kt * 4];
-                dmma884(c[0][j][0], c[0][j][1], a0, b);
-                dmma884(c[1][j][0], c[1][j][1], a1, b);
-            }
+            for (int j = 0; j < DM_NT; ++j) dmma884(c[j][0], c[j][1], a0, bp[j * 8 * DM_BS + kt * 4]);
         }
+        __syncwarp();                                                 // all lanes are done with this tile's A rows
 
-        // ---- a lane's accumulator pair = one complex output: H[f][4 j + q] ----
+        // ---- a lane's accumulator pair = one complex output: H[f0 + g][4 j + q] ----
+        if (g < nf) {
+            double2 *out = H + (f0 + g) * NSC + q;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int f = mt * 8 + g;
-            if (f < nf) {
-                double2 *out = H + (f0 + f) * NSC + q;
-#pragma unroll
-                for (int j = 0; j < DM_NT; ++j)
-                    if (4 * j + q < NSC) st_stream(out + 4 * j, make_double2(c[mt][j][0], c[mt][j][1]));
-            }
+            for (int j = 0; j < DM_NT; ++j)
+                if (4 * j + q < NSC) st_stream(out + 4 * j, make_double2(c[j][0], c[j][1]));
         }
     }
 }
