@@ -43,6 +43,7 @@ SIGNATURES = {
     "wifi_synth_frames": [_vp, _i, _u64, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "wifi_synth_covariance": [_vp, _vp],
     "wifi_error_stats": [_vp, _i, _vp, _vp, _i64, _vp],
+    "wifi_measure_peak": [_vp, _i, C.POINTER(_d)],
     "wifi_lt_ls_host": [_vp, _i, _vp, _vp, _vp, _i64],
     "wifi_ps_host": [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i64],
     "wifi_equalize_host": [_vp, _i, _vp, _vp, _vp, _vp, _i64],

@@ -379,6 +379,15 @@ class WifiContext:
         self._ck(self.lib.wifi_error_stats(self.h, dt, a.ptr, b.ptr, a.size, stats.data_ptr()))
         return stats
 
+    def measure_peaks(self):
+        """Measured ceilings of this GPU: FP32/FP64 FMA and FP64 DMMA in TFLOP/s, streaming copy in GB/s."""
+        out = {}
+        for which, name in enumerate(("fp32_fma_tflops", "fp64_fma_tflops", "fp64_dmma_tflops", "copy_gbs")):
+            v = C.c_double()
+            self._ck(self.lib.wifi_measure_peak(self.h, which, C.byref(v)))
+            out[name] = v.value
+        return out
+
 
 _default = None
 

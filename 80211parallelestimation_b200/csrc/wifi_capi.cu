@@ -395,6 +395,14 @@ int wifi_error_stats(wifi_ctx *ctx, wifi_dtype dt, const void *H, const void *Hr
     return WIFI_OK;
 }
 
+int wifi_measure_peak(wifi_ctx *ctx, int which, double *value)
+{
+    ENTER();
+    NEED(which >= 0 && which <= 3 && value);
+    CK(measure_peak(which, value, ctx->stream));
+    return WIFI_OK;
+}
+
 // ---- host-pointer pipeline ------------------------------------------------------------------------------
 int wifi_host_alloc(void **p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? WIFI_OK : WIFI_ERR_NOMEM; }
 int wifi_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? WIFI_OK : WIFI_ERR_CUDA; }

@@ -63,6 +63,9 @@ cudaError_t launch_synth(wifi_dtype dt, uint64_t seed, int64_t first, int64_t n,
 cudaError_t launch_synth_cov(void *R64, cudaStream_t s);
 cudaError_t launch_error_stats(wifi_dtype dt, const void *H, const void *Href, int64_t n_elems, double *stats, cudaStream_t s);
 
+// measured ceilings (wifi_peaks.cu): which = 0 FP32 FMA, 1 FP64 FMA, 2 FP64 DMMA (TFLOP/s), 3 streaming copy (GB/s)
+cudaError_t measure_peak(int which, double *value, cudaStream_t s);
+
 // number of kernel launches the last launcher call issued (for gpu_launches accounting)
 extern thread_local int g_last_launches;
 

@@ -33,6 +33,8 @@ METRIC = "MMSE channel estimates/sec (53-subcarrier frames)"
 UNIT = "frames/s"
 OW2 = 9.6172e-08
 AMP = 8.875
+# DRAM bytes of ONE mmse_shared_tc launch over 1 Mi frames from the ncu --set full capture (0.889 GB read + 0.403 GB written)
+NCU_DRAM_BYTES_PER_MI_FRAMES = 1.2925e9
 
 
 def measured_peaks():
@@ -73,7 +75,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def result(self):
         self.stop_flag = True
@@ -164,12 +166,13 @@ def run_reference(args):
         "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def extras_block(wifi, ctx, torch, peaks, n_frames, steps, warmup):
-    """Secondary kernels: frames/s + roofline fraction each (algorithmic bytes/flops per frame from SURVEY 8(d))."""
+def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
+    """Secondary kernels: frames/s + roofline fraction each (algorithmic bytes/flops per frame from SURVEY 8(d)).
+    FLOP fractions are given against the nominal peak and against the FMA / DMMA rate measured on this GPU (mp)."""
     out = {}
     hbm = peaks["hbm_gbs"]
 
-    def rate(fn, n, bytes_per_frame=None, flops_per_frame=None, peak_tflops=None):
+    def rate(fn, n, bytes_per_frame=None, flops_per_frame=None, peak_tflops=None, measured_tflops=None):
         total, per = time_steps(fn, steps, warmup, torch)
         ms = float(np.median(per))
         r = {"frames_per_s": n / (ms * 1e-3), "ms": ms, "n_frames": n}
@@ -183,6 +186,9 @@ def extras_block(wifi, ctx, torch, peaks, n_frames, steps, warmup):
             if peak_tflops:
                 r["peak_tflops_nominal"] = peak_tflops
                 r["flop_frac_of_nominal"] = r["TFLOPs"] / peak_tflops
+            if measured_tflops:
+                r["peak_tflops_measured"] = measured_tflops
+                r["flop_frac_of_measured"] = r["TFLOPs"] / measured_tflops
         return r
 
     for prec, cbytes in (("f32", 8), ("f64", 16)):
@@ -201,20 +207,24 @@ def extras_block(wifi, ctx, torch, peaks, n_frames, steps, warmup):
         del fr
         Hm = torch.empty_like(tx0)
         if prec == "f64":
-            out["mmse_shared_f64"] = rate(lambda: ctx.mmse_shared(tx0, rx0, out=Hm), n, 159 * cbytes, 22472, 37.0)
+            out["mmse_shared_f64"] = rate(lambda: ctx.mmse_shared(tx0, rx0, out=Hm), n, 159 * cbytes, 22472, 37.2, mp["fp64_dmma_tflops"])
         # per-frame solve: 256 Ki frames (configs[3])
         npf = min(n, 1 << 18)
         s2 = ctx.synth_frames(npf, prec, per_frame_sigma=True, want=("sigma2",))["sigma2"]
         R = ctx.synth_covariance()
         Rp = R if prec == "f64" else R.to(torch.complex64)
         Hp = torch.empty_like(tx0[:npf])
+        nom, meas = (74.4, mp["fp32_fma_tflops"]) if prec == "f32" else (37.2, mp["fp64_fma_tflops"])
         out["mmse_perframe_hpd_" + prec] = rate(
-            lambda: ctx.mmse_perframe(Rp, tx0[:npf], rx0[:npf], s2, flags=wifi.SOLVE_HPD, out=Hp), npf, 159 * cbytes, 441949,
-            74.0 if prec == "f32" else 37.0)
+            lambda: ctx.mmse_perframe(Rp, tx0[:npf], rx0[:npf], s2, flags=wifi.SOLVE_HPD, out=Hp), npf, 159 * cbytes, 441949, nom, meas)
+        if prec == "f32":   # FP32 storage, FP64 arithmetic: the FP32-I/O mode that meets the 1e-4 accuracy bound
+            out["mmse_perframe_hpd_f32_wide"] = rate(
+                lambda: ctx.mmse_perframe(Rp, tx0[:npf], rx0[:npf], s2, flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE, out=Hp), npf, 159 * cbytes,
+                441949, 37.2, mp["fp64_fma_tflops"])
         npv = min(npf, 1 << 15)
         out["mmse_perframe_pivot_" + prec] = rate(
             lambda: ctx.mmse_perframe(Rp, tx0[:npv], rx0[:npv], s2[:npv], flags=wifi.SOLVE_PIVOT, out=Hp[:npv]), npv, 159 * cbytes, 441949,
-            74.0 if prec == "f32" else 37.0)
+            nom, meas)
         del tx0, rx0, Hm, Hp
         torch.cuda.empty_cache()
     return out
@@ -255,7 +265,6 @@ def run_ours(args):
     l0 = ctx.launches
     total_ms, per = time_steps(step, args.steps, args.warmup, torch, dist)
     launches = (ctx.launches - l0) * args.steps // (args.steps + args.warmup)
-    clocks = sampler.result()
     t = torch.tensor([total_ms], dtype=torch.float64, device=tx.device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,9 +294,11 @@ def run_ours(args):
         dist.barrier()
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = n_total * e2e_steps / float(te[0])
+    clocks = sampler.result()          # sampled every 5 ms from the first warm-up step to the end of the e2e region
     e2e_ok = bool(np.allclose(hH[:1024], H[:1024].cpu().numpy(), rtol=1e-5, atol=1e-8))
 
     if rank == 0:
+        mp = ctx.measure_peaks()           # on-box FP32/FP64 FMA, DMMA and copy ceilings
         bytes_per_frame = 159 * 8          # read tx 53c + rx 53c, write H 53c, FP32 complex (fused LS + filter)
         achieved = n_local * bytes_per_frame / (kernel_ms * 1e-3) / 1e9
         line = {
@@ -299,12 +310,17 @@ def run_ours(args):
                        "frames_per_gpu": n_local, "frames_total": n_total, "l2_policy": "inputs per pass (%.2f GB) >> 126 MB L2, no flush" % (n_local * bytes_per_frame / 1e9),
                        "parallelism": "frame-sharded x%d, no data-path collective" % world, "filter_form_ms": filter_ms},
             "roofline": {"bound": "hbm", "kernel": "mmse_shared (fused LS divide + 53x53 complex filter GEMM)", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": int(NCU_DRAM_BYTES_PER_MI_FRAMES * n_local / (1 << 20)),
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 1 Mi frames "
+                                           "(profiles/r01b_ncu_mmse_shared_tc.txt), scaled to this launch's frame count",
+                         "peak_source": peaks["source"],
                          "algorithmic_bytes_per_frame": bytes_per_frame, "kernel_ms": kernel_ms,
                          "tensor_TFLOPs_3xTF32": n_local * 3 * 2 * 112 * 112 / (kernel_ms * 1e-3) / 1e12},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_local * NSC * 8), "d2h_bytes_per_step": int(n_local * NSC * 8),
                     "steps": e2e_steps, "matches_device_result": e2e_ok, "api": "WifiContext.mmse_shared(numpy pinned) -> wifi_mmse_shared_host"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "measured_peaks": dict(mp, nominal={"fp32_fma_tflops": 74.4, "fp64_fma_tflops": 37.2, "fp64_dmma_tflops": 37.2,
+                                                "note": "148 SMs x 128 (FP32) / 64 (FP64) FMA lanes x 2 x 1.965 GHz"}),
             "accuracy": {"nmse_vs_true_channel": stats["nmse"], "max_abs_err": stats["max_abs_err"], "count": stats["count"]},
         }
         if world == 1 and not args.no_cpu:
@@ -312,7 +328,7 @@ def run_ours(args):
             line["cpu_baseline"] = cb
         if world == 1 and not args.no_extras:
             del htx, hrx, hH
-            line["extras"] = extras_block(wifi, ctx, torch, peaks, min(n_local, 1 << 20), max(3, min(args.steps, 10)), 3)
+            line["extras"] = extras_block(wifi, ctx, torch, peaks, mp, min(n_local, 1 << 20), max(3, min(args.steps, 10)), 3)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -146,6 +146,10 @@ int wifi_synth_covariance(wifi_ctx *ctx, void *R_f64);
 /* per-shard error statistics, stats[4] (device doubles): sum|H-Href|^2, sum|Href|^2, count, max|H-Href| */
 int wifi_error_stats(wifi_ctx *ctx, wifi_dtype dt, const void *H, const void *H_ref, int64_t n_elems, double *stats);
 
+/* measured ceilings of this GPU, for the roofline fractions bench.py reports (blocking; a few ms each):
+ * which = 0 FP32 FMA TFLOP/s, 1 FP64 FMA TFLOP/s, 2 FP64 DMMA (mma.sync m8n8k4) TFLOP/s, 3 streaming copy GB/s */
+int wifi_measure_peak(wifi_ctx *ctx, int which, double *value);
+
 /* ---- host-pointer variants: H2D + kernels + D2H inside, chunked and double-buffered ---- */
 int wifi_lt_ls_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n_frames);
 int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbols, const void *rx_symbols,
