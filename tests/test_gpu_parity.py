@@ -151,6 +151,34 @@ def test_equalize(ctx, oracle, gold, prec):
         assert rel_err(got, oracle.equalize(r32(rxs, prec), r32(a, prec), r32(b, prec)), floor=1e-6) < TOL[prec]
 
 
+@pytest.mark.parametrize("n", [1, 3, 64, 1001])
+def test_f32_views_at_odd_frames(ctx, oracle, n):
+    """An FP32 view that starts at an odd frame is only 8-byte aligned (a frame is 424 B): the 16-byte vector kernels
+    must not be used on it; every estimator still has to match."""
+    import torch
+    fr = synth.make_frames(n + 1, seed=4242 + n, dtype=np.complex64)
+    d = {k: dev(fr[k]) for k in ("tx_pre", "rx_pre", "tx_symb", "rx_symb")}
+    v = {k: d[k][1:] for k in d}                                   # views: base + 424 B (preambles) / + 6360 B (frames)
+    assert v["tx_pre"].data_ptr() % 16 == 8
+    h = {k: fr[k][1:] for k in ("tx_pre", "rx_pre", "tx_symb", "rx_symb")}
+    ref_lt = oracle.lt_ls(h["tx_pre"].astype(complex), h["rx_pre"].astype(complex))
+    out_lt = torch.empty((n + 1, NSC), dtype=torch.complex64, device="cuda")[1:]
+    lt = ctx.lt_ls(v["tx_pre"], v["rx_pre"], out=out_lt)
+    assert rel_err(host(lt), ref_lt) < TOL["f32"]
+    ps = ctx.ps(v["tx_symb"], v["rx_symb"], ("linear",))
+    ref_ps = oracle.ps_linear(h["tx_symb"][:, 0, :].astype(complex), h["rx_symb"][:, 0, :].astype(complex))
+    assert rel_err(host(ps["linear"]), ref_ps) < TOL["f32"]
+    eq = host(ctx.equalize(v["rx_symb"], lt, ps["linear"]))
+    ref_eq = oracle.equalize(h["rx_symb"].astype(complex), host(lt).astype(complex), host(ps["linear"]).astype(complex))
+    assert rel_err(eq, ref_eq, floor=1e-6) < TOL["f32"]
+    R = synth.channel_covariance()
+    dd = synth.OW2 / np.abs(h["tx_symb"][0, 0].astype(complex)) ** 2
+    W = host(ctx.mmse_filter_form(dev(R), dev(dd)))
+    got = host(ctx.mmse_shared(v["tx_symb"].reshape(-1), v["rx_symb"].reshape(-1), frame_stride=15 * NSC, n_frames=n))
+    ref = oracle.mmse_apply(W, h["rx_symb"][:, 0, :].astype(complex) / h["tx_symb"][:, 0, :].astype(complex))
+    assert rel_err(got, ref, 1e-2) < TOL["f32"]
+
+
 # ------------------------------------------------------------------ MMSE, shared filter
 def test_mmse_filter_form(ctx, oracle):
     R = synth.channel_covariance()
