@@ -22,12 +22,14 @@ def main():
         outs = {k: torch.empty_like(tx0) for k in ("linear", "cubic", "sinc")}
         eq = torch.empty_like(fr["rx_symb"][: n // 8])
         Rp = R if prec == "f64" else R.to(torch.complex64)
-        for rep in range(2):
+        for rep in range(int(os.environ.get('PROFILE_REPS', '2'))):
             if want("lt_ls"): ctx.lt_ls(fr["tx_pre"], fr["rx_pre"], out=H)
             if want("ps_interp"): ctx.ps(fr["tx_symb"], fr["rx_symb"], out=outs)
             if want("equalize"): ctx.equalize(fr["rx_symb"][: n // 8], H[: n // 8], outs["linear"][: n // 8], out=eq)
             if want("mmse_shared"): ctx.mmse_shared(tx0, rx0, out=H)
             if want("mmse_hpd"): ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD, out=H[: 1 << 16])
+            if want("mmse_hpd") and prec == "f32":
+                ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE, out=H[: 1 << 16])
         torch.cuda.synchronize()
         del fr, tx0, rx0, H, outs, eq
         torch.cuda.empty_cache()
