@@ -159,11 +159,11 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     cb["value"] = val
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f80 (x87 long double)",
         "data": "synthetic", "config": {"workload": "configs[2]: shared-filter PS_MMSE, bounded sample of %d frames per step on the host cores" % n},
-        "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
@@ -329,13 +329,30 @@ def run_ours(args):
         if world == 1 and not args.no_extras:
             del htx, hrx, hH
             line["extras"] = extras_block(wifi, ctx, torch, peaks, mp, min(n_local, 1 << 20), max(3, min(args.steps, 10)), 3)
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints to fd 1 (NCCL's version banner, ...)
+    was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
