@@ -28,6 +28,7 @@ SIGNATURES = {
     "wifi_lt_ls_batch": [_vp, _i, _vp, _vp, _vp, _i64],
     "wifi_ps_batch": [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i64],
     "wifi_equalize_batch": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
+    "wifi_frontend_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_filter_form": [_vp, _vp, _vp, _vp],
     "wifi_mmse_filter_set": [_vp, _vp],
     "wifi_mmse_shared_apply_batch": [_vp, _i, _vp, _vp, _i64],
@@ -47,6 +48,7 @@ SIGNATURES = {
     "wifi_lt_ls_host": [_vp, _i, _vp, _vp, _vp, _i64],
     "wifi_ps_host": [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i64],
     "wifi_equalize_host": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
+    "wifi_frontend_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_filter_form_host": [_vp, _vp, _vp, _vp],
     "wifi_mmse_shared_host": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
     "wifi_mmse_perframe_host": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],

@@ -168,6 +168,24 @@ class WifiContext:
     def ps_sinc(self, tx, rx, **kw):
         return self.ps(tx, rx, ("sinc",), **kw)["sinc"]
 
+    def frontend(self, packet, lptot, want_ow2=True, out=None):
+        """Receiver front-end (WiFi_blocks_extraction.m, WiFi_RX.m:19-31) for one side of n frames: packet [n][1200],
+        lptot [n][160] -> (symb [n][15][53], pre_fft [n][53], ow2 [n] or None)."""
+        pk, lp = _Arg(packet), _Arg(lptot)
+        dev, dt = _same(pk, lp)
+        n = pk.size // 1200
+        if lp.size != n * 160:
+            raise ValueError("packet is [n][1200] and lptot [n][160] for the same n")
+        if out is not None:
+            symb, pre, ow2 = out
+        else:
+            symb, pre = pk.empty_like((n, NBLK, NSC)), pk.empty_like((n, NSC))
+            ow2 = pk.empty_like((n,), real=True) if want_ow2 else None
+        self._sync_stream(dev)
+        fn = self.lib.wifi_frontend_batch if dev else self.lib.wifi_frontend_host
+        self._ck(fn(self.h, dt, pk.ptr, lp.ptr, _ptr(symb), _ptr(pre), _ptr(ow2), n))
+        return symb, pre, ow2
+
     def equalize(self, rx_frames, H_lt, H_ps, out=None):
         """WiFi_Equalization.m: rx [n][15][53], H_lt / H_ps [n][53] -> [n][15][53]."""
         rx, a, b = _Arg(rx_frames), _Arg(H_lt), _Arg(H_ps)

@@ -208,6 +208,16 @@ int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx, const void
     return WIFI_OK;
 }
 
+int wifi_frontend_batch(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft, void *ow2, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (packet && lptot && symb && pre_fft)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    NEED(((((uintptr_t)packet) | ((uintptr_t)lptot)) & 15) == 0);      // samples are read as 16-byte vectors
+    Timed t(ctx, ctx->stream);
+    CK(launch_frontend(dt, packet, lptot, symb, pre_fft, ow2, n, ctx->stream));
+    return WIFI_OK;
+}
+
 // ---- MMSE ---------------------------------------------------------------------------------------
 static int install_filter(wifi_ctx *ctx, cudaStream_t s)
 {
@@ -529,6 +539,21 @@ int wifi_equalize_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx, const void 
                              CK(launch_equalize(dt, d[0], d[1], d[2], d[3], nc, s));
                              return (int)WIFI_OK;
                          });
+}
+
+int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft, void *ow2, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (packet && lptot && symb && pre_fft)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t es = esize(dt);
+    std::vector<Arr> arrs = {in_arr(packet, WIFI_PACKET * es, WIFI_PACKET * es), in_arr(lptot, WIFI_LPTOT * es, WIFI_LPTOT * es),
+                             out_arr(symb, WIFI_FRAME * es), out_arr(pre_fft, WIFI_NSC * es)};
+    if (ow2) arrs.push_back(out_arr(ow2, es / 2));
+    return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+        Timed t(ctx, s);
+        CK(launch_frontend(dt, d[0], d[1], d[2], d[3], ow2 ? d[4] : nullptr, nc, s));
+        return (int)WIFI_OK;
+    });
 }
 
 int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R, const double *d, void *W_out)

@@ -30,6 +30,10 @@ cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, 
 cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n_frames,
                             cudaStream_t s);
 
+// receiver front-end (wifi_frontend.cu): packet [n][1200], lptot [n][160] -> symb [n][15][53], pre_fft [n][53], ow2 [n] (may be NULL)
+cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft, void *ow2,
+                            int64_t n_frames, cudaStream_t s);
+
 // dense solves (wifi_solve.cu)
 cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s);
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);

@@ -205,6 +205,14 @@ def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
         del eq
         tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
         del fr
+        # receiver front-end: 15 x 64 packet samples + 128 lptot samples in, 15 x 53 + 53 values + ow2 out
+        nfe = min(n, 1 << 18)
+        cdt, rdt = (torch.complex64, torch.float32) if prec == "f32" else (torch.complex128, torch.float64)
+        pk = torch.randn(nfe, 1200, dtype=cdt, device=tx0.device); lp = torch.randn(nfe, 160, dtype=cdt, device=tx0.device)
+        fe_out = (torch.empty(nfe, NBLK, NSC, dtype=cdt, device=tx0.device), torch.empty(nfe, NSC, dtype=cdt, device=tx0.device),
+                  torch.empty(nfe, dtype=rdt, device=tx0.device))
+        out["frontend_" + prec] = rate(lambda: ctx.frontend(pk, lp, out=fe_out), nfe, (1088 + 848) * cbytes + cbytes // 2)
+        del pk, lp, fe_out
         Hm = torch.empty_like(tx0)
         if prec == "f64":
             out["mmse_shared_f64"] = rate(lambda: ctx.mmse_shared(tx0, rx0, out=Hm), n, 159 * cbytes, 22472, 37.2, mp["fp64_dmma_tflops"])

@@ -37,6 +37,8 @@ extern "C" {
 #define WIFI_NBLK 15       /* OFDMBLK,  utils.h:15 */
 #define WIFI_FRAME (WIFI_NSC * WIFI_NBLK) /* SIZESYMBOL, utils.h:12 */
 #define WIFI_DC 26
+#define WIFI_PACKET 1200   /* time samples per frame: 15 x (16 CP + 64), WiFi_RX.m:11-14 */
+#define WIFI_LPTOT 160     /* long-training field samples (32 GI + 2 x 64) */
 #define WIFI_P0 5          /* utils.h:16-19 */
 #define WIFI_P1 19
 #define WIFI_P2 33
@@ -97,6 +99,15 @@ int wifi_ps_batch(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbol
 int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
                         void *eq, int64_t n_frames);
 
+/* ---- receiver front-end: time samples -> the estimators' inputs ------------------------------------
+ * WiFi_blocks_extraction.m:5-10 and WiFi_RX.m:19-31, for one side (tx or rx) of n frames:
+ *   packet [n][1200] = 15 OFDM blocks of 16 cyclic-prefix + 64 samples;  lptot [n][160] = long-training field
+ *   symb [n][15][53] = keep53(circshift(fft64(block without CP), 26));   pre_fft [n][53] = the same of (p1 + p2)/2,
+ *   p1 = lptot[96..159], p2 = lptot[32..95];   ow2 [n] (real, optional) = sum |p2 - p1|^2 / 128.
+ * packet and lptot must be 16-byte aligned. */
+int wifi_frontend_batch(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft,
+                        void *ow2, int64_t n_frames);
+
 /* ---- PS_MMSE, intended formula  H = R (R + s2 (X X^H)^-1)^-1 (rx/tx) ------------- */
 /* Shared-filter case.  Form W = R (R + diag(d))^-1 once in FP64 on the device
  * (R: 53x53 double2 row-major, d: 53 doubles = s2/|x_k|^2, W_out: optional 53x53 double2)
@@ -156,6 +167,8 @@ int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbols
                  int64_t frame_stride, void *H_linear, void *H_cubic, void *H_sinc, int64_t n_frames);
 int wifi_equalize_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
                        void *eq, int64_t n_frames);
+int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft,
+                       void *ow2, int64_t n_frames);
 int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);
 int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                           int64_t frame_stride, void *H, int64_t n_frames);

@@ -78,6 +78,14 @@ class Oracle:
         self.lib.orc_ps_matlab(C.c_int({"linear": 0, "cubic": 1, "sinc": 2}[which]), ptx, prx, H.ctypes.data_as(_dp), C.c_long(n))
         return H
 
+    def frontend(self, packet, lptot):
+        """WiFi_blocks_extraction.m + WiFi_RX.m:19-31: time samples -> (symb [n][15][53], pre_fft [n][53], ow2 [n])."""
+        pk, ppk = _c(packet); lp, plp = _c(lptot)
+        n = pk.size // 1200
+        symb = np.empty((n, NBLK, NSC), np.complex128); pre = np.empty((n, NSC), np.complex128); ow2 = np.empty(n, np.float64)
+        self.lib.orc_frontend(ppk, plp, symb.ctypes.data_as(_dp), pre.ctypes.data_as(_dp), ow2.ctypes.data_as(_dp), C.c_long(n))
+        return symb, pre, ow2
+
     def equalize(self, rx_frames, H_lt, H_ps):
         rx, prx = _c(rx_frames); a, pa = _c(H_lt); b, pb = _c(H_ps)
         n = rx.size // (NSC * NBLK)

@@ -518,4 +518,49 @@ void orc_mmse_rank1(const double *tx, const double *rx, double ow2, const double
     for (int k = 0; k < NSC; ++k) ld_put(H, k, g * ld_get(H_ls, k));
 }
 
+/* ------------------------------------------------------------------ */
+/* receiver front-end (the step before the estimators)  */
+/* ------------------------------------------------------------------ */
+
+/* y[i] = X[(i - 26) mod 64], i < 53, X = 64-point DFT of x (MATLAB fft: X[k] = sum_n x[n] exp(-2 pi i k n / 64)),
+ * evaluated as the O(N^2) definition in long double: WiFi_blocks_extraction.m:7-9, WiFi_RX.m:22-23. */
+static void dft64_shift_keep53(const ldc x[64], ldc y[NSC])
+{
+    for (int i = 0; i < NSC; ++i) {
+        int k = (i - 26 + 64) % 64;
+        ldc acc = 0;
+        for (int n = 0; n < 64; ++n) {
+            int m = (k * n) % 64;                       /* exact argument reduction */
+            acc += x[n] * (cosl(-2.0L * M_PIl * m / 64.0L) + sinl(-2.0L * M_PIl * m / 64.0L) * I);
+        }
+        y[i] = acc;
+    }
+}
+
+/* WiFi_blocks_extraction.m:5-10 + WiFi_RX.m:19-31.  packet [n][1200] (15 blocks of 16 CP + 64 samples), lptot [n][160]
+ * (two 64-sample long-training symbols at the end) -> symb [n][15][53], pre_fft [n][53], ow2 [n] (may be NULL):
+ *   symb[b]  = keep53(circshift(fft(block b without its cyclic prefix), 26))
+ *   pre_fft  = keep53(circshift(fft((p1 + p2)/2), 26)),  p1 = lptot[96:160], p2 = lptot[32:96]
+ *   ow2      = sum |p2 - p1|^2 / (2*64) */
+void orc_frontend(const double *packet, const double *lptot, double *symb, double *pre_fft, double *ow2, long n_frames)
+{
+    for (long f = 0; f < n_frames; ++f) {
+        ldc x[64], y[NSC];
+        for (int b = 0; b < NBLK; ++b) {
+            for (int n = 0; n < 64; ++n) x[n] = ld_get(packet, 1200 * f + 80 * b + 16 + n);
+            dft64_shift_keep53(x, y);
+            for (int k = 0; k < NSC; ++k) ld_put(symb, NSC * NBLK * f + NSC * b + k, y[k]);
+        }
+        long double nv = 0;
+        for (int n = 0; n < 64; ++n) {
+            ldc p1 = ld_get(lptot, 160 * f + 96 + n), p2 = ld_get(lptot, 160 * f + 32 + n), dlt = p2 - p1;
+            x[n] = (p1 + p2) / 2.0L;
+            nv += creall(dlt * conjl(dlt));
+        }
+        dft64_shift_keep53(x, y);
+        for (int k = 0; k < NSC; ++k) ld_put(pre_fft, NSC * f + k, y[k]);
+        if (ow2) ow2[f] = (double)(nv / 128.0L);
+    }
+}
+
 int orc_sizeof_long_double(void) { return (int)sizeof(long double); }

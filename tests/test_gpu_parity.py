@@ -179,6 +179,37 @@ def test_f32_views_at_odd_frames(ctx, oracle, n):
     assert rel_err(got, ref, 1e-2) < TOL["f32"]
 
 
+# ------------------------------------------------------------------ receiver front-end
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_frontend_matlab_golden(ctx, oracle, gold, prec):
+    """Time samples of the reference's own workspace (matlab.mat) -> OFDM symbols, preamble spectrum, noise estimate."""
+    m, g = gold["matlab_mat"], gold["inputs_h"]
+    for side in ("tx", "rx"):
+        pk = m[side + "_packet"].reshape(1, 1200).astype(CDT[prec]); lp = m[side + "_lptot"].reshape(1, 160).astype(CDT[prec])
+        symb, pre, ow2 = ctx.frontend(dev(pk), dev(lp))
+        rs, rp, ro = oracle.frontend(r32(pk, prec), r32(lp, prec))
+        assert rel_err(host(symb), rs) < TOL[prec] and rel_err(host(pre), rp) < TOL[prec]
+        assert abs(host(ow2)[0] - ro[0]) <= (1e-12 if prec == "f64" else 1e-5) * ro[0]          # the tx preambles are identical: 0
+        if prec == "f64":
+            assert rel_err(host(symb)[0], m[side + "_symb"].T) < 1e-10                  # MATLAB's own fft
+            assert rel_err(host(pre)[0], m[side + "_preamble_fft"].ravel()) < 1e-10
+    assert abs(host(ow2)[0] / float(g["ow2"]) - 1) < 1e-4                             # inputs.h:18
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 333])
+def test_frontend_ragged_and_host(ctx, oracle, prec, n):
+    rng = np.random.default_rng(900 + n)
+    pk = (rng.standard_normal((n, 1200)) + 1j * rng.standard_normal((n, 1200))).astype(CDT[prec])
+    lp = (rng.standard_normal((n, 160)) + 1j * rng.standard_normal((n, 160))).astype(CDT[prec])
+    symb, pre, ow2 = ctx.frontend(dev(pk), dev(lp))
+    rs, rp, ro = oracle.frontend(r32(pk, prec), r32(lp, prec))
+    assert rel_err(host(symb), rs) < TOL[prec] and rel_err(host(pre), rp) < TOL[prec]
+    assert np.allclose(host(ow2), ro, rtol=1e-12 if prec == "f64" else 1e-5)
+    hs, hp, ho = ctx.frontend(pk, lp)                                                  # host pointers: H2D + kernel + D2H
+    assert np.array_equal(hs, host(symb)) and np.array_equal(hp, host(pre)) and np.array_equal(ho, host(ow2))
+
+
 # ------------------------------------------------------------------ MMSE, shared filter
 def test_mmse_filter_form(ctx, oracle):
     R = synth.channel_covariance()

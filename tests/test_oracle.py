@@ -101,6 +101,18 @@ def test_matlab_goldens(oracle, gold):
     assert np.all(eq[0][:, 26] == 0)
 
 
+def test_frontend_matlab_goldens(oracle, gold):
+    """CP strip + 64-point FFT + circshift 26 + keep 53 (WiFi_blocks_extraction.m), LTS averaging and the noise
+    estimate (WiFi_RX.m:19-31) against the workspace the reference saved in matlab.mat."""
+    m, g = gold["matlab_mat"], gold["inputs_h"]
+    for side in ("tx", "rx"):
+        symb, pre, ow2 = oracle.frontend(m[side + "_packet"].ravel(), m[side + "_lptot"].ravel())
+        # the DC bin of tx (-1e-4 against 8.875) is a cancellation residue of the FFT: floor 1e-3 like the estimators
+        assert rel_err(symb[0], m[side + "_symb"].T) < 1e-12, side
+        assert rel_err(pre[0], m[side + "_preamble_fft"].ravel()) < 1e-12, side
+    assert abs(ow2[0] / float(g["ow2"]) - 1) < 1e-4          # inputs.h:18 prints ow2 to 5 significant digits
+
+
 def test_inputs_h_is_rounded_matlab_frame(gold):
     """layout check: tx_symb[53*b + k] (inputs.h) == MATLAB tx_symb(k+1, b+1) to 4 decimals"""
     m, g = gold["matlab_mat"], gold["inputs_h"]
