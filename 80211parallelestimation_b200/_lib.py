@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(HERE, "libwifi_b200.so")
 
 F32, F64 = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_SINGULAR, ERR_NO_DEVICE, ERR_STATE = range(7)
-PS_LINEAR, PS_CUBIC, PS_SINC = 1, 2, 4
+PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB = 1, 2, 4, 8
 SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE = 0, 1, 2
 SOLVE_WIDE = SOLVE_REFINE
 AS_WRITTEN, INTENDED = 0, 1

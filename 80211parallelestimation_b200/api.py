@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, AS_WRITTEN, INTENDED)
+from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, AS_WRITTEN, INTENDED)
 
 NSC, NBLK, FRAME = 53, 15, 795
 
@@ -142,16 +142,17 @@ class WifiContext:
         self._ck(fn(self.h, dt, tx.ptr, rx.ptr, _ptr(H), n))
         return H
 
-    def ps(self, tx_symbols, rx_symbols, which=("linear", "cubic", "sinc"), frame_stride=None, n_frames=None, out=None):
+    def ps(self, tx_symbols, rx_symbols, which=("linear", "cubic", "sinc"), frame_stride=None, n_frames=None, out=None, matlab=False):
         """PS_Linear / PS_Cubic / PS_Sinc (main.c:77-146) fused over one pilot-LS pass.  tx/rx: [n][53] block vectors
-        (frame_stride 53) or whole frames [n][15][53] with frame_stride=795 (block 0 is used, main.c:30-33)."""
+        (frame_stride 53) or whole frames [n][15][53] with frame_stride=795 (block 0 is used, main.c:30-33).
+        matlab=True: WiFi_channel_estimation_PS_*.m semantics (average over blocks 1..4 of whole frames, true cubic spans)."""
         tx, rx = _Arg(tx_symbols), _Arg(rx_symbols)
         dev, dt = _same(tx, rx)
         if frame_stride is None:
             frame_stride = FRAME if (len(tx.shape) == 3 and tx.shape[-2:] == (NBLK, NSC)) else NSC
         if n_frames is None:
             n_frames = tx.size // frame_stride
-        mask = sum({"linear": PS_LINEAR, "cubic": PS_CUBIC, "sinc": PS_SINC}[w] for w in which)
+        mask = sum({"linear": PS_LINEAR, "cubic": PS_CUBIC, "sinc": PS_SINC}[w] for w in which) | (PS_MATLAB if matlab else 0)
         outs = {w: (out[w] if out else tx.empty_like((n_frames, NSC))) for w in which}
         self._sync_stream(dev)
         fn = self.lib.wifi_ps_batch if dev else self.lib.wifi_ps_host

@@ -73,7 +73,7 @@ struct Timed {
 // ---- interpolation weights (host, long double, once per context) -------------------------------
 // H_k = sum_i w[k][i] Hp_i.  Linear: main.c:86-100; Cubic: main.c:112-120 expanded (every divided
 // difference / 14, sic); Sinc: main.c:135-145 with sinc of utils.c:727-733 evaluated in double like the reference.
-static void build_tables(double *w /* [3][53][4] */)
+static void build_tables(double *w /* [4][53][4] */)
 {
     const int P[4] = {WIFI_P0, WIFI_P1, WIFI_P2, WIFI_P3};
     const long double delta = WIFI_P1 - WIFI_P0;
@@ -91,6 +91,14 @@ static void build_tables(double *w /* [3][53][4] */)
             w[(0 * WIFI_NSC + k) * 4 + i] = (double)wl[i];
             w[(1 * WIFI_NSC + k) * 4 + i] = (double)wc[i];
             w[(2 * WIFI_NSC + k) * 4 + i] = sc;
+            // table 3 = WiFi_channel_estimation_PS_Cubic.m:7-15: Newton form with the TRUE spans 14 / 28 / 42, evaluated
+            // on the unit vector e_i
+            long double h[4] = {0, 0, 0, 0};
+            h[i] = 1;
+            long double f01 = (h[1] - h[0]) / 14, f12 = (h[2] - h[1]) / 14, f23 = (h[3] - h[2]) / 14;
+            long double f012 = (f12 - f01) / 28, f123 = (f23 - f12) / 28, f0123 = (f123 - f012) / 42;
+            w[(3 * WIFI_NSC + k) * 4 + i] = (double)(h[0] + f01 * (k - P[0]) + f012 * (k - P[0]) * (k - P[1]) +
+                                                      f0123 * (k - P[0]) * (k - P[1]) * (k - P[2]));
         }
     }
 }
@@ -118,10 +126,10 @@ int wifi_create(int device, wifi_ctx **out)
         int gran = g ? atoi(g) : 32;
         if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
     }
-    double w[3 * WIFI_NSC * 4];
-    float wf[3 * WIFI_NSC * 4];
+    double w[4 * WIFI_NSC * 4];
+    float wf[4 * WIFI_NSC * 4];
     build_tables(w);
-    for (int i = 0; i < 3 * WIFI_NSC * 4; ++i) wf[i] = (float)w[i];
+    for (int i = 0; i < 4 * WIFI_NSC * 4; ++i) wf[i] = (float)w[i];
     const size_t nW = (size_t)WIFI_NSC * WIFI_NSC;
     bool ok = cudaMalloc(&ctx->tab.w64, sizeof(w)) == cudaSuccess && cudaMalloc(&ctx->tab.w32, sizeof(wf)) == cudaSuccess &&
               cudaMemcpy(ctx->tab.w64, w, sizeof(w), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -191,7 +199,8 @@ int wifi_ps_batch(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx, const
                   void *Hc, void *Hs, int64_t n)
 {
     ENTER();
-    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && which > 0 && which < 8 && frame_stride >= WIFI_NSC);
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && (which & 7) != 0 && which < 16 && frame_stride >= WIFI_NSC);
+    NEED(!(which & WIFI_PS_MATLAB) || frame_stride >= 4 * WIFI_NSC);      // MATLAB mode reads OFDM blocks 0..3 of whole frames
     NEED(n == 0 || (tx && rx));
     NEED(n == 0 || ((!(which & WIFI_PS_LINEAR) || Hl) && (!(which & WIFI_PS_CUBIC) || Hc) && (!(which & WIFI_PS_SINC) || Hs)));
     Timed t(ctx, ctx->stream);
@@ -512,17 +521,19 @@ int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx, const 
                  void *Hs, int64_t n)
 {
     ENTER();
-    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && which > 0 && which < 8 && frame_stride >= WIFI_NSC && (n == 0 || (tx && rx)));
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && (which & 7) != 0 && which < 16 && frame_stride >= WIFI_NSC && (n == 0 || (tx && rx)));
+    NEED(!(which & WIFI_PS_MATLAB) || frame_stride >= 4 * WIFI_NSC);
     NEED(n == 0 || ((!(which & WIFI_PS_LINEAR) || Hl) && (!(which & WIFI_PS_CUBIC) || Hc) && (!(which & WIFI_PS_SINC) || Hs)));
+    const int nb = (which & WIFI_PS_MATLAB) ? 4 : 1;                       // OFDM blocks that cross the bus per frame
     const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
-    std::vector<Arr> arrs = {in_arr(tx, row, pitch), in_arr(rx, row, pitch)};
+    std::vector<Arr> arrs = {in_arr(tx, nb * row, pitch), in_arr(rx, nb * row, pitch)};
     int il = -1, ic = -1, is = -1;
     if (which & WIFI_PS_LINEAR) { il = (int)arrs.size(); arrs.push_back(out_arr(Hl, row)); }
     if (which & WIFI_PS_CUBIC) { ic = (int)arrs.size(); arrs.push_back(out_arr(Hc, row)); }
     if (which & WIFI_PS_SINC) { is = (int)arrs.size(); arrs.push_back(out_arr(Hs, row)); }
     return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
         Timed t(ctx, s);
-        CK(launch_ps(dt, which, d[0], d[1], WIFI_NSC, il >= 0 ? d[il] : nullptr, ic >= 0 ? d[ic] : nullptr, is >= 0 ? d[is] : nullptr,
+        CK(launch_ps(dt, which, d[0], d[1], nb * WIFI_NSC, il >= 0 ? d[il] : nullptr, ic >= 0 ? d[ic] : nullptr, is >= 0 ? d[is] : nullptr,
                      nc, ctx->tab, s));
         return (int)WIFI_OK;
     });

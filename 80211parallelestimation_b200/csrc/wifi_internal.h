@@ -10,8 +10,8 @@ namespace wifi {
 
 // interpolation weight tables: H_k = sum_i w[est][k][i] * Hp_i  (est: 0 linear, 1 cubic, 2 sinc)
 struct InterpTables {
-    float *w32;   // [3][53][4]
-    double *w64;  // [3][53][4]
+    float *w32;   // [4][53][4]  (table 3: MATLAB cubic, true divided differences)
+    double *w64;  // [4][53][4]
 };
 
 // shared MMSE filter operand images (built by filter_install from W, 53x53 double2 row-major)

@@ -139,10 +139,19 @@ __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__re
     const int nf = (int)min((int64_t)PS_TILE, n_frames - f0);
 
     // phase 1: pilot LS  Hp_i = rx[P_i] / tx[P_i]  (main.c:82-84), one (frame, pilot) pair per thread
+    // MATLAB mode (WiFi_channel_estimation_PS_*.m): the estimators are linear in Hp, so the average of the estimates of OFDM
+    // blocks 1..4 is the estimate of the averaged pilot LS values
+    const int navg = (which & WIFI_PS_MATLAB) ? 4 : 1;
     for (int idx = threadIdx.x; idx < nf * 4; idx += PS_THREADS) {
         int f = idx >> 2, p = idx & 3;
         int64_t off = (f0 + f) * frame_stride + (WIFI_P0 + (WIFI_P1 - WIFI_P0) * p);
-        hp[f][p] = cdiv(ld_gather(rx + off), ld_gather(tx + off));
+        cx<T> h = cdiv(ld_gather(rx + off), ld_gather(tx + off));
+        if (navg == 4) {
+#pragma unroll
+            for (int b = 1; b < 4; ++b) h = cadd(h, cdiv(ld_gather(rx + off + b * NSC), ld_gather(tx + off + b * NSC)));
+            h = mk<T>(h.x * (T)0.25, h.y * (T)0.25);
+        }
+        hp[f][p] = h;
     }
     // this thread's sub-carrier and its weights (registers)
     const int k = threadIdx.x % NSC, fsub = threadIdx.x / NSC;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__re
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         wl[i] = __ldg(wtab + (0 * NSC + k) * 4 + i);
-        wc[i] = __ldg(wtab + (1 * NSC + k) * 4 + i);
+        wc[i] = __ldg(wtab + (((which & WIFI_PS_MATLAB) ? 3 : 1) * NSC + k) * 4 + i);   // table 3: true divided differences
         ws[i] = __ldg(wtab + (2 * NSC + k) * 4 + i);
     }
     __syncthreads();

@@ -61,6 +61,9 @@ typedef enum {
 #define WIFI_PS_LINEAR 1
 #define WIFI_PS_CUBIC 2
 #define WIFI_PS_SINC 4
+/* OR-ed in: MATLAB semantics (WiFi_channel_estimation_PS_*.m) instead of main.c's -- the estimate is averaged over OFDM
+ * blocks 1..4 of a whole frame (frame_stride >= 212) and Cubic uses the true divided-difference spans 14/28/42 */
+#define WIFI_PS_MATLAB 8
 
 /* flags of wifi_mmse_perframe_batch */
 #define WIFI_SOLVE_PIVOT 0      /* partial-pivoting Gauss-Jordan (any non-singular R + D) */

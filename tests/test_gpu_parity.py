@@ -210,6 +210,37 @@ def test_frontend_ragged_and_host(ctx, oracle, prec, n):
     assert np.array_equal(hs, host(symb)) and np.array_equal(hp, host(pre)) and np.array_equal(ho, host(ow2))
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_wifi_rx_m_end_to_end(ctx, oracle, gold, prec):
+    """WiFi_RX.m on the device: the reference's time samples -> front-end -> LT_LS -> PS_Linear/Cubic/Sinc in MATLAB mode
+    -> equalizer, every stage against the workspace MATLAB saved (matlab.mat)."""
+    m = gold["matlab_mat"]
+    side = {}
+    for sd in ("tx", "rx"):
+        pk = dev(m[sd + "_packet"].reshape(1, 1200).astype(CDT[prec])); lp = dev(m[sd + "_lptot"].reshape(1, 160).astype(CDT[prec]))
+        side[sd] = ctx.frontend(pk, lp)
+    tol = TOL[prec]
+    lt = ctx.lt_ls(side["tx"][1], side["rx"][1])
+    assert rel_err(host(lt)[0], m["H_EST_LT_LS"].ravel()) < tol
+    ps = ctx.ps(side["tx"][0], side["rx"][0], matlab=True)
+    for name, key in (("linear", "H_EST_PS_Linear"), ("cubic", "H_EST_PS_Cubic"), ("sinc", "H_EST_PS_Sinc")):
+        assert rel_err(host(ps[name])[0], m[key].ravel()) < tol, name
+    eq = ctx.equalize(side["rx"][0], lt, ps["linear"])
+    assert rel_err(host(eq)[0], m["eq_symbols"].T, floor=1e-6) < (tol if prec == "f64" else 2e-4)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [1, 47, 500])
+def test_ps_matlab_mode(ctx, oracle, prec, n):
+    fr = synth.make_frames(n, seed=77 + n, dtype=CDT[prec])
+    ps = ctx.ps(dev(fr["tx_symb"]), dev(fr["rx_symb"]), matlab=True)
+    for name in ("linear", "cubic", "sinc"):
+        ref = oracle.ps_matlab(name, r32(fr["tx_symb"], prec), r32(fr["rx_symb"], prec))
+        assert rel_err(host(ps[name]), ref) < TOL[prec], name
+    hs = ctx.ps(fr["tx_symb"], fr["rx_symb"], ("cubic",), matlab=True)                 # host pointers: 4 blocks cross the bus
+    assert np.array_equal(hs["cubic"], host(ps["cubic"]))
+
+
 # ------------------------------------------------------------------ MMSE, shared filter
 def test_mmse_filter_form(ctx, oracle):
     R = synth.channel_covariance()
