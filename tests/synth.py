@@ -83,3 +83,25 @@ def rel_err(got, ref, floor=1e-3):
     den = np.maximum(np.abs(r), floor * scale)
     den = np.where(den == 0, 1.0, den)
     return float((np.abs(g - r) / den).max()) if g.size else 0.0
+
+
+def to_time_domain(fr, seed=1, lts_noise=2e-4):
+    """Time samples whose front-end output (WiFi_blocks_extraction.m, WiFi_RX.m:19-31) is `fr` again:
+    symb[i] = X[(i - 26) mod 64] is inverted, a 16-sample cyclic prefix is prepended to every OFDM block, and the long
+    training field is [32 guard samples, p2, p1] with p1,2 = t -+ w (so (p1 + p2)/2 = t and ow2 = sum |2w|^2 / 128)."""
+    rng = np.random.default_rng(seed)
+
+    def td(spec53):                                     # [..., 53] -> [..., 64] time samples
+        X = np.zeros(spec53.shape[:-1] + (64,), np.complex128)
+        X[..., (np.arange(NSC) - 26) % 64] = spec53
+        return np.fft.ifft(X, axis=-1)
+
+    out = {}
+    n = fr["tx_pre"].shape[0]
+    for side in ("tx", "rx"):
+        x = td(fr[side + "_symb"].astype(np.complex128))                    # [n][15][64]
+        out[side + "_packet"] = np.concatenate([x[..., 48:], x], axis=-1).reshape(n, NBLK * 80)
+        t = td(fr[side + "_pre"].astype(np.complex128))                     # [n][64]
+        w = (rng.standard_normal((n, 64)) + 1j * rng.standard_normal((n, 64))) * (lts_noise if side == "rx" else 0.0)
+        out[side + "_lptot"] = np.concatenate([t[:, 32:], t - w, t + w], axis=-1)      # p2 = lptot[32:96], p1 = lptot[96:160]
+    return out
