@@ -252,11 +252,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             //         runs under the epilogue of the group's previous tile below, and the LDGs of step a. then hit L2.
             //         Measured at 1 Mi frames: no prefetch 0.329 ms, this 0.238 ms; prefetching 2 / 4 / 6 tiles ahead is
             //         slower (0.281 / 0.343 / 0.355 ms) -- the prefetched-but-unread footprint of 148 CTAs starts to thrash L2. ----
-            if (vec_ok && lane == 0 && it < my_tiles) {
+            if (it < my_tiles) {
                 const int64_t fn = (blockIdx.x + (int64_t)it * gridDim.x) * TC_M + quarter * 32;
-                if (fn + 32 <= n_frames) {
-                    l2_prefetch(a_in + fn * NSC, TC_CHUNK_F * 4);
-                    if (FUSED) l2_prefetch(rx + fn * NSC, TC_CHUNK_F * 4);
+                if (vec_ok) {
+                    if (lane == 0 && fn + 32 <= n_frames) {
+                        l2_prefetch(a_in + fn * NSC, TC_CHUNK_F * 4);
+                        if (FUSED) l2_prefetch(rx + fn * NSC, TC_CHUNK_F * 4);
+                    }
+                } else if (fn + 32 < n_frames) {
+                    // strided rows (block vectors read in place from whole frames): lane r prefetches row r, widened to
+                    // 16-byte boundaries (the neighbouring value on either side belongs to the same array)
+                    const float2 *ra = a_in + (fn + lane) * frame_stride;
+                    const uintptr_t lo = (uintptr_t)ra & ~(uintptr_t)15, hi = ((uintptr_t)(ra + NSC) + 15) & ~(uintptr_t)15;
+                    if (lo >= (uintptr_t)a_in) l2_prefetch((const void *)lo, (uint32_t)(hi - lo));
+                    if (FUSED) {
+                        const float2 *rr = rx + (fn + lane) * frame_stride;
+                        const uintptr_t lo2 = (uintptr_t)rr & ~(uintptr_t)15, hi2 = ((uintptr_t)(rr + NSC) + 15) & ~(uintptr_t)15;
+                        if (lo2 >= (uintptr_t)rx) l2_prefetch((const void *)lo2, (uint32_t)(hi2 - lo2));
+                    }
                 }
             }
             // ---- c. epilogue of this group's previous tile (it-2); must precede this iteration's a_ready arrival ----
@@ -325,6 +338,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     for (int j = 0; j < NB; ++j) {
                         const int i = b * NB + j;
                         if (i < 26 || (i == 26 && lane < 16)) b4[32 * i] = ls_pair<FUSED>(va[b & 1][j], vr[b & 1][j]);
+                    }
+                }
+            } else if (valid == 32) {
+                // whole chunk, rows at frame_stride (or only 8-byte aligned): lane l takes sub-carriers l and l + 32 of every
+                // row -- a warp load is one contiguous 256-byte (168-byte) piece of a row -- 4 rows = 16 loads in flight
+                float2 *b2 = reinterpret_cast<float2 *>(buf);
+                const float2 *pa = a_in + f0 * frame_stride + lane;
+                const float2 *pr = FUSED ? rx + f0 * frame_stride + lane : nullptr;
+                const bool second = lane + 32 < NSC;
+                constexpr int RB = 4;
+                float2 va[2][RB][2], vr[2][RB][2];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    va[0][j][0] = ld_stream(pa + j * frame_stride);
+                    if (FUSED) vr[0][j][0] = ld_stream(pr + j * frame_stride);
+                    if (second) { va[0][j][1] = ld_stream(pa + j * frame_stride + 32); if (FUSED) vr[0][j][1] = ld_stream(pr + j * frame_stride + 32); }
+                }
+#pragma unroll
+                for (int b = 0; b < 32 / RB; ++b) {
+                    if (b + 1 < 32 / RB) {
+#pragma unroll
+                        for (int j = 0; j < RB; ++j) {
+                            const int64_t ro = (int64_t)((b + 1) * RB + j) * frame_stride;
+                            va[(b + 1) & 1][j][0] = ld_stream(pa + ro);
+                            if (FUSED) vr[(b + 1) & 1][j][0] = ld_stream(pr + ro);
+                            if (second) { va[(b + 1) & 1][j][1] = ld_stream(pa + ro + 32); if (FUSED) vr[(b + 1) & 1][j][1] = ld_stream(pr + ro + 32); }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int r = b * RB + j;
+                        b2[r * NSC + lane] = FUSED ? cdiv_fast(vr[b & 1][j][0], va[b & 1][j][0]) : va[b & 1][j][0];
+                        if (second) b2[r * NSC + lane + 32] = FUSED ? cdiv_fast(vr[b & 1][j][1], va[b & 1][j][1]) : va[b & 1][j][1];
                     }
                 }
             } else {
