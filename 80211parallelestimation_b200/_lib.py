@@ -34,6 +34,8 @@ SIGNATURES = {
     "wifi_mmse_shared_apply_batch": [_vp, _i, _vp, _vp, _i64],
     "wifi_mmse_shared_batch": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
     "wifi_mmse_perframe_batch": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
+    "wifi_mmse_eig_prepare": [_vp, _vp, _vp],
+    "wifi_mmse_perframe_eig_batch": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_batch": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_chermitian_batch": [_vp, _i, _i, _vp, _i, _i, _vp, _i64],
@@ -52,6 +54,7 @@ SIGNATURES = {
     "wifi_mmse_filter_form_host": [_vp, _vp, _vp, _vp],
     "wifi_mmse_shared_host": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
     "wifi_mmse_perframe_host": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
+    "wifi_mmse_perframe_eig_host": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_host": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_chermitian_host": [_vp, _i, _i, _vp, _i, _i, _vp, _i64],

@@ -262,6 +262,32 @@ class WifiContext:
         self._ck(fn(self.h, dt, r.ptr, tx.ptr, rx.ptr, frame_stride, s.ptr, _ptr(H), n_frames, flags))
         return H
 
+    def mmse_eig_prepare(self, R, absx2):
+        """Eigen-domain operands for mmse_perframe_eig: R 53x53 complex128, absx2 = the shared |tx_k|^2 pattern (53 float64)."""
+        import torch
+        r = R if _is_torch(R) else torch.from_numpy(np.ascontiguousarray(np.asarray(R, np.complex128))).cuda(self.device)
+        a = absx2 if _is_torch(absx2) else torch.from_numpy(np.ascontiguousarray(np.asarray(absx2, np.float64))).cuda(self.device)
+        if r.dtype != torch.complex128 or a.dtype != torch.float64:
+            raise TypeError("R must be complex128 and absx2 float64")
+        r, a = r.contiguous(), a.contiguous()
+        self._sync_stream(True)
+        self._ck(self.lib.wifi_mmse_eig_prepare(self.h, r.data_ptr(), a.data_ptr()))
+
+    def mmse_perframe_eig(self, tx_symbols, rx_symbols, sigma2, frame_stride=NSC, n_frames=None, out=None):
+        """Per-frame PS_MMSE in the eigen domain (frames share |tx_k|^2; see mmse_eig_prepare)."""
+        tx, rx = _Arg(tx_symbols), _Arg(rx_symbols)
+        dev, dt = _same(tx, rx)
+        if n_frames is None:
+            n_frames = tx.size // frame_stride
+        s = _Arg(sigma2, real=True)
+        if s.dt != dt or s.device != dev:
+            raise TypeError("sigma2 must match the precision and residency of the frames")
+        H = out if out is not None else tx.empty_like((n_frames, NSC))
+        self._sync_stream(dev)
+        fn = self.lib.wifi_mmse_perframe_eig_batch if dev else self.lib.wifi_mmse_perframe_eig_host
+        self._ck(fn(self.h, dt, tx.ptr, rx.ptr, frame_stride, s.ptr, _ptr(H), n_frames))
+        return H
+
     def mmse_cconv(self, tx_symbols, rx_symbols, ow2, H_ls, out=None):
         """PS_MMSE in the calling convention of main.c:148 (R_f = H_ls H_ls^H), batched over [n][53]."""
         tx, rx, h = _Arg(tx_symbols), _Arg(rx_symbols), _Arg(H_ls)

@@ -22,6 +22,9 @@ struct wifi_ctx {
     cudaStream_t stream;
     InterpTables tab;
     FilterImages img;
+    FilterImages eig[2];     // eigen-domain per-frame MMSE: G = V^H M^-1/2 and G2 = M^1/2 V as shared-filter operands
+    double *eig_lam; void *eig_p; double *eig_scal; int eig_valid;
+    void *eig_u; size_t eig_u_bytes;     // [n][53] scratch between the two products
     int *d_info;             // device scratch: singularity flags
     int *h_info;             // pinned mirror
     char err[512];
@@ -103,6 +106,16 @@ static void build_tables(double *w /* [4][53][4] */)
     }
 }
 
+static bool alloc_images(FilterImages &im)
+{
+    const size_t nW = (size_t)WIFI_NSC * WIFI_NSC;
+    im.valid = 0;
+    return cudaMalloc(&im.W64, nW * sizeof(double2)) == cudaSuccess && cudaMalloc(&im.W32, nW * sizeof(float2)) == cudaSuccess &&
+           cudaMalloc(&im.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess && cudaMalloc(&im.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
+           cudaMalloc(&im.B64, 112 * WIFI_DMMA_BS * sizeof(double)) == cudaSuccess;
+}
+static void free_images(FilterImages &im) { cudaFree(im.W64); cudaFree(im.W32); cudaFree(im.Bhi); cudaFree(im.Blo); cudaFree(im.B64); }
+
 extern "C" {
 
 const char *wifi_version(void) { return "wifi_b200 0.1 (sm_100a)"; }
@@ -139,6 +152,9 @@ int wifi_create(int device, wifi_ctx **out)
               cudaMalloc(&ctx->img.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&ctx->img.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
               cudaMalloc(&ctx->img.B64, 112 * WIFI_DMMA_BS * sizeof(double)) == cudaSuccess &&
+              alloc_images(ctx->eig[0]) && alloc_images(ctx->eig[1]) &&
+              cudaMalloc(&ctx->eig_lam, 64 * sizeof(double)) == cudaSuccess && cudaMalloc(&ctx->eig_p, 64 * sizeof(double2)) == cudaSuccess &&
+              cudaMalloc(&ctx->eig_scal, 4 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
               cudaHostAlloc(&ctx->h_info, 4096 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
@@ -158,6 +174,8 @@ int wifi_destroy(wifi_ctx *ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->tab.w64); cudaFree(ctx->tab.w32);
     cudaFree(ctx->img.W64); cudaFree(ctx->img.W32); cudaFree(ctx->img.Bhi); cudaFree(ctx->img.Blo); cudaFree(ctx->img.B64);
+    free_images(ctx->eig[0]); free_images(ctx->eig[1]);
+    cudaFree(ctx->eig_lam); cudaFree(ctx->eig_p); cudaFree(ctx->eig_scal); cudaFree(ctx->eig_u);
     cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -228,15 +246,16 @@ int wifi_frontend_batch(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const 
 }
 
 // ---- MMSE ---------------------------------------------------------------------------------------
-static int install_filter(wifi_ctx *ctx, cudaStream_t s)
+static int install_images(wifi_ctx *ctx, FilterImages &im, cudaStream_t s)
 {
-    CK(launch_filter_install_simt(ctx->img, s));
-    CK(launch_filter_install_tc(ctx->img, s));
-    CK(launch_filter_install_dmma(ctx->img, s));
-    ctx->launches += 2;
-    ctx->img.valid = 1;
+    CK(launch_filter_install_simt(im, s));
+    CK(launch_filter_install_tc(im, s));
+    CK(launch_filter_install_dmma(im, s));
+    ctx->launches += 3;
+    im.valid = 1;
     return WIFI_OK;
 }
+static int install_filter(wifi_ctx *ctx, cudaStream_t s) { return install_images(ctx, ctx->img, s); }
 
 int wifi_mmse_filter_form(wifi_ctx *ctx, const void *R, const double *d, void *W_out)
 {
@@ -264,6 +283,38 @@ int wifi_mmse_filter_set(wifi_ctx *ctx, const void *W)
     return install_filter(ctx, ctx->stream);
 }
 
+static int gemm_with(wifi_ctx *ctx, const FilterImages &im, wifi_dtype dt, const void *a, const void *rx, int64_t frame_stride, void *H,
+                     int64_t n, cudaStream_t s)
+{
+    Timed t(ctx, s);
+    if (ctx->force_simt) CK(launch_mmse_shared_simt(dt, im, a, rx, frame_stride, H, n, s));
+    else if (dt == WIFI_F32) CK(launch_mmse_shared_tc(im, a, rx, frame_stride, H, n, s));
+    else CK(launch_mmse_shared_dmma(im, a, rx, frame_stride, H, n, s));
+    return WIFI_OK;
+}
+
+// eigen-domain per-frame MMSE on device pointers (wifi_eig.cu): two shared-matrix products with a per-frame scaling between
+static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H, int64_t n,
+                    cudaStream_t s)
+{
+    if (!ctx->eig_valid) return fail(ctx, WIFI_ERR_STATE, "no eigen-domain operands installed: call wifi_mmse_eig_prepare first");
+    if (n == 0) return WIFI_OK;
+    const size_t need = (size_t)n * WIFI_NSC * esize(dt);
+    if (ctx->eig_u_bytes < need) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->eig_u); ctx->eig_u = nullptr; ctx->eig_u_bytes = 0;
+        if (cudaMalloc(&ctx->eig_u, need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "eigen-domain scratch cudaMalloc(%zu) failed", need);
+        ctx->eig_u_bytes = need;
+    }
+    int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, ctx->eig_u, n, s);            // u = (rx/tx) G^T
+    if (rc) return rc;
+    { Timed t(ctx, s); CK(launch_eig_mid(dt, ctx->eig_u, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
+    rc = gemm_with(ctx, ctx->eig[1], dt, ctx->eig_u, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
+    if (rc) return rc;
+    { Timed t(ctx, s); CK(launch_eig_fin(dt, H, ctx->eig_u, tx, rx, frame_stride, ctx->eig_scal, n, s)); }
+    return WIFI_OK;
+}
+
 static int mmse_shared(wifi_ctx *ctx, wifi_dtype dt, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n,
                        cudaStream_t s)
 {
@@ -289,6 +340,34 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
     ENTER();
     NEED(n >= 0 && (n == 0 || (tx && rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
     return mmse_shared(ctx, dt, tx, rx, frame_stride, H, n, ctx->stream);
+}
+
+int wifi_mmse_eig_prepare(wifi_ctx *ctx, const void *R, const double *absx2)
+{
+    ENTER();
+    NEED(R && absx2);
+    ctx->eig_valid = 0;
+    CK(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+    {
+        Timed t(ctx, ctx->stream);
+        CK(launch_eig_prepare(R, absx2, ctx->eig[0].W64, ctx->eig[1].W64, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, ctx->d_info, ctx->stream));
+    }
+    int rc = install_images(ctx, ctx->eig[0], ctx->stream);
+    if (!rc) rc = install_images(ctx, ctx->eig[1], ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_info) return fail(ctx, WIFI_ERR_INVALID, "eigen-domain MMSE supports at most one null bin (|x_k|^2 < 1e-6 max) and needs max |x|^2 > 0");
+    ctx->eig_valid = 1;
+    return WIFI_OK;
+}
+
+int wifi_mmse_perframe_eig_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                                 void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    return mmse_eig(ctx, dt, tx, rx, frame_stride, sigma2, H, n, ctx->stream);
 }
 
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
@@ -619,6 +698,18 @@ int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const v
                            });
     cudaFree(dR);
     return rc;
+}
+
+int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                                void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), in_arr(sigma2, rsize(dt), rsize(dt)), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return mmse_eig(ctx, dt, d[0], d[1], WIFI_NSC, d[2], d[3], nc, s);
+                         });
 }
 
 int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, const void *ow2, const void *H_ls, void *H,

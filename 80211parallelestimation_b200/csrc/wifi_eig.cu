@@ -1,0 +1,281 @@
+// wifi_eig.cu -- eigen-domain per-frame PS_MMSE.
+//
+// When every frame carries the same pilot/data MODULUS pattern |x_k|^2 (BPSK/QPSK/any constant-modulus constellation;
+// the signs/phases may differ per frame) the per-frame system matrix is  A_f = R + sigma2_f M,  M = diag(1/|x_k|^2), with
+// one shared M.  With  S = M^-1/2 R M^-1/2 = V L V^H  (Hermitian eigen-decomposition, once per batch)
+//     A_f^-1 = M^-1/2 V (L + sigma2_f)^-1 V^H M^-1/2
+//     H = y - sigma2_f M A_f^-1 y = y - G2 ( s_f (.) (G y) ),   G = V^H M^-1/2,  G2 = M^1/2 V,  s_fi = sigma2_f / (l_i + sigma2_f)
+// i.e. the per-frame 53 x 53 solve (4.4e5 flop) becomes two shared-matrix products (4.5e4 flop) on the tensor cores with a
+// per-frame diagonal scaling in between -- and in FP32 it is accurate to ~1e-5, where FP32 elimination of R + D loses
+// the sigma2/|x|^2 diagonal (3.7e-3).
+//
+// A bin with (almost) no transmit energy -- the DC bin of the inputs.h frame, |x_26| = 1e-4 against 8.875 -- would put a
+// factor 1e4 into M^1/2 and wreck the similarity transform, so at most one such "null" bin d is carried exactly as a
+// border instead (N = the other bins, b = R_Nd, p = G b):
+//     beta = b^H A_NN^-1 y_N = sum_i conj(p_i) u_i / (l_i + sigma2),    gamma = b^H A_NN^-1 b = sum_i |p_i|^2 / (l_i + sigma2)
+//     z_d = (y_d - beta) / (sigma2 m_d + R_dd - gamma)
+//     H_N = y_N - G2 ( s (.) (u - p z_d) ),      H_d = beta + (y_d - beta) (R_dd - gamma) / (sigma2 m_d + R_dd - gamma)
+//
+// eig_prepare_kernel   one CTA, FP64: scaled matrix, cyclic Jacobi with a round-robin parallel ordering (27 disjoint
+//                      rotations per round, 53 rounds per sweep), builds the two 53 x 53 "filters" W1 (= G, rows = eigen
+//                      index) and W2 (= G2, columns = eigen index) for the shared-filter GEMM kernels, l, p and the scalars.
+// eig_mid_kernel       warp per frame, between the two GEMMs: beta, gamma, z_d by warp reductions, v = s (.) (u - p z_d) in place.
+// eig_fin_kernel       flat, after the second GEMM: H = rx/tx - c, null bin from the value eig_mid stashed.
+#include <algorithm>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+constexpr int EG_N = 54;                    // 53 padded to an even count for the round-robin pairing
+constexpr int EG_LD = 55;                   // leading dimension of the shared-memory matrices (odd: conflict-light columns)
+constexpr int EG_THREADS = 512;
+constexpr int EG_SWEEPS = 12;               // the prototype converges to 1e-30 off-diagonal in 11 sweeps
+
+__device__ __forceinline__ double2 zmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 zconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// R [53][53] double2, absx2 [53] -> W1, W2 [53][53] double2 (row-major), lam [53], p [53] double2,
+// scal[0] = R_dd, scal[1] = m_d = 1/|x_d|^2, scal[2] = index of the null bin or -1, scal[3] = number of eigen pairs
+__global__ void __launch_bounds__(EG_THREADS, 1)
+    eig_prepare_kernel(const double2 *__restrict__ R, const double *__restrict__ absx2, double2 *__restrict__ W1,
+                       double2 *__restrict__ W2, double *__restrict__ lam, double2 *__restrict__ p, double *__restrict__ scal,
+                       int *__restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char eg_smem[];
+    double2 *A = (double2 *)eg_smem;            // [54][55]
+    double2 *V = A + EG_N * EG_LD;              // [54][55]
+    double2 *rot = V + EG_N * EG_LD;            // [27] (c, s) and [27] phase
+    double2 *rph = rot + 32;
+    __shared__ int bins[NSC];                   // compressed index -> bin
+    __shared__ double ax[NSC];                  // |x| of the compressed index
+    __shared__ int s_nb, s_dc;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        double mx = 0;
+        for (int k = 0; k < NSC; ++k) mx = fmax(mx, absx2[k]);
+        int nb = 0, dc = -1, nnull = 0;
+        for (int k = 0; k < NSC; ++k) {
+            if (absx2[k] < 1e-6 * mx) { dc = k; ++nnull; }
+            else { bins[nb] = k; ax[nb] = sqrt(absx2[k]); ++nb; }
+        }
+        if (nnull > 1 || mx <= 0) { *info = 1; nb = 0; }          // at most one null bin is supported
+        s_nb = nb; s_dc = dc;
+    }
+    __syncthreads();
+    const int nb = s_nb, dc = s_dc;
+    if (nb == 0) return;
+    // S = |x_i| R_ij |x_j| on the non-null bins (Hermitian by construction: the lower triangle mirrors the upper), V = I
+    for (int e = tid; e < EG_N * EG_N; e += EG_THREADS) {
+        const int i = e / EG_N, j = e - i * EG_N;
+        double2 a = make_double2(0, 0);
+        if (i < nb && j < nb) {
+            const double2 r = i <= j ? R[bins[i] * NSC + bins[j]] : zconj(R[bins[j] * NSC + bins[i]]);
+            const double sc = ax[i] * ax[j];
+            a = make_double2(r.x * sc, i == j ? 0.0 : r.y * sc);
+        }
+        A[i * EG_LD + j] = a;
+        V[i * EG_LD + j] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int sweep = 0; sweep < EG_SWEEPS; ++sweep) {
+        for (int round = 0; round < EG_N - 1; ++round) {
+            // ---- rotations of this round: pair j = (pp, qq), all 27 pairs disjoint ----
+            if (tid < EG_N / 2) {
+                int pp = tid == 0 ? EG_N - 1 : (round + tid) % (EG_N - 1);
+                int qq = (round + EG_N - 1 - tid) % (EG_N - 1);
+                if (pp > qq) { int t = pp; pp = qq; qq = t; }
+                double c = 1.0, s = 0.0;
+                double2 ph = make_double2(1.0, 0.0);
+                if (qq < nb) {
+                    const double2 apq = A[pp * EG_LD + qq];
+                    const double ab = hypot(apq.x, apq.y);
+                    if (ab > 1e-300) {
+                        ph = make_double2(apq.x / ab, apq.y / ab);
+                        const double tau = (A[qq * EG_LD + qq].x - A[pp * EG_LD + pp].x) / (2.0 * ab);
+                        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                    }
+                }
+                rot[tid] = make_double2(c, s);
+                rph[tid] = ph;
+            }
+            __syncthreads();
+            // ---- column update  X[:,p] <- c X[:,p] - s conj(ph) X[:,q],  X[:,q] <- s X[:,p] + c conj(ph) X[:,q]  for X = A, V ----
+            for (int e = tid; e < (EG_N / 2) * nb; e += EG_THREADS) {
+                const int j = e / nb, k = e - j * nb;
+                int pp = j == 0 ? EG_N - 1 : (round + j) % (EG_N - 1);
+                int qq = (round + EG_N - 1 - j) % (EG_N - 1);
+                if (pp > qq) { int t = pp; pp = qq; qq = t; }
+                if (qq >= nb) continue;
+                const double c = rot[j].x, s = rot[j].y;
+                const double2 cph = zconj(rph[j]);
+                double2 xp = A[k * EG_LD + pp], xq = zmul(cph, A[k * EG_LD + qq]);
+                A[k * EG_LD + pp] = make_double2(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                A[k * EG_LD + qq] = make_double2(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                xp = V[k * EG_LD + pp]; xq = zmul(cph, V[k * EG_LD + qq]);
+                V[k * EG_LD + pp] = make_double2(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                V[k * EG_LD + qq] = make_double2(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+            }
+            __syncthreads();
+            // ---- row update  A[p,:] <- c A[p,:] - s ph A[q,:],  A[q,:] <- s A[p,:] + c ph A[q,:] ----
+            for (int e = tid; e < (EG_N / 2) * nb; e += EG_THREADS) {
+                const int j = e / nb, k = e - j * nb;
+                int pp = j == 0 ? EG_N - 1 : (round + j) % (EG_N - 1);
+                int qq = (round + EG_N - 1 - j) % (EG_N - 1);
+                if (pp > qq) { int t = pp; pp = qq; qq = t; }
+                if (qq >= nb) continue;
+                const double c = rot[j].x, s = rot[j].y;
+                const double2 xp = A[pp * EG_LD + k], xq = zmul(rph[j], A[qq * EG_LD + k]);
+                double2 np_ = make_double2(c * xp.x - s * xq.x, c * xp.y - s * xq.y);
+                double2 nq = make_double2(s * xp.x + c * xq.x, s * xp.y + c * xq.y);
+                if (k == qq) np_ = make_double2(0, 0);             // the annihilated pair, exactly
+                if (k == pp) nq = make_double2(0, 0);
+                if (k == pp) np_.y = 0;                            // the diagonal of a Hermitian matrix is real
+                if (k == qq) nq.y = 0;
+                A[pp * EG_LD + k] = np_;
+                A[qq * EG_LD + k] = nq;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- outputs ----
+    for (int e = tid; e < NSC * NSC; e += EG_THREADS) { W1[e] = make_double2(0, 0); W2[e] = make_double2(0, 0); }
+    if (tid < NSC) { lam[tid] = tid < nb ? A[tid * EG_LD + tid].x : 0.0; p[tid] = make_double2(0, 0); }
+    __syncthreads();
+    for (int e = tid; e < nb * nb; e += EG_THREADS) {
+        const int i = e / nb, kk = e - i * nb;                     // eigen index i, compressed bin kk
+        const double2 v = V[kk * EG_LD + i];
+        W1[i * NSC + bins[kk]] = make_double2(v.x * ax[kk], -v.y * ax[kk]);            // G = V^H |x|
+        W2[bins[kk] * NSC + i] = make_double2(v.x / ax[kk], v.y / ax[kk]);             // G2 = |x|^-1 V
+    }
+    if (dc >= 0 && tid < nb) {                                     // p = G b,  b = R[N, d]
+        double2 acc = make_double2(0, 0);
+        for (int kk = 0; kk < nb; ++kk) {
+            const double2 v = V[kk * EG_LD + tid];
+            const double2 g = make_double2(v.x * ax[kk], -v.y * ax[kk]);
+            const double2 b = R[bins[kk] * NSC + dc];
+            acc.x += g.x * b.x - g.y * b.y; acc.y += g.x * b.y + g.y * b.x;
+        }
+        p[tid] = acc;
+    }
+    if (tid == 0) {
+        scal[0] = dc >= 0 ? R[dc * NSC + dc].x : 0.0;
+        scal[1] = dc >= 0 ? 1.0 / absx2[dc] : 0.0;
+        scal[2] = (double)dc;
+        scal[3] = (double)nb;
+    }
+}
+
+cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, void *W2, double *lam, void *p, double *scal, int *info,
+                               cudaStream_t s)
+{
+    const size_t smem = sizeof(double2) * (2 * EG_N * EG_LD + 64);
+    cudaError_t e = cudaFuncSetAttribute(eig_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    eig_prepare_kernel<<<1, EG_THREADS, smem, s>>>((const double2 *)R64, absx2, (double2 *)W1, (double2 *)W2, lam, (double2 *)p, scal, info);
+    g_last_launches = 1;
+    return cudaGetLastError();
+}
+
+// ---- between the two products: v = s (.) (u - p z_d), in place; the null bin's H is stashed in v[52] ----
+template <typename T>
+__global__ void __launch_bounds__(256) eig_mid_kernel(cx<T> *__restrict__ U, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx,
+                                                      int64_t frame_stride, const T *__restrict__ sigma2, const double *__restrict__ lam,
+                                                      const double2 *__restrict__ p, const double *__restrict__ scal, int64_t n_frames)
+{
+    const int lane = threadIdx.x & 31;
+    const int dc = (int)scal[2];
+    const T Rdd = (T)scal[0], md = (T)scal[1];
+    // this lane's eigen indices: lane and lane + 32
+    const T l0 = (T)lam[lane], l1 = lane + 32 < NSC ? (T)lam[lane + 32] : (T)0;
+    const cx<T> p0 = mk<T>((T)p[lane].x, (T)p[lane].y);
+    const cx<T> p1 = lane + 32 < NSC ? mk<T>((T)p[lane + 32].x, (T)p[lane + 32].y) : mk<T>(0, 0);
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < n_frames; f += wstride) {
+        cx<T> *u = U + f * NSC;
+        const T s2 = sigma2[f];
+        cx<T> u0 = u[lane], u1 = lane + 32 < NSC ? u[lane + 32] : mk<T>(0, 0);
+        const T i0 = (T)1 / (l0 + s2), i1 = (T)1 / (l1 + s2);
+        cx<T> zd = mk<T>(0, 0);
+        if (dc >= 0) {                                             // warp-uniform
+            // beta = sum conj(p_i) u_i / (l_i + s2), gamma = sum |p_i|^2 / (l_i + s2)   (p is zero beyond the eigen pairs)
+            T br = (p0.x * u0.x + p0.y * u0.y) * i0 + (p1.x * u1.x + p1.y * u1.y) * i1;
+            T bi = (p0.x * u0.y - p0.y * u0.x) * i0 + (p1.x * u1.y - p1.y * u1.x) * i1;
+            T ga = (p0.x * p0.x + p0.y * p0.y) * i0 + (p1.x * p1.x + p1.y * p1.y) * i1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                br += __shfl_xor_sync(0xffffffffu, br, o);
+                bi += __shfl_xor_sync(0xffffffffu, bi, o);
+                ga += __shfl_xor_sync(0xffffffffu, ga, o);
+            }
+            const cx<T> yd = cdiv(rx[f * frame_stride + dc], tx[f * frame_stride + dc]);
+            const T q = Rdd - ga, den = s2 * md + q;
+            const cx<T> dlt = mk<T>(yd.x - br, yd.y - bi);
+            zd = mk<T>(dlt.x / den, dlt.y / den);
+            if (lane == 0) u[NSC - 1] = mk<T>(br + dlt.x * (q / den), bi + dlt.y * (q / den));      // H_d, picked up by eig_fin
+        }
+        // v_i = s_i (u_i - p_i z_d),  s_i = s2 / (l_i + s2)
+        const cx<T> w0 = csub(u0, cmul(p0, zd)), w1 = csub(u1, cmul(p1, zd));
+        u[lane] = mk<T>(w0.x * (s2 * i0), w0.y * (s2 * i0));
+        if (lane + 32 < NSC && !(dc >= 0 && lane + 32 == NSC - 1)) u[lane + 32] = mk<T>(w1.x * (s2 * i1), w1.y * (s2 * i1));
+    }
+}
+
+// ---- after the second product (H holds c = G2 v): H = rx/tx - c, null bin from the stash; one thread per value ----
+template <typename T>
+__global__ void __launch_bounds__(256) eig_fin_kernel(cx<T> *__restrict__ H, const cx<T> *__restrict__ V, const cx<T> *__restrict__ tx,
+                                                      const cx<T> *__restrict__ rx, int64_t frame_stride, const double *__restrict__ scal,
+                                                      int64_t n_elems)
+{
+    const int dc = (int)scal[2];
+    const int64_t e0 = (int64_t)blockIdx.x * 256;
+    const int64_t fb = e0 / NSC;                                   // one 64-bit division per thread, 32-bit arithmetic below
+    const unsigned rem = (unsigned)(e0 - fb * NSC) + threadIdx.x;
+    const int64_t e = e0 + threadIdx.x;
+    if (e >= n_elems) return;
+    const unsigned q = rem / NSC, k = rem - q * NSC;
+    const int64_t f = fb + q;
+    cx<T> h;
+    if ((int)k == dc) h = V[f * NSC + NSC - 1];
+    else h = csub(cdiv(ld_stream(rx + f * frame_stride + k), ld_stream(tx + f * frame_stride + k)), H[e]);
+    st_stream(H + e, h);
+}
+
+cudaError_t launch_eig_mid(wifi_dtype dt, void *U, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                           const double *lam, const void *p, const double *scal, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_frames + 7) / 8, 148 * 8);
+    if (dt == WIFI_F32)
+        eig_mid_kernel<float><<<grid, 256, 0, s>>>((float2 *)U, (const float2 *)tx, (const float2 *)rx, frame_stride, (const float *)sigma2, lam,
+                                                   (const double2 *)p, scal, n_frames);
+    else
+        eig_mid_kernel<double><<<grid, 256, 0, s>>>((double2 *)U, (const double2 *)tx, (const double2 *)rx, frame_stride, (const double *)sigma2,
+                                                    lam, (const double2 *)p, scal, n_frames);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eig_fin(wifi_dtype dt, void *H, const void *V, const void *tx, const void *rx, int64_t frame_stride, const double *scal,
+                           int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const int64_t n_elems = n_frames * NSC;
+    const unsigned grid = (unsigned)((n_elems + 255) / 256);
+    if (dt == WIFI_F32)
+        eig_fin_kernel<float><<<grid, 256, 0, s>>>((float2 *)H, (const float2 *)V, (const float2 *)tx, (const float2 *)rx, frame_stride, scal, n_elems);
+    else
+        eig_fin_kernel<double><<<grid, 256, 0, s>>>((double2 *)H, (const double2 *)V, (const double2 *)tx, (const double2 *)rx, frame_stride, scal,
+                                                    n_elems);
+    return cudaGetLastError();
+}
+
+}  // namespace wifi

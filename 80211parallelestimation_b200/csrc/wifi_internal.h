@@ -67,6 +67,14 @@ cudaError_t launch_synth(wifi_dtype dt, uint64_t seed, int64_t first, int64_t n,
 cudaError_t launch_synth_cov(void *R64, cudaStream_t s);
 cudaError_t launch_error_stats(wifi_dtype dt, const void *H, const void *Href, int64_t n_elems, double *stats, cudaStream_t s);
 
+// eigen-domain per-frame MMSE (wifi_eig.cu)
+cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, void *W2, double *lam, void *p, double *scal, int *info,
+                               cudaStream_t s);
+cudaError_t launch_eig_mid(wifi_dtype dt, void *U, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                           const double *lam, const void *p, const double *scal, int64_t n_frames, cudaStream_t s);
+cudaError_t launch_eig_fin(wifi_dtype dt, void *H, const void *V, const void *tx, const void *rx, int64_t frame_stride, const double *scal,
+                           int64_t n_frames, cudaStream_t s);
+
 // measured ceilings (wifi_peaks.cu): which = 0 FP32 FMA, 1 FP64 FMA, 2 FP64 DMMA (TFLOP/s), 3 streaming copy (GB/s)
 cudaError_t measure_peak(int which, double *value, cudaStream_t s);
 

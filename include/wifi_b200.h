@@ -128,6 +128,15 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols,
 int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols,
                              const void *rx_symbols, int64_t frame_stride, const void *sigma2, void *H,
                              int64_t n_frames, int flags);
+/* Per-frame case in the eigen domain, for frames that share their modulus pattern |tx_k|^2 (any constant-modulus
+ * constellation; signs/phases are free): with S = |x| R |x| = V L V^H computed once (FP64 Jacobi on the device),
+ * H = y - G2 (s_f (.) (G y)), s_fi = sigma2_f/(l_i + sigma2_f) -- two shared-matrix products on the tensor cores instead of
+ * a 53x53 solve per frame, and accurate to ~1e-5 in FP32.  At most one null bin (|x_k|^2 < 1e-6 max, e.g. DC) is carried
+ * exactly as a border.  R: 53x53 double2 (device), absx2: 53 doubles (device).  The frames passed to the apply call MUST
+ * have |tx_k|^2 == absx2[k]; this is not checked. */
+int wifi_mmse_eig_prepare(wifi_ctx *ctx, const void *R_f64, const double *absx2_f64);
+int wifi_mmse_perframe_eig_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                                 int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
 /* C calling convention of main.c:148 batched: R_f = H_ls,f H_ls,f^H (main.c:186-189 intent),
  * tx/rx block vectors [n][53], ow2 [n] real, H_ls [n][53] -> H [n][53] */
 int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
@@ -177,6 +186,8 @@ int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, 
                           int64_t frame_stride, void *H, int64_t n_frames);
 int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols, const void *rx_symbols,
                             int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames, int flags);
+int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                                int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
 int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                          const void *ow2, const void *H_ls, void *H, int64_t n_frames);
 int wifi_cmatmul_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch);

@@ -355,6 +355,45 @@ def test_mmse_perframe_hpd_ragged_and_strided(ctx, wifi, oracle, prec, flags, n)
     assert np.isfinite(got).all()
 
 
+@pytest.mark.parametrize("prec,tol", [("f64", 2e-10), ("f32", 1e-4)])
+@pytest.mark.parametrize("rank", ["rank4", "full"])
+@pytest.mark.parametrize("n", [1, 9, 300])
+def test_mmse_perframe_eigen_domain(ctx, oracle, prec, tol, rank, n):
+    """Eigen-domain per-frame PS_MMSE (frames share |tx_k|^2: BPSK data, DC = -1e-4 carried as a border) against the
+    long-double per-frame solve of the oracle, over sigma2 in [1e-8, 1e-5].  FP64: measured 5e-11; FP32 (3xTF32 products):
+    measured ~3e-5 -- the plain FP32 elimination of R + D is at 3.7e-3."""
+    fr = synth.make_frames(n, seed=500 + n, sigma2="perframe", dtype=CDT[prec])
+    tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
+    s2 = fr["sigma2"].astype(np.float64 if prec == "f64" else np.float32)
+    R = synth.channel_covariance()
+    if rank == "full":
+        R = R + synth.random_hpd(np.random.default_rng(3), scale=1e-6)
+    R = R.astype(CDT[prec]).astype(np.complex128)                        # the problem both sides solve
+    absx2 = np.abs(tx[0].astype(np.complex128)) ** 2
+    assert np.array_equal(np.abs(tx) ** 2, np.broadcast_to(np.abs(tx[0]) ** 2, tx.shape))
+    ctx.mmse_eig_prepare(R, absx2)
+    got = host(ctx.mmse_perframe_eig(dev(tx), dev(rx), dev(s2)))
+    pick = np.unique(np.r_[0, n - 1, np.random.default_rng(n).integers(0, n, 40)])
+    ref = oracle.mmse_perframe(R, tx[pick].astype(np.complex128), rx[pick].astype(np.complex128), s2[pick].astype(np.float64))
+    assert rel_err(got[pick], ref) < tol
+    assert np.isfinite(got).all()
+    if n == 300:                                                       # whole frames in place + host pointers
+        g2 = host(ctx.mmse_perframe_eig(dev(fr["tx_symb"]).reshape(-1), dev(fr["rx_symb"]).reshape(-1), dev(s2), frame_stride=15 * NSC, n_frames=n))
+        assert np.array_equal(g2, got)
+        g3 = ctx.mmse_perframe_eig(tx, rx, s2)
+        assert np.array_equal(g3, got)
+
+
+def test_mmse_eigen_domain_needs_prepare_and_one_null_bin(wifi):
+    c = wifi.WifiContext(0)
+    z = np.zeros((1, NSC), np.complex128) + 1
+    with pytest.raises(wifi.WifiError):
+        c.mmse_perframe_eig(dev(z), dev(z), dev(np.ones(1)))
+    a = np.full(NSC, 78.0); a[3] = a[26] = 1e-9
+    with pytest.raises(wifi.WifiError):
+        c.mmse_eig_prepare(synth.channel_covariance(), a)
+
+
 # ------------------------------------------------------------------ utils.h
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_utils_vs_reference(ctx, wifi, gold, prec):
