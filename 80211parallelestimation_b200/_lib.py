@@ -37,6 +37,7 @@ SIGNATURES = {
     "wifi_mmse_eig_prepare": [_vp, _vp, _vp],
     "wifi_mmse_perframe_eig_batch": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
+    "wifi_mmse_matlab_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_batch": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_chermitian_batch": [_vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_cadd_batch": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
@@ -56,6 +57,7 @@ SIGNATURES = {
     "wifi_mmse_perframe_host": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
     "wifi_mmse_perframe_eig_host": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
+    "wifi_mmse_matlab_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_host": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_chermitian_host": [_vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_cadd_host": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],

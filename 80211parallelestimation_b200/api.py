@@ -305,6 +305,23 @@ class WifiContext:
         self._ck(fn(self.h, dt, tx.ptr, rx.ptr, s.ptr, h.ptr, _ptr(H), n))
         return H
 
+    def mmse_matlab(self, tx_frames, rx_frames, ow2, H_ls, out=None):
+        """WiFi_channel_estimation_PS_MMSE.m as written, averaged over OFDM blocks 1..4: tx/rx [n][15][53], H_ls [n][53]."""
+        tx, rx, h = _Arg(tx_frames), _Arg(rx_frames), _Arg(H_ls)
+        dev, dt = _same(tx, rx, h)
+        n = tx.size // FRAME
+        rdt = np.float32 if dt == F32 else np.float64
+        s = np.broadcast_to(np.asarray(ow2, rdt), (n,)).copy() if not _is_torch(ow2) else ow2
+        if dev and not _is_torch(s):
+            import torch
+            s = torch.from_numpy(s).to(tx.x.device)
+        s = _Arg(s, real=True)
+        H = out if out is not None else h.empty_like((n, NSC))
+        self._sync_stream(dev)
+        fn = self.lib.wifi_mmse_matlab_batch if dev else self.lib.wifi_mmse_matlab_host
+        self._ck(fn(self.h, dt, tx.ptr, rx.ptr, s.ptr, h.ptr, _ptr(H), n))
+        return H
+
     # ---- utils.h ----
     @staticmethod
     def _mat(a):

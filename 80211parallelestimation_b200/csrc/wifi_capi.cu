@@ -342,6 +342,21 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
     return mmse_shared(ctx, dt, tx, rx, frame_stride, H, n, ctx->stream);
 }
 
+static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
+                         const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check);
+
+// R_f = H_ls H_ls^H: closed form (wifi_ls.cu mmse_rank1_kernel); WIFI_B200_CCONV=solve keeps the general pivoted solve of
+// R_f + D for A/B checks (C convention only)
+static int mmse_cconv(wifi_ctx *ctx, wifi_dtype dt, int matlab, const void *tx, const void *rx, int64_t frame_stride, const void *ow2,
+                      const void *hls, void *H, int64_t n, cudaStream_t s)
+{
+    static const int use_solve = [] { const char *e = getenv("WIFI_B200_CCONV"); return e && !strcmp(e, "solve"); }();
+    if (use_solve && !matlab) return mmse_perframe(ctx, dt, nullptr, tx, rx, frame_stride, ow2, hls, H, n, WIFI_SOLVE_PIVOT, s, false);
+    Timed t(ctx, s);
+    CK(launch_mmse_rank1(dt, matlab, tx, rx, frame_stride, ow2, hls, H, n, s));
+    return WIFI_OK;
+}
+
 int wifi_mmse_eig_prepare(wifi_ctx *ctx, const void *R, const double *absx2)
 {
     ENTER();
@@ -397,7 +412,15 @@ int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const vo
 {
     ENTER();
     NEED(n >= 0 && (n == 0 || (tx && rx && ow2 && H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
-    return mmse_perframe(ctx, dt, nullptr, tx, rx, WIFI_NSC, ow2, H_ls, H, n, WIFI_SOLVE_PIVOT, ctx->stream, false);
+    return mmse_cconv(ctx, dt, 0, tx, rx, WIFI_NSC, ow2, H_ls, H, n, ctx->stream);
+}
+
+int wifi_mmse_matlab_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, const void *rx_frames, const void *ow2, const void *H_ls,
+                           void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx_frames && rx_frames && ow2 && H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    return mmse_cconv(ctx, dt, 1, tx_frames, rx_frames, WIFI_FRAME, ow2, H_ls, H, n, ctx->stream);
 }
 
 // ---- utils ------------------------------------------------------------------------------------------
@@ -720,7 +743,19 @@ int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const voi
     const size_t row = WIFI_NSC * esize(dt);
     return host_pipeline(ctx, n, {in_arr(tx, row, row), in_arr(rx, row, row), in_arr(ow2, rsize(dt), rsize(dt)), in_arr(H_ls, row, row), out_arr(H, row)},
                          [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
-                             return mmse_perframe(ctx, dt, nullptr, d[0], d[1], WIFI_NSC, d[2], d[3], d[4], nc, WIFI_SOLVE_PIVOT, s, false);
+                             return mmse_cconv(ctx, dt, 0, d[0], d[1], WIFI_NSC, d[2], d[3], d[4], nc, s);
+                         });
+}
+
+int wifi_mmse_matlab_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, const void *rx_frames, const void *ow2, const void *H_ls,
+                          void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx_frames && rx_frames && ow2 && H_ls && H)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t row = WIFI_NSC * esize(dt), frow = WIFI_FRAME * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx_frames, 4 * row, frow), in_arr(rx_frames, 4 * row, frow), in_arr(ow2, rsize(dt), rsize(dt)), in_arr(H_ls, row, row), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return mmse_cconv(ctx, dt, 1, d[0], d[1], 4 * WIFI_NSC, d[2], d[3], d[4], nc, s);
                          });
 }
 

@@ -30,6 +30,10 @@ cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, 
 cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n_frames,
                             cudaStream_t s);
 
+// PS_MMSE with R_f = H_ls H_ls^H (main.c:148 convention) in closed form; matlab = 1: the .m text, averaged over blocks 0..3
+cudaError_t launch_mmse_rank1(wifi_dtype dt, int matlab, const void *tx, const void *rx, int64_t frame_stride, const void *ow2, const void *Hls,
+                              void *H, int64_t n_frames, cudaStream_t s);
+
 // receiver front-end (wifi_frontend.cu): packet [n][1200], lptot [n][160] -> symb [n][15][53], pre_fft [n][53], ow2 [n] (may be NULL)
 cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft, void *ow2,
                             int64_t n_frames, cudaStream_t s);

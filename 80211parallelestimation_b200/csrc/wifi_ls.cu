@@ -10,6 +10,7 @@
 //              stores of a warp are one contiguous run of the [n][53] output.
 //   equalize   flat over the contiguous [n][15][53] arrays like lt_ls (16-byte vectors, 4 in flight); the two channel
 //              values of an element are gathered through L1 (each is reused by the 15 OFDM blocks of its frame).
+#include <algorithm>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -326,6 +327,88 @@ cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, cons
             (const double2 *)rx, (const double2 *)Hlt, (const double2 *)Hps, (double2 *)eq, n_fk);
         ++g_last_launches;
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// PS_MMSE in the reference's own calling convention (main.c:148 / WiFi_channel_estimation_PS_MMSE.m): R_f = H_ls H_ls^H
+// ------------------------------------------------------------------------------------------
+// With the rank-one covariance the intended estimator  R (R + ow2 (X X^H)^-1)^-1 (rx/tx)  has the closed form (Sherman-
+// Morrison)
+//     H = H_ls * (v^H rx) / (ow2 + v^H v),   v = tx (.) H_ls
+// -- 212 complex values of traffic per frame instead of a 53 x 53 solve (the pivoted kernel: 11 M frames/s).
+// MODE 1 is the MATLAB text as written (WiFi_channel_estimation_PS_MMSE.m:27-33: Rhy = Rhh F' X with X NOT conjugated,
+// result averaged over OFDM blocks 1..4 of whole frames):  c_b = (v'^H w),  w = (v v^H + ow2 I)^-1 rx,  v' = conj(tx) (.) H_ls,
+// evaluated with e = v' - v (exactly zero for real tx) so that the BPSK case carries no cancellation:
+//     c_b = a3/(ow2 + vv) + [er (ow2 + vv) - ev a3] / (ow2 (ow2 + vv)),   a3 = v^H rx, vv = v^H v, er = e^H rx, ev = e^H v.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) mmse_rank1_kernel(const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx, int64_t frame_stride,
+                                                         const T *__restrict__ ow2, const cx<T> *__restrict__ Hls, cx<T> *__restrict__ H,
+                                                         int64_t n_frames)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < n_frames; f += wstride) {
+        const bool second = lane + 32 < NSC;
+        const cx<T> h0 = Hls[f * NSC + lane], h1 = second ? Hls[f * NSC + lane + 32] : mk<T>(0, 0);
+        const T s2 = ow2[f];
+        cx<T> c = mk<T>(0, 0);
+#pragma unroll
+        for (int b = 0; b < (MODE == 1 ? 4 : 1); ++b) {
+            const cx<T> *tp = tx + f * frame_stride + b * NSC, *rp = rx + f * frame_stride + b * NSC;
+            const cx<T> x0 = ld_stream(tp + lane), r0 = ld_stream(rp + lane);
+            const cx<T> x1 = second ? ld_stream(tp + lane + 32) : mk<T>(0, 0), r1 = second ? ld_stream(rp + lane + 32) : mk<T>(0, 0);
+            const cx<T> v0 = cmul(x0, h0), v1 = cmul(x1, h1);
+            // a3 = v^H rx, vv = v^H v
+            T a3x = v0.x * r0.x + v0.y * r0.y + v1.x * r1.x + v1.y * r1.y;
+            T a3y = v0.x * r0.y - v0.y * r0.x + v1.x * r1.y - v1.y * r1.x;
+            T vv = v0.x * v0.x + v0.y * v0.y + v1.x * v1.x + v1.y * v1.y;
+            // MODE 1: e = v' - v = (conj(tx) - tx) (.) H_ls  (exactly zero for real tx);  er = e^H rx, ev = e^H v
+            T erx = 0, ery = 0, evx = 0, evy = 0;
+            if (MODE == 1) {
+                const cx<T> e0 = mk<T>((T)2 * x0.y * h0.y, (T)-2 * x0.y * h0.x), e1 = mk<T>((T)2 * x1.y * h1.y, (T)-2 * x1.y * h1.x);
+                erx = e0.x * r0.x + e0.y * r0.y + e1.x * r1.x + e1.y * r1.y;
+                ery = e0.x * r0.y - e0.y * r0.x + e1.x * r1.y - e1.y * r1.x;
+                evx = e0.x * v0.x + e0.y * v0.y + e1.x * v1.x + e1.y * v1.y;
+                evy = e0.x * v0.y - e0.y * v0.x + e1.x * v1.y - e1.y * v1.x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a3x += __shfl_xor_sync(0xffffffffu, a3x, o); a3y += __shfl_xor_sync(0xffffffffu, a3y, o);
+                vv += __shfl_xor_sync(0xffffffffu, vv, o);
+                if (MODE == 1) {
+                    erx += __shfl_xor_sync(0xffffffffu, erx, o); ery += __shfl_xor_sync(0xffffffffu, ery, o);
+                    evx += __shfl_xor_sync(0xffffffffu, evx, o); evy += __shfl_xor_sync(0xffffffffu, evy, o);
+                }
+            }
+            const T den = s2 + vv;
+            if (MODE == 0) {
+                c = mk<T>(a3x / den, a3y / den);
+            } else {
+                // v'^H w = [a1 ow2 + (a1 vv - a2 a3)] / (ow2 (ow2 + vv)) with a1 = a3 + er, a2 = vv + ev:
+                //        = a3 / (ow2 + vv) + [er (ow2 + vv) - ev a3] / (ow2 (ow2 + vv))       (second term: complex tx only)
+                const T dx = erx * den - (evx * a3x - evy * a3y), dy = ery * den - (evx * a3y + evy * a3x);
+                c.x += a3x / den + dx / (s2 * den);
+                c.y += a3y / den + dy / (s2 * den);
+            }
+        }
+        if (MODE == 1) c = mk<T>(c.x * (T)0.25, c.y * (T)0.25);
+        st_stream(H + f * NSC + lane, cmul(h0, c));
+        if (second) st_stream(H + f * NSC + lane + 32, cmul(h1, c));
+    }
+}
+
+cudaError_t launch_mmse_rank1(wifi_dtype dt, int matlab, const void *tx, const void *rx, int64_t frame_stride, const void *ow2, const void *Hls,
+                              void *H, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_frames + 7) / 8, (int64_t)148 * 8);
+#define R1(T, M) mmse_rank1_kernel<T, M><<<grid, 256, 0, s>>>((const cx<T> *)tx, (const cx<T> *)rx, frame_stride, (const T *)ow2, (const cx<T> *)Hls, (cx<T> *)H, n_frames)
+    if (dt == WIFI_F32) { if (matlab) R1(float, 1); else R1(float, 0); }
+    else { if (matlab) R1(double, 1); else R1(double, 0); }
+#undef R1
     return cudaGetLastError();
 }
 

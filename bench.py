@@ -240,7 +240,12 @@ def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
                                                     "four-pass implementation moves ~3.7x that")
         out["mmse_perframe_eig_" + prec]["speedup_vs_direct_solve"] = (out["mmse_perframe_eig_" + prec]["frames_per_s"] /
                                                                       out["mmse_perframe_hpd_" + prec]["frames_per_s"])
-        del He, s2n
+        s2n2 = s2n
+        del He
+        # PS_MMSE in main.c:148's calling convention (R_f = H_ls H_ls^H), rank-one closed form: 212 c + ow2 per frame
+        Hc = torch.empty_like(tx0)
+        out["mmse_cconv_" + prec] = rate(lambda: ctx.mmse_cconv(tx0, rx0, s2n2, H, out=Hc), n, 212 * cbytes + cbytes // 2)
+        del Hc
         npv = min(npf, 1 << 15)
         out["mmse_perframe_pivot_" + prec] = rate(
             lambda: ctx.mmse_perframe(Rp, tx0[:npv], rx0[:npv], s2[:npv], flags=wifi.SOLVE_PIVOT, out=Hp[:npv]), npv, 159 * cbytes, 441949,

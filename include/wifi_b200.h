@@ -141,6 +141,11 @@ int wifi_mmse_perframe_eig_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_sy
  * tx/rx block vectors [n][53], ow2 [n] real, H_ls [n][53] -> H [n][53] */
 int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                           const void *ow2, const void *H_ls, void *H, int64_t n_frames);
+/* WiFi_channel_estimation_PS_MMSE.m as written (Rhh = ifft(H_ls) ifft(H_ls)', X unconjugated in Rhy), averaged over OFDM
+ * blocks 1..4: tx/rx whole frames [n][15][53], ow2 [n] real, H_ls [n][53] -> H [n][53].  Both calls use the closed form of
+ * the rank-one covariance, H = H_ls (v^H rx)/(ow2 + v^H v), v = tx (.) H_ls (212 complex values of traffic per frame). */
+int wifi_mmse_matlab_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, const void *rx_frames,
+                           const void *ow2, const void *H_ls, void *H, int64_t n_frames);
 
 /* ---- batched complex matrix utils (utils.h:38-60), order <= WIFI_MAX_ORDER --------- */
 /* multiply utils.c:16-31: C[b] = A[b] (r1 x c1) * B[b] (r2 x c2); c1 != r2 -> WIFI_ERR_INVALID, nothing written */
@@ -190,6 +195,8 @@ int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_sym
                                 int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
 int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                          const void *ow2, const void *H_ls, void *H, int64_t n_frames);
+int wifi_mmse_matlab_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, const void *rx_frames,
+                          const void *ow2, const void *H_ls, void *H, int64_t n_frames);
 int wifi_cmatmul_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch);
 int wifi_chermitian_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch);
 int wifi_cadd_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch);

@@ -355,6 +355,45 @@ def test_mmse_perframe_hpd_ragged_and_strided(ctx, wifi, oracle, prec, flags, n)
     assert np.isfinite(got).all()
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [1, 8, 9, 1000])
+def test_mmse_cconv_closed_form(ctx, oracle, prec, n):
+    """main.c:148's calling convention (R_f = H_ls H_ls^H) through the rank-one closed form, against the oracle's full
+    long-double 53x53 solve of the same system; complex (QPSK-like) tx included."""
+    fr = synth.make_frames(n, seed=60 + n, sigma2="perframe", dtype=CDT[prec])
+    rng = np.random.default_rng(n)
+    tx = (fr["tx_symb"][:, 0, :] * np.exp(0.5j * np.pi * rng.integers(0, 4, (n, NSC)))).astype(CDT[prec])      # QPSK phases
+    rx = (fr["rx_symb"][:, 0, :] * (tx / fr["tx_symb"][:, 0, :])).astype(CDT[prec])
+    hls = (fr["H_true"] * (1 + 0.01 * rng.standard_normal((n, NSC)))).astype(CDT[prec]); hls[:, 26] = 0
+    ow2 = fr["sigma2"].astype(np.float64 if prec == "f64" else np.float32)
+    got = host(ctx.mmse_cconv(dev(tx), dev(rx), dev(ow2), dev(hls)))
+    pick = np.unique(np.r_[0, n - 1, rng.integers(0, n, 24)])
+    ref = oracle.mmse_cconv_batch(r32(tx[pick], prec), r32(rx[pick], prec), ow2[pick].astype(np.float64), r32(hls[pick], prec))
+    assert rel_err(got[pick], ref) < TOL[prec]
+    assert np.all(got[:, 26] == 0)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_mmse_matlab_mode(ctx, oracle, gold, prec):
+    """WiFi_channel_estimation_PS_MMSE.m as written (one 53x53 system per OFDM block, blocks 1..4 averaged) on the matlab.mat
+    frame and on synthetic frames, against the oracle's restatement of the .m text.  (matlab.mat holds no MMSE output:
+    parity unpinned by the reference's artifacts)"""
+    m, g = gold["matlab_mat"], gold["inputs_h"]
+    cases = [(m["tx_symb"].T.reshape(1, NBLK, NSC), m["rx_symb"].T.reshape(1, NBLK, NSC), m["H_EST_LT_LS"].reshape(1, NSC), np.array([float(g["ow2"])]))]
+    fr = synth.make_frames(5, seed=9, sigma2="perframe")
+    cases.append((fr["tx_symb"], fr["rx_symb"], oracle.lt_ls(fr["tx_pre"], fr["rx_pre"]), fr["sigma2"]))
+    for tx, rx, hls, ow2 in cases:
+        tx, rx, hls = tx.astype(CDT[prec]), rx.astype(CDT[prec]), hls.astype(CDT[prec])
+        ow2 = ow2.astype(np.float64 if prec == "f64" else np.float32)
+        got = host(ctx.mmse_matlab(dev(tx), dev(rx), dev(ow2), dev(hls)))
+        ref = np.zeros((tx.shape[0], NSC), np.complex128)
+        for f in range(tx.shape[0]):
+            for b in range(4):
+                ref[f] += oracle.mmse_matlab_block(r32(tx[f, b], prec), r32(rx[f, b], prec), float(ow2[f]), r32(hls[f], prec)) / 4
+        assert rel_err(got, ref) < (1e-9 if prec == "f64" else 1e-4)          # the oracle's own G-J solve is ~1e-10 here
+        assert np.array_equal(ctx.mmse_matlab(tx, rx, ow2, hls), got)          # host pointers
+
+
 @pytest.mark.parametrize("prec,tol", [("f64", 2e-10), ("f32", 1e-4)])
 @pytest.mark.parametrize("rank", ["rank4", "full"])
 @pytest.mark.parametrize("n", [1, 9, 300])
