@@ -202,7 +202,18 @@ def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
         out["ps_linear_" + prec] = rate(lambda: ctx.ps(fr["tx_symb"], fr["rx_symb"], ("linear",), out=o1), n, 61 * cbytes)
         eq = torch.empty_like(fr["rx_symb"])
         out["equalize_" + prec] = rate(lambda: ctx.equalize(fr["rx_symb"], H, outs["linear"], out=eq), n, 1696 * cbytes)
-        del eq
+        # BASELINE configs[4] per GPU: all five estimators + the equalizer on whole frames, in place (block 0 at stride 795)
+        Hm5 = torch.empty_like(H)
+        txf, rxf = fr["tx_symb"].reshape(-1), fr["rx_symb"].reshape(-1)
+
+        def all5():
+            ctx.lt_ls(fr["tx_pre"], fr["rx_pre"], out=H)
+            ctx.ps(fr["tx_symb"], fr["rx_symb"], out=outs)
+            ctx.mmse_shared(txf, rxf, frame_stride=NBLK * NSC, n_frames=n, out=Hm5)
+            ctx.equalize(fr["rx_symb"], H, outs["linear"], out=eq)
+        out["all5_plus_equalizer_" + prec] = rate(all5, n, (159 + 167 + 159 + 1696) * cbytes)
+        out["all5_plus_equalizer_" + prec]["note"] = "LT_LS + PS_Linear/Cubic/Sinc + shared-filter PS_MMSE + equalizer, 4 launches per pass"
+        del eq, Hm5, txf, rxf
         tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
         del fr
         # receiver front-end: 15 x 64 packet samples + 128 lptot samples in, 15 x 53 + 53 values + ow2 out
