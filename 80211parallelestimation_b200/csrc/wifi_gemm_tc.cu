@@ -187,10 +187,20 @@ template <bool FUSED> __device__ __forceinline__ float4 ls_pair(float4 a, float4
     return make_float4(h0.x, h0.y, h1.x, h1.y);
 }
 
-template <bool FUSED>
+// RESID (the second product of the eigen-domain per-frame MMSE, wifi_eig.cu): the epilogue writes  res_rx/res_tx - acc  instead
+// of acc, and the null bin `dc` (if any) takes the value stashed in column 52 of the A operand's row.
+struct TcResid {
+    const float2 *tx, *rx;      // the frames' block vectors (y = rx/tx is recomputed: cheaper than a round trip through HBM)
+    int64_t stride;
+    const float2 *stash;        // [n][53]; element [f][52] = H of the null bin
+    int dc;                     // null bin index or -1
+};
+
+template <bool FUSED, bool RESID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
-                          const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16)
+                          const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16,
+                          TcResid res)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(tc_smem_raw);
@@ -275,6 +285,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // ---- c. epilogue of this group's previous tile (it-2); must precede this iteration's a_ready arrival ----
             if (it >= 2) {
                 const int pt = it - 2;
+                if (RESID && lane == 0 && res.stride == NSC) {           // the epilogue's own inputs: HBM -> L2 while the MMAs finish
+                    const int64_t fe = (blockIdx.x + (int64_t)pt * gridDim.x) * TC_M + quarter * 32;
+                    if (fe + 32 <= n_frames && ((((uintptr_t)res.tx) | ((uintptr_t)res.rx)) & 15) == 0) {
+                        l2_prefetch(res.tx + fe * NSC, TC_CHUNK_F * 4);
+                        l2_prefetch(res.rx + fe * NSC, TC_CHUNK_F * 4);
+                    }
+                }
                 mbar_wait(&sm.bar_mma_done[pt & 1], (pt >> 1) & 1);
                 tc_fence_after();
                 const int64_t tile = blockIdx.x + (int64_t)pt * gridDim.x;
@@ -295,7 +312,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (valid == 32 && aligned16) {
+                if (RESID) {
+                    // H = rx/tx - acc, null bin from the stash
+                    const bool rvec = res.stride == NSC && ((((uintptr_t)res.tx) | ((uintptr_t)res.rx) | ((uintptr_t)H)) & 15) == 0;
+                    if (valid == 32 && rvec) {
+                        const float4 *b4 = reinterpret_cast<const float4 *>(buf);
+                        const float4 *pt4 = reinterpret_cast<const float4 *>(res.tx + f0 * NSC), *pr4 = reinterpret_cast<const float4 *>(res.rx + f0 * NSC);
+                        float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
+#pragma unroll 9
+                        for (int i = 0; i < 27; ++i) {
+                            int q = i * 32 + lane;
+                            if (q < TC_CHUNK_F / 4) {
+                                const float4 y = ls_pair<true>(ld_stream(pt4 + q), ld_stream(pr4 + q)), c = b4[q];
+                                st_stream(po + q, make_float4(y.x - c.x, y.y - c.y, y.z - c.z, y.w - c.w));
+                            }
+                        }
+                    } else {
+                        const float2 *b2 = reinterpret_cast<const float2 *>(buf);
+                        for (int e = lane; e < valid * NSC; e += 32) {
+                            const int r = e / NSC, k = e - r * NSC;
+                            const int64_t off = (f0 + r) * res.stride + k;
+                            const float2 y = cdiv_fast(ld_stream(res.rx + off), ld_stream(res.tx + off)), c = b2[e];
+                            H[f0 * NSC + e] = make_float2(y.x - c.x, y.y - c.y);
+                        }
+                    }
+                    if (res.dc >= 0) {
+                        __syncwarp();                    // orders this warp's stores above before the one below (same addresses)
+                        if (lane < valid) H[(f0 + lane) * NSC + res.dc] = res.stash[(f0 + lane) * NSC + NSC - 1];
+                    }
+                } else if (valid == 32 && aligned16) {
                     const float4 *b4 = reinterpret_cast<const float4 *>(buf);
                     float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
 #pragma unroll 9
@@ -423,29 +468,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
+template <bool FUSED, bool RESID>
+static cudaError_t launch_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
+                             const TcResid &res, cudaStream_t s)
+{
+    const size_t smem = sizeof(TcSmem);
+    const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
+    const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;
+    cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmse_shared_tc_kernel<FUSED, RESID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
+                                                                       (float2 *)H, n_frames, aligned16, res);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
                                   int64_t n_frames, cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const size_t smem = sizeof(TcSmem);
-    const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
-    const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;
-    cudaError_t e;
-    if (rx) {
-        e = cudaFuncSetAttribute(mmse_shared_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mmse_shared_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
-                                                                   (float2 *)H, n_frames, aligned16);
-    } else {
-        e = cudaFuncSetAttribute(mmse_shared_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mmse_shared_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, nullptr, NSC, (float2 *)H,
-                                                                    n_frames, aligned16);
-    }
-    return cudaGetLastError();
+    const TcResid none = {nullptr, nullptr, 0, nullptr, -1};
+    return rx ? launch_tc<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+              : launch_tc<false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
+}
+
+// H = rx/tx - v W^T (W = img), null bin `dc` from v[f][52]: the second product of the eigen-domain per-frame MMSE
+cudaError_t launch_mmse_shared_tc_resid(const FilterImages &img, const void *v, const void *tx, const void *rx, int64_t frame_stride,
+                                        int dc, void *H, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const TcResid res = {(const float2 *)tx, (const float2 *)rx, frame_stride, (const float2 *)v, dc};
+    return launch_tc<false, true>(img, v, nullptr, NSC, H, n_frames, res, s);
 }
 
 }  // namespace wifi
