@@ -548,7 +548,12 @@ struct Arr {
     size_t pitch_bytes;  // host distance between consecutive frames
 };
 
-constexpr size_t CHUNK_BYTES = 48u << 20;   // per-array staging target per chunk
+static size_t chunk_bytes()
+{
+    static const size_t v = [] { const char *e = getenv("WIFI_B200_HOST_CHUNK_MB"); long mb = e ? atol(e) : 48; return (size_t)(mb > 0 ? mb : 48) << 20; }();
+    return v;
+}
+#define CHUNK_BYTES chunk_bytes()   // per-array staging target per chunk (WIFI_B200_HOST_CHUNK_MB, default 48: 1 Mi frames e2e 18.2 ms at 48 MB, 18.9 at 16, 22.4 at 4 -- the pass is H2D-bound at ~49 GB/s)
 
 // Runs `body(dev_ptrs, n_chunk, stream)` over chunks of frames; arrays are staged compactly (pitch = row_bytes).
 template <typename Body>
