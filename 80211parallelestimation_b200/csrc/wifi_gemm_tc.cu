@@ -299,6 +299,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
                 const uint32_t dcol = lane_base + ((pt & 1) ? TC_COL_D1 : TC_COL_D0);
                 float2 *rowo = reinterpret_cast<float2 *>(buf + lane * TC_ROWF);
+                // RESID: the epilogue's own inputs (tx, rx of this chunk) in three batches of 9 + 9 vectors; the first batch is
+                // issued before the TMEM -> shared staging below and each next one before the previous is consumed
+                constexpr int RB = 9;
+                float4 qt[2][RB], qr[2][RB];
+                const bool rvec = RESID && valid == 32 && res.stride == NSC &&
+                                  ((((uintptr_t)res.tx) | ((uintptr_t)res.rx) | ((uintptr_t)H)) & 15) == 0;
+                const float4 *pt4 = RESID ? reinterpret_cast<const float4 *>(res.tx + f0 * NSC) + lane : nullptr;
+                const float4 *pr4 = RESID ? reinterpret_cast<const float4 *>(res.rx + f0 * NSC) + lane : nullptr;
+                if (rvec) {
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) { qt[0][j] = ld_stream(pt4 + 32 * j); qr[0][j] = ld_stream(pr4 + 32 * j); }
+                }
 #pragma unroll
                 for (int g = 0; g < TC_N / 16; ++g) {
                     uint32_t v[16];
@@ -314,17 +326,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 __syncwarp();
                 if (RESID) {
                     // H = rx/tx - acc, null bin from the stash
-                    const bool rvec = res.stride == NSC && ((((uintptr_t)res.tx) | ((uintptr_t)res.rx) | ((uintptr_t)H)) & 15) == 0;
-                    if (valid == 32 && rvec) {
-                        const float4 *b4 = reinterpret_cast<const float4 *>(buf);
-                        const float4 *pt4 = reinterpret_cast<const float4 *>(res.tx + f0 * NSC), *pr4 = reinterpret_cast<const float4 *>(res.rx + f0 * NSC);
-                        float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
-#pragma unroll 9
-                        for (int i = 0; i < 27; ++i) {
-                            int q = i * 32 + lane;
-                            if (q < TC_CHUNK_F / 4) {
-                                const float4 y = ls_pair<true>(ld_stream(pt4 + q), ld_stream(pr4 + q)), c = b4[q];
-                                st_stream(po + q, make_float4(y.x - c.x, y.y - c.y, y.z - c.z, y.w - c.w));
+                    if (rvec) {
+                        const float4 *b4 = reinterpret_cast<const float4 *>(buf) + lane;
+                        float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC) + lane;
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) {
+                            if (b < 2) {
+#pragma unroll
+                                for (int j = 0; j < RB; ++j) {
+                                    const int i = (b + 1) * RB + j;
+                                    if (i < 26 || (i == 26 && lane < 16)) { qt[(b + 1) & 1][j] = ld_stream(pt4 + 32 * i); qr[(b + 1) & 1][j] = ld_stream(pr4 + 32 * i); }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < RB; ++j) {
+                                const int i = b * RB + j;
+                                if (i < 26 || (i == 26 && lane < 16)) {
+                                    const float4 y = ls_pair<true>(qt[b & 1][j], qr[b & 1][j]), c = b4[32 * i];
+                                    st_stream(po + 32 * i, make_float4(y.x - c.x, y.y - c.y, y.z - c.z, y.w - c.w));
+                                }
                             }
                         }
                     } else {
