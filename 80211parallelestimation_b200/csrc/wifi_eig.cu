@@ -182,6 +182,16 @@ cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, v
     return cudaGetLastError();
 }
 
+// 1/x: FP32 with the hardware approximation + one Newton step (the IEEE '/' is ~12 instructions and a slow-path branch; the
+// mid pass was issue-bound at 76 % with eight of them per lane), FP64 exact
+__device__ __forceinline__ float rcp_t(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
+
 // ---- between the two products: v = s (.) (u - p z_d), in place; the null bin's H is stashed in v[52] ----
 template <typename T>
 __global__ void __launch_bounds__(256) eig_mid_kernel(cx<T> *__restrict__ U, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx,
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(256) eig_mid_kernel(cx<T> *__restrict__ U, con
                 if (dc >= 0) { ntd = tx[fn * frame_stride + dc]; nrd = rx[fn * frame_stride + dc]; }
             }
         }
-        const T i0 = (T)1 / (l0 + s2), i1 = (T)1 / (l1 + s2);
+        const T i0 = rcp_t(l0 + s2), i1 = rcp_t(l1 + s2);
         cx<T> zd = mk<T>(0, 0);
         if (dc >= 0) {                                             // warp-uniform
             // beta = sum conj(p_i) u_i / (l_i + s2), gamma = sum |p_i|^2 / (l_i + s2)   (p is zero beyond the eigen pairs)
@@ -232,11 +242,12 @@ __global__ void __launch_bounds__(256) eig_mid_kernel(cx<T> *__restrict__ U, con
                 bi += __shfl_xor_sync(0xffffffffu, bi, o);
                 ga += __shfl_xor_sync(0xffffffffu, ga, o);
             }
-            const cx<T> yd = cdiv(rd, td);
-            const T q = Rdd - ga, den = s2 * md + q;
+            const T itd = rcp_t(td.x * td.x + td.y * td.y);
+            const cx<T> yd = mk<T>((rd.x * td.x + rd.y * td.y) * itd, (rd.y * td.x - rd.x * td.y) * itd);
+            const T q = Rdd - ga, iden = rcp_t(s2 * md + q);
             const cx<T> dlt = mk<T>(yd.x - br, yd.y - bi);
-            zd = mk<T>(dlt.x / den, dlt.y / den);
-            if (lane == 0) u[NSC - 1] = mk<T>(br + dlt.x * (q / den), bi + dlt.y * (q / den));      // H_d, picked up by the last pass
+            zd = mk<T>(dlt.x * iden, dlt.y * iden);
+            if (lane == 0) u[NSC - 1] = mk<T>(br + dlt.x * (q * iden), bi + dlt.y * (q * iden));    // H_d, picked up by the last pass
         }
         // v_i = s_i (u_i - p_i z_d),  s_i = s2 / (l_i + s2)
         const cx<T> w0 = csub(u0, cmul(p0, zd)), w1 = csub(u1, cmul(p1, zd));

@@ -30,6 +30,14 @@ def main():
             if want("mmse_hpd"): ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD, out=H[: 1 << 16])
             if want("mmse_hpd") and prec == "f32":
                 ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE, out=H[: 1 << 16])
+            if want("eig") and rep == 0:
+                ctx.mmse_eig_prepare(R, (tx0[0].abs().to(torch.float64)) ** 2)
+            if want("eig"): ctx.mmse_perframe_eig(tx0, rx0, fr["sigma2"], out=H)
+            if want("rank1"): ctx.mmse_cconv(tx0, rx0, fr["sigma2"], outs["linear"], out=H)
+            if want("frontend") and rep == 0:
+                m = 1 << 17
+                cdt = torch.complex64 if prec == "f32" else torch.complex128
+                ctx.frontend(torch.randn(m, 1200, dtype=cdt, device="cuda"), torch.randn(m, 160, dtype=cdt, device="cuda"))
         torch.cuda.synchronize()
         del fr, tx0, rx0, H, outs, eq
         torch.cuda.empty_cache()
