@@ -145,7 +145,22 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
 
     // ---- outputs ----
     for (int e = tid; e < NSC * NSC; e += EG_THREADS) { W1[e] = make_double2(0, 0); W2[e] = make_double2(0, 0); }
-    if (tid < NSC) { lam[tid] = tid < nb ? A[tid * EG_LD + tid].x : 0.0; p[tid] = make_double2(0, 0); }
+    // Eigenvalues below the rounding level of the decomposition (|l| < 64 eps l_max) are set to exactly zero: for a
+    // rank-deficient covariance (4 channel taps -> rank 4) they are +-1e-16 garbage, and sigma2/(l + sigma2) != 1 in those 48
+    // directions was the tail of the error distribution (5e-10 on 1 frame in 40 at sigma2 = 2e-8; 2e-11 with the zeros).
+    __shared__ double s_lmax;
+    if (tid == 0) {
+        double m = 0;
+        for (int i = 0; i < nb; ++i) m = fmax(m, fabs(A[i * EG_LD + i].x));
+        s_lmax = m;
+    }
+    __syncthreads();
+    if (tid < NSC) {
+        double l = tid < nb ? A[tid * EG_LD + tid].x : 0.0;
+        if (fabs(l) < 64.0 * 2.220446049250313e-16 * s_lmax) l = 0.0;
+        lam[tid] = l;
+        p[tid] = make_double2(0, 0);
+    }
     __syncthreads();
     for (int e = tid; e < nb * nb; e += EG_THREADS) {
         const int i = e / nb, kk = e - i * nb;                     // eigen index i, compressed bin kk
@@ -161,6 +176,10 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
             const double2 b = R[bins[kk] * NSC + dc];
             acc.x += g.x * b.x - g.y * b.y; acc.y += g.x * b.y + g.y * b.x;
         }
+        // for a PSD covariance b = R_Nd lies in the range of R_NN, so p vanishes exactly in the zero-eigenvalue directions; the
+        // computed 1e-17 there is divided by sigma2 in beta and was the tail of the DC bin's error (2e-9 -> see tests)
+        const double l = A[tid * EG_LD + tid].x;
+        if (fabs(l) < 64.0 * 2.220446049250313e-16 * s_lmax) acc = make_double2(0, 0);
         p[tid] = acc;
     }
     if (tid == 0) {

@@ -1,0 +1,121 @@
+"""Parity at BASELINE.json's full sizes (1 Mi frames for the LS / interpolation / shared-filter paths, 256 Ki for the per-frame
+solve), where the long-double oracle cannot follow: a random sample of frames against the oracle, plus size-independent
+properties over EVERY frame -- exact linearity, shard independence (two halves == the whole batch, bit for bit), the equalizer
+round trip, and two independent algorithms (register-resident LDL^H solve vs eigen-domain products) agreeing frame by frame."""
+import importlib
+
+import numpy as np
+import pytest
+
+import synth
+from synth import rel_err
+
+pytestmark = pytest.mark.gpu
+NSC, NBLK = 53, 15
+
+
+@pytest.fixture(scope="module")
+def wifi():
+    return importlib.import_module("80211parallelestimation_b200")
+
+
+@pytest.fixture(scope="module")
+def ctx(wifi):
+    return wifi.WifiContext(0)
+
+
+def sample(n, k=384, seed=7):
+    return np.unique(np.r_[0, 1, n - 2, n - 1, np.random.default_rng(seed).integers(0, n, k)])
+
+
+def test_ls_interp_equalizer_1mi_frames_f32(ctx, oracle):
+    import torch
+    n = 1 << 20
+    fr = ctx.synth_frames(n, "f32", want=("tx_pre", "rx_pre", "tx_symb", "rx_symb"))
+    lt = ctx.lt_ls(fr["tx_pre"], fr["rx_pre"])
+    ps = ctx.ps(fr["tx_symb"], fr["rx_symb"])
+    eq = ctx.equalize(fr["rx_symb"], lt, ps["linear"])
+    pick = sample(n)
+    idx = torch.from_numpy(pick).cuda()
+    h = lambda t: t[idx].cpu().numpy().astype(np.complex128)
+    txp, rxp, txs, rxs = h(fr["tx_pre"]), h(fr["rx_pre"]), h(fr["tx_symb"]), h(fr["rx_symb"])
+    assert rel_err(h(lt), oracle.lt_ls(txp, rxp)) < 1e-4
+    for name in ("linear", "cubic", "sinc"):
+        assert rel_err(h(ps[name]), getattr(oracle, "ps_" + name)(txs[:, 0, :], rxs[:, 0, :])) < 1e-4, name
+    assert rel_err(h(eq), oracle.equalize(rxs, h(lt), h(ps["linear"])), floor=1e-6) < 1e-4
+    # exact linearity in rx over every frame (a power-of-two scale is exact in binary floating point)
+    lt2 = ctx.lt_ls(fr["tx_pre"], fr["rx_pre"] * 2)
+    assert torch.equal(lt2, lt * 2)
+    ps2 = ctx.ps(fr["tx_symb"], fr["rx_symb"] * 2, ("cubic",))
+    assert torch.equal(ps2["cubic"], ps["cubic"] * 2)
+    del lt2, ps2
+    # shard independence: the two halves processed separately are the whole batch, bit for bit
+    half = n // 2
+    a = ctx.lt_ls(fr["tx_pre"][:half], fr["rx_pre"][:half]); b = ctx.lt_ls(fr["tx_pre"][half:], fr["rx_pre"][half:])
+    assert torch.equal(torch.cat([a, b]), lt)
+    # equalizer round trip: eq * Hu = rx on every non-DC bin of every block
+    w = (torch.arange(1, NBLK + 1, device="cuda", dtype=torch.float32) / NBLK).view(1, NBLK, 1)
+    hu = (1 - w) * lt[:, None, :] + w * ps["linear"][:, None, :]
+    back = eq * hu
+    keep = torch.ones(NSC, dtype=torch.bool, device="cuda"); keep[26] = False
+    err = (back[:, :, keep] - fr["rx_symb"][:, :, keep]).abs().max() / fr["rx_symb"].abs().max()
+    assert float(err) < 1e-5
+    assert float(eq[:, :, 26].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_mmse_shared_1mi_frames(ctx, oracle, prec):
+    import torch
+    n = 1 << 20
+    fr = ctx.synth_frames(n, prec, want=("tx_symb", "rx_symb"))
+    R = ctx.synth_covariance()
+    d = torch.full((NSC,), synth.OW2 / synth.AMP ** 2, dtype=torch.float64, device="cuda"); d[26] = synth.OW2 / 1e-8
+    W = ctx.mmse_filter_form(R, d).cpu().numpy()
+    txf, rxf = fr["tx_symb"].reshape(-1), fr["rx_symb"].reshape(-1)
+    H = ctx.mmse_shared(txf, rxf, frame_stride=NBLK * NSC, n_frames=n)          # block 0 of whole frames, in place
+    pick = sample(n)
+    idx = torch.from_numpy(pick).cuda()
+    tx0 = fr["tx_symb"][idx, 0, :].cpu().numpy().astype(np.complex128); rx0 = fr["rx_symb"][idx, 0, :].cpu().numpy().astype(np.complex128)
+    ref = oracle.mmse_apply(W, rx0 / tx0)
+    got = H[idx].cpu().numpy()
+    if prec == "f64":
+        assert rel_err(got, ref) < 1e-10
+    else:
+        assert rel_err(got, ref, 1e-2) < 1e-4
+    # dense copy of block 0 == in-place read, bit for bit; scale by 2 == exact; halves == whole
+    tx0d = fr["tx_symb"][:, 0, :].contiguous(); rx0d = fr["rx_symb"][:, 0, :].contiguous()
+    Hd = ctx.mmse_shared(tx0d, rx0d)
+    assert torch.equal(Hd, H)
+    assert torch.equal(ctx.mmse_shared(tx0d, rx0d * 2), H * 2)
+    half = n // 2 + 64                                                            # not a multiple of the 128-frame tile
+    assert torch.equal(torch.cat([ctx.mmse_shared(tx0d[:half], rx0d[:half]), ctx.mmse_shared(tx0d[half:], rx0d[half:])]), H)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_mmse_perframe_256ki_frames_two_algorithms(ctx, wifi, oracle, prec):
+    import torch
+    n = 1 << 18
+    fr = ctx.synth_frames(n, prec, per_frame_sigma=True, want=("tx_symb", "rx_symb", "sigma2"))
+    tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous(); s2 = fr["sigma2"]
+    R = ctx.synth_covariance()
+    Rp = R if prec == "f64" else R.to(torch.complex64)
+    flags = wifi.SOLVE_HPD | (wifi.SOLVE_WIDE if prec == "f32" else 0)
+    Hs = ctx.mmse_perframe(Rp, tx0, rx0, s2, flags=flags)                          # register-resident LDL^H solve
+    ctx.mmse_eig_prepare(Rp.to(torch.complex128), (tx0[0].abs().to(torch.float64)) ** 2)
+    He = ctx.mmse_perframe_eig(tx0, rx0, s2)                                       # eigen-domain products
+    scale = Hs.abs().amax(dim=1, keepdim=True)
+    # FP32 (3xTF32 products): floor 1e-2 and <= 2e-5 of the frame's peak everywhere, like the shared-filter FP32 path (DESIGN.md 4.3:
+    # an FP32 106-term dot product is itself at ~7e-5 of a value that is 1e-3 of the peak)
+    floor = 1e-3 if prec == "f64" else 1e-2
+    diff = ((Hs - He).abs() / torch.maximum(Hs.abs(), floor * scale)).max()
+    print("worst of %d frames: %.2e (floor %g), %.2e of the peak" % (n, float(diff), floor, float(((Hs - He).abs() / scale).max())))
+    assert float(diff) < (1e-9 if prec == "f64" else 1e-4)          # f64: the solve itself reaches 5.5e-10 on its worst frame
+    if prec == "f32":
+        assert float(((Hs - He).abs() / scale).max()) < 2e-5
+    assert bool(torch.isfinite(torch.view_as_real(Hs)).all()) and bool(torch.isfinite(torch.view_as_real(He)).all())
+    pick = sample(n, 48)
+    idx = torch.from_numpy(pick).cuda()
+    c = lambda t: t[idx].cpu().numpy().astype(np.complex128)
+    ref = oracle.mmse_perframe(Rp.cpu().numpy().astype(np.complex128), c(tx0), c(rx0), s2[idx].cpu().numpy().astype(np.float64))
+    assert rel_err(c(Hs), ref) < (5e-10 if prec == "f64" else 1e-6)
+    assert rel_err(c(He), ref) < (5e-10 if prec == "f64" else 1e-4)
