@@ -164,6 +164,7 @@ struct TcSmem {
     float chunk[TC_CONV_WARPS][TC_CHUNK_F];        // per-warp private staging (input H_ls chunk, then output chunk)
     uint64_t bar_a_ready;                          // 128 converter arrivals per tile
     uint64_t bar_mma_done[2];                      // tcgen05.commit per accumulator buffer
+    uint64_t bar_b_ready;                          // the two bulk copies of the filter images
     uint32_t tmem_base;
 };
 
@@ -207,22 +208,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: filter images -> smem, barriers, TMEM ----
-    {
-        const uint4 *gh = reinterpret_cast<const uint4 *>(Bhi_g), *gl = reinterpret_cast<const uint4 *>(Blo_g);
-        uint4 *sh = reinterpret_cast<uint4 *>(sm.bhi), *sl = reinterpret_cast<uint4 *>(sm.blo);
-        for (int i = threadIdx.x; i < TC_B_BYTES / 16; i += TC_THREADS) { sh[i] = __ldg(gh + i); sl[i] = __ldg(gl + i); }
-    }
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar_a_ready, 128);
         mbar_init(&sm.bar_mma_done[0], 1);
         mbar_init(&sm.bar_mma_done[1], 1);
+        mbar_init(&sm.bar_b_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // The two 50 KB filter images come in as TMA bulk copies that complete on an mbarrier only the MMA issuer waits for:
+        // the converter warps start on their first tile at once (a 288-thread LDG/STS copy loop here cost ~5 us per launch).
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.bar_b_ready)), "r"(2u * TC_B_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm.bhi)), "l"(Bhi_g), "r"((uint32_t)TC_B_BYTES), "r"(smem_u32(&sm.bar_b_ready)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm.blo)), "l"(Blo_g), "r"((uint32_t)TC_B_BYTES), "r"(smem_u32(&sm.bar_b_ready)) : "memory");
     }
     if (warp == TC_CONV_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // B images (generic-proxy writes) -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint64_t dhi = make_b_desc(smem_u32(sm.bhi)), dlo = make_b_desc(smem_u32(sm.blo));
+            mbar_wait(&sm.bar_b_ready, 0);                                      // filter images have landed (async proxy writes)
             for (int it = 0; it < my_tiles; ++it) {
                 mbar_wait(&sm.bar_a_ready, it & 1);
                 tc_fence_after();
