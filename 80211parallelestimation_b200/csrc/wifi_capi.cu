@@ -23,7 +23,7 @@ struct wifi_ctx {
     InterpTables tab;
     FilterImages img;
     FilterImages eig[2];     // eigen-domain per-frame MMSE: G = V^H M^-1/2 and G2 = M^1/2 V as shared-filter operands
-    double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc;
+    double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc; double eig_Rdd, eig_md;
     void *eig_u; size_t eig_u_bytes;     // [n][53] scratch between the two products
     int *d_info;             // device scratch: singularity flags
     int *h_info;             // pinned mirror
@@ -308,12 +308,14 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
     }
     int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, ctx->eig_u, n, s);            // u = (rx/tx) G^T
     if (rc) return rc;
-    { Timed t(ctx, s); CK(launch_eig_mid(dt, ctx->eig_u, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
-    if (dt == WIFI_F32 && !ctx->force_simt) {                                                   // H = rx/tx - v G2^T in one kernel
+    if (dt == WIFI_F32 && !ctx->force_simt) {
+        // one kernel: v = s (.) (u - p z_d) in the converter stage, c = v G2^T on tcgen05, H = rx/tx - c in the epilogue
         Timed t(ctx, s);
-        CK(launch_mmse_shared_tc_resid(ctx->eig[1], ctx->eig_u, tx, rx, frame_stride, ctx->eig_dc, H, n, s));
+        CK(launch_mmse_shared_tc_resid(ctx->eig[1], ctx->eig_u, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p,
+                                       ctx->eig_Rdd, ctx->eig_md, H, n, s));
         return WIFI_OK;
     }
+    { Timed t(ctx, s); CK(launch_eig_mid(dt, ctx->eig_u, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
     rc = gemm_with(ctx, ctx->eig[1], dt, ctx->eig_u, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
     if (rc) return rc;
     { Timed t(ctx, s); CK(launch_eig_fin(dt, H, ctx->eig_u, tx, rx, frame_stride, ctx->eig_scal, n, s)); }
@@ -380,7 +382,7 @@ int wifi_mmse_eig_prepare(wifi_ctx *ctx, const void *R, const double *absx2)
     if (*ctx->h_info) return fail(ctx, WIFI_ERR_INVALID, "eigen-domain MMSE supports at most one null bin (|x_k|^2 < 1e-6 max) and needs max |x|^2 > 0");
     double scal[4];
     CK(cudaMemcpy(scal, ctx->eig_scal, sizeof scal, cudaMemcpyDeviceToHost));
-    ctx->eig_dc = (int)scal[2];
+    ctx->eig_dc = (int)scal[2]; ctx->eig_Rdd = scal[0]; ctx->eig_md = scal[1];
     ctx->eig_valid = 1;
     return WIFI_OK;
 }

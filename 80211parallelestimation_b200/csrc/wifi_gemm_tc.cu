@@ -165,6 +165,8 @@ struct TcSmem {
     uint64_t bar_a_ready;                          // 128 converter arrivals per tile
     uint64_t bar_mma_done[2];                      // tcgen05.commit per accumulator buffer
     uint64_t bar_b_ready;                          // the two bulk copies of the filter images
+    float lam[56];                                 // MID: eigenvalues and border vector
+    float2 pv[56];
     uint32_t tmem_base;
 };
 
@@ -195,9 +197,22 @@ struct TcResid {
     int64_t stride;
     const float2 *stash;        // [n][53]; element [f][52] = H of the null bin
     int dc;                     // null bin index or -1
+    // MID: the A operand is u = y G^T and the converter forms v = s (.) (u - p z_d) itself (the eig_mid pass of wifi_eig.cu)
+    const float *sigma2;        // [n]
+    const double *lam;          // [53] eigenvalues
+    const double2 *p;           // [53] border vector
+    float Rdd, md;              // R_dd and 1/|x_d|^2 of the null bin
 };
 
-template <bool FUSED, bool RESID>
+// 1/x with the hardware approximation and one Newton step
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+template <bool FUSED, bool RESID, bool MID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
                           const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16,
@@ -221,6 +236,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                      ::"r"(smem_u32(sm.bhi)), "l"(Bhi_g), "r"((uint32_t)TC_B_BYTES), "r"(smem_u32(&sm.bar_b_ready)) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sm.blo)), "l"(Blo_g), "r"((uint32_t)TC_B_BYTES), "r"(smem_u32(&sm.bar_b_ready)) : "memory");
+    }
+    if (MID && threadIdx.x < 56) {
+        const bool in = threadIdx.x < NSC;
+        sm.lam[threadIdx.x] = in ? (float)res.lam[threadIdx.x] : 0.f;
+        sm.pv[threadIdx.x] = in ? make_float2((float)res.p[threadIdx.x].x, (float)res.p[threadIdx.x].y) : make_float2(0.f, 0.f);
     }
     if (warp == TC_CONV_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
@@ -261,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         float *buf = sm.chunk[warp];
         const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
         const bool vec_ok = (frame_stride == NSC) && aligned16;
+        float2 hd_stash = make_float2(0.f, 0.f);             // MID: H of the null bin of this lane's frame, from converter to epilogue
         for (int it = group; it < my_tiles + 2; it += 2) {
             // ---- 0. pull this warp's chunk of THIS tile from HBM into L2 now (no registers, no shared memory): the transfer
             //         runs under the epilogue of the group's previous tile below, and the LDGs of step a. then hit L2.
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     }
                     if (res.dc >= 0) {
                         __syncwarp();                    // orders this warp's stores above before the one below (same addresses)
-                        if (lane < valid) H[(f0 + lane) * NSC + res.dc] = res.stash[(f0 + lane) * NSC + NSC - 1];
+                        if (lane < valid) H[(f0 + lane) * NSC + res.dc] = MID ? hd_stash : res.stash[(f0 + lane) * NSC + NSC - 1];
                     }
                 } else if (valid == 32 && aligned16) {
                     const float4 *b4 = reinterpret_cast<const float4 *>(buf);
@@ -382,6 +403,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
             const int64_t f0 = tile * TC_M + quarter * 32;                       // first frame of this warp's chunk
             const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
+            // MID: this lane's per-frame scalars, requested now and used after the chunk has been staged
+            float m_s2 = 1.f;
+            float2 m_td = make_float2(1.f, 0.f), m_rd = make_float2(0.f, 0.f);
+            if (MID && lane < valid) {
+                m_s2 = res.sigma2[f0 + lane];
+                if (res.dc >= 0) { m_td = res.tx[(f0 + lane) * res.stride + res.dc]; m_rd = res.rx[(f0 + lane) * res.stride + res.dc]; }
+            }
             // ---- a. chunk -> private buffer (row-major [32][106] floats), LS divide fused; loads software-pipelined ----
             if (vec_ok && valid == 32) {
                 const float4 *pa = reinterpret_cast<const float4 *>(a_in + f0 * NSC) + lane;
@@ -459,6 +487,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // ---- b. my frame -> hi/lo -> TMEM (A operand), after the previous tile's MMAs have released it ----
             if (it > 0) { mbar_wait(&sm.bar_mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
             const float2 *row = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
+            float2 m_zd = make_float2(0.f, 0.f);
+            if (MID) {
+                // beta = sum conj(p_i) u_i / (l_i + s2), gamma = sum |p_i|^2 / (l_i + s2) over this lane's row (wifi_eig.cu)
+                float br = 0.f, bi = 0.f, ga = 0.f;
+#pragma unroll 4
+                for (int cc = 0; cc < NSC; ++cc) {
+                    const float inv = rcp_fast(sm.lam[cc] + m_s2);
+                    const float2 u = row[cc], pp = sm.pv[cc];
+                    br = fmaf((pp.x * u.x + pp.y * u.y), inv, br);
+                    bi = fmaf((pp.x * u.y - pp.y * u.x), inv, bi);
+                    ga = fmaf((pp.x * pp.x + pp.y * pp.y), inv, ga);
+                }
+                if (res.dc >= 0) {
+                    const float2 yd = cdiv_fast(m_rd, m_td);
+                    const float q = res.Rdd - ga, iden = rcp_fast(m_s2 * res.md + q);
+                    const float2 dlt = make_float2(yd.x - br, yd.y - bi);
+                    m_zd = make_float2(dlt.x * iden, dlt.y * iden);
+                    hd_stash = make_float2(br + dlt.x * (q * iden), bi + dlt.y * (q * iden));
+                }
+            }
 #pragma unroll
             for (int g = 0; g < TC_K / 16; ++g) {
                 uint32_t hi[16], lo[16];
@@ -466,6 +514,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int c = 0; c < 8; ++c) {
                     int cc = g * 8 + c;
                     float2 v = (cc < NSC) ? row[cc] : make_float2(0.f, 0.f);
+                    if (MID && cc < NSC) {                                    // v_i = s_i (u_i - p_i z_d), s_i = s2 / (l_i + s2)
+                        const float sc = m_s2 * rcp_fast(sm.lam[cc] + m_s2);
+                        const float2 pp = sm.pv[cc];
+                        v = make_float2(sc * (v.x - (pp.x * m_zd.x - pp.y * m_zd.y)), sc * (v.y - (pp.x * m_zd.y + pp.y * m_zd.x)));
+                    }
                     uint32_t hx, hy;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
@@ -492,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-template <bool FUSED, bool RESID>
+template <bool FUSED, bool RESID, bool MID>
 static cudaError_t launch_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
                              const TcResid &res, cudaStream_t s)
 {
@@ -500,9 +553,9 @@ static cudaError_t launch_tc(const FilterImages &img, const void *a, const void 
     const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;
-    cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, RESID, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mmse_shared_tc_kernel<FUSED, RESID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
+    mmse_shared_tc_kernel<FUSED, RESID, MID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
                                                                        (float2 *)H, n_frames, aligned16, res);
     return cudaGetLastError();
 }
@@ -513,20 +566,24 @@ cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const 
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const TcResid none = {nullptr, nullptr, 0, nullptr, -1};
-    return rx ? launch_tc<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
-              : launch_tc<false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
+    const TcResid none = {nullptr, nullptr, 0, nullptr, -1, nullptr, nullptr, nullptr, 0.f, 0.f};
+    return rx ? launch_tc<true, false, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+              : launch_tc<false, false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
 }
 
-// H = rx/tx - v W^T (W = img), null bin `dc` from v[f][52]: the second product of the eigen-domain per-frame MMSE
+// H = rx/tx - v W^T (W = img), null bin `dc` from v[f][52]: the second product of the eigen-domain per-frame MMSE.
+// With sigma2 != NULL the input is u = y G^T and the kernel forms v = s (.) (u - p z_d) itself (no separate mid pass).
 cudaError_t launch_mmse_shared_tc_resid(const FilterImages &img, const void *v, const void *tx, const void *rx, int64_t frame_stride,
-                                        int dc, void *H, int64_t n_frames, cudaStream_t s)
+                                        int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
+                                        int64_t n_frames, cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const TcResid res = {(const float2 *)tx, (const float2 *)rx, frame_stride, (const float2 *)v, dc};
-    return launch_tc<false, true>(img, v, nullptr, NSC, H, n_frames, res, s);
+    const TcResid res = {(const float2 *)tx, (const float2 *)rx, frame_stride, (const float2 *)v, dc,
+                         (const float *)sigma2, lam, (const double2 *)p, (float)Rdd, (float)md};
+    return sigma2 ? launch_tc<false, true, true>(img, v, nullptr, NSC, H, n_frames, res, s)
+                  : launch_tc<false, true, false>(img, v, nullptr, NSC, H, n_frames, res, s);
 }
 
 }  // namespace wifi

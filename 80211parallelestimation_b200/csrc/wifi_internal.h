@@ -55,7 +55,8 @@ cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // 
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                   int64_t n_frames, cudaStream_t s);             // FP32 I/O, 3xTF32 on tcgen05
 cudaError_t launch_mmse_shared_tc_resid(const FilterImages &img, const void *v, const void *tx, const void *rx, int64_t frame_stride,
-                                        int dc, void *H, int64_t n_frames, cudaStream_t s);   // H = rx/tx - v W^T (eigen-domain MMSE)
+                                        int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
+                                        int64_t n_frames, cudaStream_t s);   // H = rx/tx - v W^T (eigen-domain MMSE; sigma2: fused mid pass)
 cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s);   // W64 -> B64
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                     int64_t n_frames, cudaStream_t s);           // FP64 I/O, DMMA m8n8k4
