@@ -19,6 +19,8 @@
 //   * a lane's accumulator pair is one complex output (re, im): 16-byte streaming stores straight from registers.
 // Replaces multiply() utils.c:16-31 applied per frame (main.c:201-207 intent) in the FP64 mode.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -158,16 +160,194 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 1)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-specialised version: the DMMA pipe never waits for a conversion.
+// ------------------------------------------------------------------------------------------
+// 16 warps = 8 (consumer, producer) pairs, two pairs per scheduler.  A producer loads 8-frame tiles of tx / rx (L2-prefetched
+// one tile ahead, software-pipelined 16-byte loads), does the LS divide and fills one of its pair's two A buffers; the
+// consumer issues the tile's 27 x 14 DMMAs back to back and stores its accumulators while the producer is already refilling.
+// Two DMMA warps per scheduler are needed: ptxas paces a warp's consecutive DMMAs with NOPs, and one consumer alone left
+// the pipe at 73 % (ncu); one producer for two consumers could not keep up (56 %).  Hand-over by mbarriers (full / empty
+// per buffer, one elected arrival after __syncwarp).
+constexpr int DW_ROWS = 8;                                  // frames per tile (one m8 fragment)
+constexpr int DW_PAIRS = 8;
+constexpr int DW_NEL = DW_ROWS * NSC;                       // 848 complex values per tile and array
+constexpr int DW_LB = 5;                                    // load batch (vectors per lane and array), 3 batches cover 424 values
+constexpr int DW_THREADS = DW_PAIRS * 64;                   // 8 pairs x (consumer warp + producer warp)
+
+__device__ __forceinline__ uint32_t dm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dm_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dm_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dm_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t addr = dm_smem_u32(bar), done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 22)) __trap();             // a protocol bug traps instead of hanging the GPU
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+    mmse_shared_dmma_ws_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
+                               int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames)
+{
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    double *Bt = (double *)dm_smem;                                   // [112][116]
+    double *As_all = Bt + DM_N * DM_BS;                               // [pair][2][16][108]
+    uint64_t *bars = (uint64_t *)(As_all + DW_PAIRS * 2 * DW_ROWS * DM_AS);   // [pair][2] full, [pair][2] empty
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp & 7;                                        // warps p (consumer) and p + 8 (producer): same scheduler
+    const bool producer = warp >= DW_PAIRS;
+    double *As = As_all + pair * (2 * DW_ROWS * DM_AS);
+    uint64_t *full = bars + pair * 4, *empty = full + 2;
+
+    {
+        const double2 *src = (const double2 *)Bt_g;
+        double2 *dst = (double2 *)Bt;
+        for (int e = threadIdx.x; e < DM_N * DM_BS / 2; e += DW_THREADS) dst[e] = src[e];
+        if (producer && lane < 2 * DW_ROWS) { As[lane * DM_AS + 106] = 0.0; As[lane * DM_AS + 107] = 0.0; }   // K padding of both buffers
+        if (threadIdx.x < DW_PAIRS * 4) dm_mbar_init(bars + threadIdx.x, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (n_frames + DW_ROWS - 1) / DW_ROWS;
+    const int64_t tstep = (int64_t)gridDim.x * DW_PAIRS;
+    const int64_t tile0 = (int64_t)blockIdx.x * DW_PAIRS + pair;
+
+    if (producer) {
+        int it = 0;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep, ++it) {
+            const int b = it & 1, k = it >> 1;
+            const int64_t f0 = tile * DW_ROWS;
+            const int nf = (int)min((int64_t)DW_ROWS, n_frames - f0);
+            double *Ab = As + b * (DW_ROWS * DM_AS);
+            // first batch of loads goes out before the wait for the buffer
+            double2 tv[2][DW_LB], rv[2][DW_LB];
+            auto issue = [&](int batch, int slot) {
+#pragma unroll
+                for (int u = 0; u < DW_LB; ++u) {
+                    const int e = (batch * DW_LB + u) * 32 + lane;
+                    const int f = e / NSC, kk = e - f * NSC;
+                    tv[slot][u] = make_double2(FUSED ? 1.0 : 0.0, 0.0);
+                    if (FUSED) rv[slot][u] = make_double2(0.0, 0.0);
+                    if (e < DW_NEL && f < nf) {
+                        const int64_t off = (f0 + f) * frame_stride + kk;
+                        tv[slot][u] = ld_stream(a_in + off);
+                        if (FUSED) rv[slot][u] = ld_stream(rx + off);
+                    }
+                }
+            };
+            issue(0, 0);
+            // HBM -> L2 for the team's next tile (no registers, no shared memory): its loads then cost an L2 latency each
+            if (tile + tstep < n_tiles) {
+                const int64_t fn = (tile + tstep) * DW_ROWS;
+                const int nfn = (int)min((int64_t)DW_ROWS, n_frames - fn);
+                if (frame_stride == NSC) {
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a_in + fn * NSC), "r"((uint32_t)(nfn * NSC * 16)) : "memory");
+                        if (FUSED) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rx + fn * NSC), "r"((uint32_t)(nfn * NSC * 16)) : "memory");
+                    }
+                } else if (lane < nfn) {
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a_in + (fn + lane) * frame_stride), "r"((uint32_t)(NSC * 16)) : "memory");
+                    if (FUSED) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rx + (fn + lane) * frame_stride), "r"((uint32_t)(NSC * 16)) : "memory");
+                }
+            }
+            if (k > 0) dm_mbar_wait(&empty[b], (k - 1) & 1);          // the consumer has finished with this buffer
+#pragma unroll
+            for (int batch = 0; batch < 3; ++batch) {
+                if (batch < 2) issue(batch + 1, (batch + 1) & 1);
+#pragma unroll
+                for (int u = 0; u < DW_LB; ++u) {
+                    const int e = (batch * DW_LB + u) * 32 + lane;
+                    const int f = e / NSC, kk = e - f * NSC;
+                    if (e < DW_NEL) {
+                        double2 y = tv[batch & 1][u];
+                        if (FUSED) {                                  // per-block LS rx/tx (main.c:83); rows >= nf: 0/1 = 0
+                            const double2 t = tv[batch & 1][u], r = rv[batch & 1][u];
+                            const double inv = 1.0 / (t.x * t.x + t.y * t.y);
+                            y = make_double2((r.x * t.x + r.y * t.y) * inv, (r.y * t.x - r.x * t.y) * inv);
+                        }
+                        *reinterpret_cast<double2 *>(Ab + f * DM_AS + 2 * kk) = y;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) dm_mbar_arrive(&full[b]);
+        }
+    } else {
+        const int g = lane >> 2, q = lane & 3;                        // fragment row / position in the group of 4
+        const double *bp = Bt + g * DM_BS + q;
+        int it = 0;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tstep, ++it) {
+            const int b = it & 1, k = it >> 1;
+            const int64_t f0 = tile * DW_ROWS;
+            const int nf = (int)min((int64_t)DW_ROWS, n_frames - f0);
+            const double *ap = As + b * (DW_ROWS * DM_AS) + g * DM_AS + q;
+            double c[DM_NT][2];
+#pragma unroll
+            for (int j = 0; j < DM_NT; ++j) c[j][0] = c[j][1] = 0.0;
+            dm_mbar_wait(&full[b], k & 1);
+            double a0 = ap[0];
+#pragma unroll 3
+            for (int kt = 0; kt < DM_KT; ++kt) {
+                const double na0 = ap[(kt + 1 < DM_KT ? kt + 1 : kt) * 4];          // next k-step's A fragment
+#pragma unroll
+                for (int j = 0; j < DM_NT; ++j) dmma884(c[j][0], c[j][1], a0, bp[j * 8 * DM_BS + kt * 4]);
+                a0 = na0;
+            }
+            __syncwarp();
+            if (lane == 0) dm_mbar_arrive(&empty[b]);                 // the producer may refill while the results are stored
+            if (g < nf) {
+                double2 *out = H + (f0 + g) * NSC + q;
+#pragma unroll
+                for (int j = 0; j < DM_NT; ++j)
+                    if (4 * j + q < NSC) st_stream(out + 4 * j, make_double2(c[j][0], c[j][1]));
+            }
+        }
+    }
+}
+
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
                                     int64_t n_frames, cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
+    static const int variant = [] { const char *e = getenv("WIFI_B200_DMMA"); return (e && !strcmp(e, "symmetric")) ? 0 : 1; }();
+    cudaError_t e;
+    if (variant == 1) {
+        const size_t smem = sizeof(double) * (DM_N * DM_BS + DW_PAIRS * 2 * DW_ROWS * DM_AS) + sizeof(uint64_t) * DW_PAIRS * 4;
+        const int64_t n_tiles = (n_frames + DW_ROWS - 1) / DW_ROWS;
+        const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DW_PAIRS - 1) / DW_PAIRS, 148);
+        if (rx) {
+            e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            mmse_shared_dmma_ws_kernel<true><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
+                                                                              (double2 *)H, n_frames);
+        } else {
+            e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            mmse_shared_dmma_ws_kernel<false><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, nullptr, NSC, (double2 *)H, n_frames);
+        }
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(double) * (DM_N * DM_BS + DM_WARPS * DM_ROWS * DM_AS);
     const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
     const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DM_WARPS - 1) / DM_WARPS, 148);
-    cudaError_t e;
     if (rx) {
         e = cudaFuncSetAttribute(mmse_shared_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
