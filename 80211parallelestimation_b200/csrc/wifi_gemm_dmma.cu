@@ -175,6 +175,18 @@ constexpr int DW_NEL = DW_ROWS * NSC;                       // 848 complex value
 constexpr int DW_LB = 5;                                    // load batch (vectors per lane and array), 3 batches cover 424 values
 constexpr int DW_THREADS = DW_PAIRS * 64;                   // 8 pairs x (consumer warp + producer warp)
 
+// 1/x for the LS divide with as few FP64-pipe instructions as possible (the FP64 pipe is the DMMA pipe and the producers'
+// arithmetic queues behind the consumers' DMMAs): FP32 hardware reciprocal of the rounded argument as the seed (23 bits),
+// two Newton steps in FP64 (46, 92 bits).  |tx|^2 of a frame is far inside the FP32 range.
+__device__ __forceinline__ double dm_rcp(double x)
+{
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+    double r = (double)rf;
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 __device__ __forceinline__ uint32_t dm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dm_mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
                         double2 y = tv[batch & 1][u];
                         if (FUSED) {                                  // per-block LS rx/tx (main.c:83); rows >= nf: 0/1 = 0
                             const double2 t = tv[batch & 1][u], r = rv[batch & 1][u];
-                            const double inv = 1.0 / (t.x * t.x + t.y * t.y);
+                            const double inv = dm_rcp(t.x * t.x + t.y * t.y);
                             y = make_double2((r.x * t.x + r.y * t.y) * inv, (r.y * t.x - r.x * t.y) * inv);
                         }
                         *reinterpret_cast<double2 *>(Ab + f * DM_AS + 2 * kk) = y;
