@@ -24,7 +24,8 @@ struct wifi_ctx {
     FilterImages img;
     FilterImages eig[2];     // eigen-domain per-frame MMSE: G = V^H M^-1/2 and G2 = M^1/2 V as shared-filter operands
     double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc; double eig_Rdd, eig_md;
-    void *eig_u; size_t eig_u_bytes;     // [n][53] scratch between the two products
+    void *eig_u[2]; size_t eig_u_bytes[2];   // [n][53] scratch between the two products, one per pipeline stream (the two
+                                             // chunks of a *_host call are in flight at the same time)
     int *d_info;             // device scratch: singularity flags
     int *h_info;             // pinned mirror
     char err[512];
@@ -175,7 +176,7 @@ int wifi_destroy(wifi_ctx *ctx)
     cudaFree(ctx->tab.w64); cudaFree(ctx->tab.w32);
     cudaFree(ctx->img.W64); cudaFree(ctx->img.W32); cudaFree(ctx->img.Bhi); cudaFree(ctx->img.Blo); cudaFree(ctx->img.B64);
     free_images(ctx->eig[0]); free_images(ctx->eig[1]);
-    cudaFree(ctx->eig_lam); cudaFree(ctx->eig_p); cudaFree(ctx->eig_scal); cudaFree(ctx->eig_u);
+    cudaFree(ctx->eig_lam); cudaFree(ctx->eig_p); cudaFree(ctx->eig_scal); cudaFree(ctx->eig_u[0]); cudaFree(ctx->eig_u[1]);
     cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -295,30 +296,31 @@ static int gemm_with(wifi_ctx *ctx, const FilterImages &im, wifi_dtype dt, const
 
 // eigen-domain per-frame MMSE on device pointers (wifi_eig.cu): two shared-matrix products with a per-frame scaling between
 static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H, int64_t n,
-                    cudaStream_t s)
+                    cudaStream_t s, int slot = 0)
 {
     if (!ctx->eig_valid) return fail(ctx, WIFI_ERR_STATE, "no eigen-domain operands installed: call wifi_mmse_eig_prepare first");
     if (n == 0) return WIFI_OK;
     const size_t need = (size_t)n * WIFI_NSC * esize(dt);
-    if (ctx->eig_u_bytes < need) {
+    if (ctx->eig_u_bytes[slot] < need) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(ctx->eig_u); ctx->eig_u = nullptr; ctx->eig_u_bytes = 0;
-        if (cudaMalloc(&ctx->eig_u, need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "eigen-domain scratch cudaMalloc(%zu) failed", need);
-        ctx->eig_u_bytes = need;
+        cudaFree(ctx->eig_u[slot]); ctx->eig_u[slot] = nullptr; ctx->eig_u_bytes[slot] = 0;
+        if (cudaMalloc(&ctx->eig_u[slot], need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "eigen-domain scratch cudaMalloc(%zu) failed", need);
+        ctx->eig_u_bytes[slot] = need;
     }
-    int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, ctx->eig_u, n, s);            // u = (rx/tx) G^T
+    void *U = ctx->eig_u[slot];
+    int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, U, n, s);            // u = (rx/tx) G^T
     if (rc) return rc;
     if (dt == WIFI_F32 && !ctx->force_simt) {
         // one kernel: v = s (.) (u - p z_d) in the converter stage, c = v G2^T on tcgen05, H = rx/tx - c in the epilogue
         Timed t(ctx, s);
-        CK(launch_mmse_shared_tc_resid(ctx->eig[1], ctx->eig_u, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p,
+        CK(launch_mmse_shared_tc_resid(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p,
                                        ctx->eig_Rdd, ctx->eig_md, H, n, s));
         return WIFI_OK;
     }
-    { Timed t(ctx, s); CK(launch_eig_mid(dt, ctx->eig_u, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
-    rc = gemm_with(ctx, ctx->eig[1], dt, ctx->eig_u, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
+    { Timed t(ctx, s); CK(launch_eig_mid(dt, U, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
+    rc = gemm_with(ctx, ctx->eig[1], dt, U, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
     if (rc) return rc;
-    { Timed t(ctx, s); CK(launch_eig_fin(dt, H, ctx->eig_u, tx, rx, frame_stride, ctx->eig_scal, n, s)); }
+    { Timed t(ctx, s); CK(launch_eig_fin(dt, H, U, tx, rx, frame_stride, ctx->eig_scal, n, s)); }
     return WIFI_OK;
 }
 
@@ -746,7 +748,7 @@ int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, co
     const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
     return host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), in_arr(sigma2, rsize(dt), rsize(dt)), out_arr(H, row)},
                          [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
-                             return mmse_eig(ctx, dt, d[0], d[1], WIFI_NSC, d[2], d[3], nc, s);
+                             return mmse_eig(ctx, dt, d[0], d[1], WIFI_NSC, d[2], d[3], nc, s, s == ctx->hstream[1] ? 1 : 0);
                          });
 }
 
