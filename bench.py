@@ -161,7 +161,7 @@ def run_reference(args):
     cb["value"] = val
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f80 (x87 long double)",
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f80",
         "data": "synthetic", "config": {"workload": "configs[2]: shared-filter PS_MMSE, bounded sample of %d frames per step on the host cores" % n},
         "cpu_baseline": cb, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
@@ -340,11 +340,12 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (3xTF32 tensor-core products, FP32 accumulate; filter formed in f64)" if os.environ.get("WIFI_B200_GEMM", "tc") == "tc" else "f32",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "configs[2]: batched PS_MMSE, shared Rhh/sigma2, %d frames per GPU as one complex GEMM (LS divide fused), FP32 I/O" % n_local,
                        "frames_per_gpu": n_local, "frames_total": n_total, "l2_policy": "inputs per pass (%.2f GB) >> 126 MB L2, no flush" % (n_local * bytes_per_frame / 1e9),
-                       "parallelism": "frame-sharded x%d, no data-path collective" % world, "filter_form_ms": filter_ms},
+                       "parallelism": "frame-sharded x%d, no data-path collective" % world, "filter_form_ms": filter_ms,
+                       "arithmetic": "FP32 I/O; products as 3xTF32 on tcgen05 with FP32 accumulation in TMEM; filter formed once in double-double"},
             "roofline": {"bound": "hbm", "kernel": "mmse_shared (fused LS divide + 53x53 complex filter GEMM)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": int(NCU_DRAM_BYTES_PER_MI_FRAMES * n_local / (1 << 20)),
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 1 Mi frames "
