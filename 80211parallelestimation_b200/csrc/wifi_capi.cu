@@ -317,6 +317,12 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
                                        ctx->eig_Rdd, ctx->eig_md, H, n, s));
         return WIFI_OK;
     }
+    if (dt == WIFI_F64 && !ctx->force_simt) {
+        Timed t(ctx, s);
+        CK(launch_mmse_shared_dmma_eig(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd,
+                                       ctx->eig_md, H, n, s));
+        return WIFI_OK;
+    }
     { Timed t(ctx, s); CK(launch_eig_mid(dt, U, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
     rc = gemm_with(ctx, ctx->eig[1], dt, U, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
     if (rc) return rc;

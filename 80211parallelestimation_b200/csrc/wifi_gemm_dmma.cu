@@ -211,15 +211,31 @@ __device__ __forceinline__ void dm_mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
-template <bool FUSED>
+// EIG (the second product of the eigen-domain per-frame MMSE, wifi_eig.cu; input u = y G^T, FUSED = false): the producer
+// turns the staged rows into v = s (.) (u - p z_d) -- four lanes per frame, beta and gamma by quad shuffles -- and the
+// consumer's epilogue writes rx/tx - acc, the null bin from the value the producer left next to the buffer.
+struct DmEig {
+    const double2 *tx, *rx;     // the frames' block vectors
+    int64_t stride;
+    const double *sigma2;       // [n]
+    const double *lam;          // [53]
+    const double2 *p;           // [53]
+    double Rdd, md;
+    int dc;
+};
+
+template <bool FUSED, bool EIG>
 __global__ void __launch_bounds__(DW_THREADS, 1)
     mmse_shared_dmma_ws_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
-                               int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames)
+                               int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames, DmEig eg)
 {
     extern __shared__ __align__(16) unsigned char dm_smem[];
     double *Bt = (double *)dm_smem;                                   // [112][116]
     double *As_all = Bt + DM_N * DM_BS;                               // [pair][2][16][108]
     uint64_t *bars = (uint64_t *)(As_all + DW_PAIRS * 2 * DW_ROWS * DM_AS);   // [pair][2] full, [pair][2] empty
+    double *slam = (double *)(bars + DW_PAIRS * 4);                   // EIG: [56] eigenvalues
+    double2 *sp = (double2 *)(slam + 56);                             // EIG: [56] border vector
+    double2 *shd = sp + 56;                                           // EIG: [pair][2][8] H of the null bin
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp & 7;                                        // warps p (consumer) and p + 8 (producer): same scheduler
     const bool producer = warp >= DW_PAIRS;
@@ -233,6 +249,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
         if (producer && lane < 2 * DW_ROWS) { As[lane * DM_AS + 106] = 0.0; As[lane * DM_AS + 107] = 0.0; }   // K padding of both buffers
         if (threadIdx.x < DW_PAIRS * 4) dm_mbar_init(bars + threadIdx.x, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (EIG && threadIdx.x < 56) {
+            slam[threadIdx.x] = threadIdx.x < NSC ? eg.lam[threadIdx.x] : 0.0;
+            sp[threadIdx.x] = threadIdx.x < NSC ? eg.p[threadIdx.x] : make_double2(0.0, 0.0);
+        }
     }
     __syncthreads();
 
@@ -298,6 +318,58 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
                 }
             }
             __syncwarp();
+            if (EIG) {
+                // row g = lane / 4 of the tile, eigen indices q, q + 4, ... of this lane
+                const int g = lane >> 2, q = lane & 3;
+                const bool live = g < nf;
+                const double s2 = live ? eg.sigma2[f0 + g] : 1.0;
+                double2 td = make_double2(1.0, 0.0), rd = make_double2(0.0, 0.0);
+                if (live && eg.dc >= 0) { td = eg.tx[(f0 + g) * eg.stride + eg.dc]; rd = eg.rx[(f0 + g) * eg.stride + eg.dc]; }
+                if (lane < 2 * nf) {                                  // the consumer's epilogue re-reads tx / rx of these rows
+                    const double2 *row = (lane < nf ? eg.tx : eg.rx) + (f0 + (lane < nf ? lane : lane - nf)) * eg.stride;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((uint32_t)(NSC * 16)) : "memory");
+                }
+                double2 *urow = reinterpret_cast<double2 *>(Ab + g * DM_AS);
+                double inv[14];
+                double br = 0.0, bi = 0.0, ga = 0.0;
+#pragma unroll
+                for (int m = 0; m < 14; ++m) {
+                    const int cc = q + 4 * m;
+                    inv[m] = 0.0;
+                    if (cc < NSC) {
+                        inv[m] = dm_rcp(slam[cc] + s2);
+                        const double2 u = urow[cc], pp = sp[cc];
+                        br = fma(pp.x * u.x + pp.y * u.y, inv[m], br);
+                        bi = fma(pp.x * u.y - pp.y * u.x, inv[m], bi);
+                        ga = fma(pp.x * pp.x + pp.y * pp.y, inv[m], ga);
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    br += __shfl_xor_sync(0xffffffffu, br, o);
+                    bi += __shfl_xor_sync(0xffffffffu, bi, o);
+                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                }
+                double2 zd = make_double2(0.0, 0.0);
+                if (eg.dc >= 0) {
+                    const double itd = dm_rcp(td.x * td.x + td.y * td.y);
+                    const double2 yd = make_double2((rd.x * td.x + rd.y * td.y) * itd, (rd.y * td.x - rd.x * td.y) * itd);
+                    const double qq = eg.Rdd - ga, iden = 1.0 / (s2 * eg.md + qq);
+                    const double2 dlt = make_double2(yd.x - br, yd.y - bi);
+                    zd = make_double2(dlt.x * iden, dlt.y * iden);
+                    if (q == 0) shd[(pair * 2 + b) * 8 + g] = make_double2(br + dlt.x * (qq * iden), bi + dlt.y * (qq * iden));
+                }
+#pragma unroll
+                for (int m = 0; m < 14; ++m) {
+                    const int cc = q + 4 * m;
+                    if (cc < NSC) {
+                        const double2 u = urow[cc], pp = sp[cc];
+                        const double sc = s2 * inv[m];
+                        urow[cc] = make_double2(sc * (u.x - (pp.x * zd.x - pp.y * zd.y)), sc * (u.y - (pp.x * zd.y + pp.y * zd.x)));
+                    }
+                }
+                __syncwarp();
+            }
             if (lane == 0) dm_mbar_arrive(&full[b]);
         }
     } else {
@@ -321,6 +393,25 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
                 for (int j = 0; j < DM_NT; ++j) dmma884(c[j][0], c[j][1], a0, bp[j * 8 * DM_BS + kt * 4]);
                 a0 = na0;
             }
+            if (EIG) {
+                const double2 hd = (eg.dc >= 0 && g < nf) ? shd[(pair * 2 + b) * 8 + g] : make_double2(0.0, 0.0);   // read before the release
+                __syncwarp();
+                if (lane == 0) dm_mbar_arrive(&empty[b]);
+                if (g < nf) {
+                    const double2 *ptx = eg.tx + (f0 + g) * eg.stride + q, *prx = eg.rx + (f0 + g) * eg.stride + q;
+                    double2 *out = H + (f0 + g) * NSC + q;
+#pragma unroll
+                    for (int j = 0; j < DM_NT; ++j)
+                        if (4 * j + q < NSC) {
+                            const double2 t = ld_stream(ptx + 4 * j), r = ld_stream(prx + 4 * j);
+                            const double inv = dm_rcp(t.x * t.x + t.y * t.y);
+                            double2 h = make_double2((r.x * t.x + r.y * t.y) * inv - c[j][0], (r.y * t.x - r.x * t.y) * inv - c[j][1]);
+                            if (4 * j + q == eg.dc) h = hd;
+                            st_stream(out + 4 * j, h);
+                        }
+                }
+                continue;
+            }
             __syncwarp();
             if (lane == 0) dm_mbar_arrive(&empty[b]);                 // the producer may refill while the results are stored
             if (g < nf) {
@@ -333,6 +424,33 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
     }
 }
 
+template <bool FUSED, bool EIG>
+static cudaError_t launch_ws(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
+                             const DmEig &eg, cudaStream_t s)
+{
+    const size_t smem = sizeof(double) * (DM_N * DM_BS + DW_PAIRS * 2 * DW_ROWS * DM_AS) + sizeof(uint64_t) * DW_PAIRS * 4 +
+                        sizeof(double) * 56 + sizeof(double2) * (56 + DW_PAIRS * 2 * 8);
+    const int64_t n_tiles = (n_frames + DW_ROWS - 1) / DW_ROWS;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DW_PAIRS - 1) / DW_PAIRS, 148);
+    cudaError_t e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<FUSED, EIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmse_shared_dmma_ws_kernel<FUSED, EIG><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
+                                                                         (double2 *)H, n_frames, eg);
+    return cudaGetLastError();
+}
+
+// H = rx/tx - v G2^T with v = s (.) (u - p z_d) formed from u inside the kernel: the whole second half of the eigen-domain MMSE
+cudaError_t launch_mmse_shared_dmma_eig(const FilterImages &img, const void *u, const void *tx, const void *rx, int64_t frame_stride,
+                                        int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
+                                        int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const DmEig eg = {(const double2 *)tx, (const double2 *)rx, frame_stride, (const double *)sigma2, lam, (const double2 *)p, Rdd, md, dc};
+    return launch_ws<false, true>(img, u, nullptr, NSC, H, n_frames, eg, s);
+}
+
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
                                     int64_t n_frames, cudaStream_t s)
 {
@@ -342,20 +460,9 @@ cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, cons
     static const int variant = [] { const char *e = getenv("WIFI_B200_DMMA"); return (e && !strcmp(e, "symmetric")) ? 0 : 1; }();
     cudaError_t e;
     if (variant == 1) {
-        const size_t smem = sizeof(double) * (DM_N * DM_BS + DW_PAIRS * 2 * DW_ROWS * DM_AS) + sizeof(uint64_t) * DW_PAIRS * 4;
-        const int64_t n_tiles = (n_frames + DW_ROWS - 1) / DW_ROWS;
-        const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DW_PAIRS - 1) / DW_PAIRS, 148);
-        if (rx) {
-            e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            mmse_shared_dmma_ws_kernel<true><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
-                                                                              (double2 *)H, n_frames);
-        } else {
-            e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            mmse_shared_dmma_ws_kernel<false><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, nullptr, NSC, (double2 *)H, n_frames);
-        }
-        return cudaGetLastError();
+        const DmEig none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0.0, 0.0, -1};
+        return rx ? launch_ws<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+                  : launch_ws<false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
     }
     const size_t smem = sizeof(double) * (DM_N * DM_BS + DM_WARPS * DM_ROWS * DM_AS);
     const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;

@@ -60,6 +60,9 @@ cudaError_t launch_mmse_shared_tc_resid(const FilterImages &img, const void *v, 
 cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s);   // W64 -> B64
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                     int64_t n_frames, cudaStream_t s);           // FP64 I/O, DMMA m8n8k4
+cudaError_t launch_mmse_shared_dmma_eig(const FilterImages &img, const void *u, const void *tx, const void *rx, int64_t frame_stride,
+                                        int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
+                                        int64_t n_frames, cudaStream_t s);   // FP64: H = rx/tx - v G2^T, v formed from u in the kernel
 cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch,
                            cudaStream_t s);
 cudaError_t launch_chermitian(wifi_dtype dt, int mode, const void *M, int row, int col, void *res, int64_t batch, cudaStream_t s);
