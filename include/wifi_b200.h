@@ -66,10 +66,11 @@ typedef enum {
 #define WIFI_PS_MATLAB 8
 
 /* flags of wifi_mmse_perframe_batch */
-#define WIFI_SOLVE_PIVOT 0      /* partial-pivoting Gauss-Jordan (any non-singular R + D) */
-#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted elimination (growth factor 1) */
+#define WIFI_SOLVE_PIVOT 0      /* LU with partial pivoting + back-substitution, H = R z (any non-singular R + D) */
+#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted L D L^H, H = y - D z (growth factor 1) */
 #define WIFI_SOLVE_WIDE 2       /* with WIFI_SOLVE_HPD and WIFI_F32: FP32 storage, FP64 arithmetic inside the solve (sigma2/|x|^2
-                                 * is below the FP32 resolution of R; the plain FP32 solve is only accurate to ~1e-1) */
+                                 * is below the FP32 resolution of R: the plain FP32 HPD solve is accurate to ~4e-3, the pivoted
+                                 * one to ~1e-1; WIDE to 1e-7).  For frames that share |tx_k|^2 see wifi_mmse_eig_*. */
 #define WIFI_SOLVE_REFINE WIFI_SOLVE_WIDE   /* former name */
 
 /* wifi_chermitian_batch / wifi_cadd_batch semantics */
@@ -123,8 +124,8 @@ int wifi_mmse_shared_apply_batch(wifi_ctx *ctx, wifi_dtype dt, const void *H_ls,
 /* fused: per-block LS divide rx/tx (main.c:83 arithmetic on all 53 bins) + the GEMM */
 int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                            int64_t frame_stride, void *H, int64_t n_frames);
-/* Per-frame case: A_f = R + diag(sigma2[f]/|tx_k|^2); solve A_f z = rx/tx; H = R z.
- * R in the compute dtype (53x53), sigma2 real [n] in the compute dtype. */
+/* Per-frame case: A_f = R + diag(sigma2[f]/|tx_k|^2); solve A_f z = rx/tx; H = R z (= rx/tx - D_f z).
+ * R in the storage dtype (53x53), sigma2 real [n] in the storage dtype; flags: WIFI_SOLVE_*. */
 int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols,
                              const void *rx_symbols, int64_t frame_stride, const void *sigma2, void *H,
                              int64_t n_frames, int flags);
