@@ -139,7 +139,16 @@ def cpu_reference_rate(sample_frames, seconds_target=12.0):
     reps = -(-n // 4096)
     txb, rxb = np.tile(tx, (reps, 1))[:n], np.tile(rx, (reps, 1))[:n]
     t0 = time.perf_counter(); run(txb, rxb); dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+    seq = None
+    if kind == "reference":                       # the same routine on ONE core (the reference's sequential build), ~2 s
+        ref.set_threads(1)
+        m = int(max(4096, min(n, 2.0 * (n / dt) / max(cores, 1))))
+        t1 = time.perf_counter(); run(txb[:m], rxb[:m]); d1 = time.perf_counter() - t1
+        ref.set_threads(cores)
+        seq = {"value": m / d1, "unit": UNIT, "cores": 1, "sample": "%d frames, %.1f s" % (m, d1)}
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sequential": seq,
+            "not_run": "the reference's MPI build (no mpirun/mpi.h on this box; main_mpi.c:1015-1080 numbers are in BASELINE.md) and its "
+                       "intra-frame OpenMP PS_MMSE (returns NaN after 278 s per frame, SURVEY 6.2)",
             "sample": "%d frames of the shared-filter MMSE workload (LS divide + 53x53 filter), %.1f s, %s" %
                       (n, dt, "oracle/_ref ref_mmse_shared_omp (reference multiply(), OpenMP over frames)" if kind == "reference"
                        else "oracle port, single thread")}, (run, txb, rxb)
