@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__res
     for (int64_t g = (int64_t)blockIdx.x * FE_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * FE_WARPS) {
         const int64_t f = g >> 2;
         const int q = (int)(g & 3);                              // transforms 4q .. 4q+3 of frame f; transform 15 = preamble
+        // HBM -> L2 for the warp's NEXT group (no registers, no shared memory): its loads below then cost an L2 latency.
+        // lanes 0..3: one 64-sample block each; the preamble of a frame's last group: p1 and p2 (lanes 3, 4)
+        {
+            const int64_t gn = g + (int64_t)gridDim.x * FE_WARPS;
+            if (gn < n_groups && lane < 5) {
+                const int64_t fn = gn >> 2;
+                const int bn = 4 * (int)(gn & 3) + lane;
+                const cx<T> *src = nullptr;
+                if (lane < 4 && bn < NBLK) src = packet + fn * FE_PKT + bn * FE_BLK + FE_CP;
+                else if ((gn & 3) == 3 && lane >= 3) src = lptot + fn * FE_LP + (lane == 3 ? 96 : 32);
+                if (src) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(64 * sizeof(cx<T>))) : "memory");
+            }
+        }
         // ---- A. samples -> tile (natural order), two consecutive samples per lane and load ----
         T nv = 0;
 #pragma unroll
