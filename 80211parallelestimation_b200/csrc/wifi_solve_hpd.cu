@@ -23,7 +23,7 @@
 //     52-k folded into one 54-entry line); its entry 53 is the forward-substituted right-hand side.
 // The cyclic distribution keeps all lanes busy as the active sub-matrix shrinks.  Back-substitution with the
 // unit-diagonal U' runs on one warp (column axpys, z_j broadcast by shuffle) and finishes with H = y - D z from
-// registers.  tx/rx of the group's next frame are prefetched into registers during the elimination.
+// registers.  tx/rx of the group's next frame are prefetched during the elimination (registers in FP32, L2 in FP64).
 //
 // TIO is the storage type of R/tx/rx/sigma2/H and T the arithmetic type: <float,float>, <double,double>, and
 // <double,float> = WIFI_SOLVE_WIDE (FP32 I/O, FP64 arithmetic: d_f is below the FP32 resolution of R).
@@ -211,20 +211,27 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
 
     const int64_t fstep = (int64_t)gridDim.x * FPC;
     int64_t f = (int64_t)blockIdx.x * FPC + grp;
-    // prefetched inputs of the current frame: lane k (and k + 32 for one-warp groups) holds sub-carrier k
+    // inputs: lane k (and k + 32 for one-warp groups) holds sub-carrier k.  FP32 arithmetic: tx/rx of the group's next frame
+    // are prefetched into registers during the elimination.  FP64 arithmetic: the next frame's rows are only pulled into L2
+    // -- holding them in registers (10 of 168) cost more in spills and lost load/FMA overlap inside the elimination than the
+    // exposed L2 latency at the top of a frame (~1 % of a frame, covered by the CTA's other groups).  Measured, register
+    // prefetch -> L2 prefetch: f64 32.9 -> 34.4 M frames/s, FP32 storage + FP64 arithmetic 33.8 -> 34.7 M, f32 77.4 -> 75.8 M.
+    constexpr bool REGPF = sizeof(T) == 4;
     constexpr int NIN = (NSC + LANES - 1) / LANES;
     cx<TIO> tin[NIN], rin[NIN];
     TIO sin = (TIO)0;
-    if (f < n_frames) {
+    auto load_inputs = [&](int64_t fr) {
 #pragma unroll
         for (int q = 0; q < NIN; ++q) {
             const int k = lane + q * LANES;
-            if (k < NSC) { tin[q] = ld_stream(tx + f * frame_stride + k); rin[q] = ld_stream(rx + f * frame_stride + k); }
+            if (k < NSC) { tin[q] = ld_stream(tx + fr * frame_stride + k); rin[q] = ld_stream(rx + fr * frame_stride + k); }
         }
-        sin = sigma2[f];
-    }
+        sin = sigma2[fr];
+    };
+    if (REGPF && f < n_frames) load_inputs(f);
     for (; f < n_frames; f += fstep) {
         // ---- per-frame inputs: y = rx/tx, d = sigma2/|tx|^2 ----
+        if (!REGPF) load_inputs(f);
 #pragma unroll
         for (int q = 0; q < NIN; ++q) {
             const int k = lane + q * LANES;
@@ -236,13 +243,11 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
         }
         {
             const int64_t fn = f + fstep;
-            if (fn < n_frames) {
-#pragma unroll
-                for (int q = 0; q < NIN; ++q) {
-                    const int k = lane + q * LANES;
-                    if (k < NSC) { tin[q] = ld_stream(tx + fn * frame_stride + k); rin[q] = ld_stream(rx + fn * frame_stride + k); }
-                }
-                sin = sigma2[fn];
+            if (REGPF) {
+                if (fn < n_frames) load_inputs(fn);
+            } else if (fn < n_frames && lane < 8) {
+                const cx<TIO> *p = (lane < 4 ? tx : rx) + fn * frame_stride;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + (lane & 3) * 128));
             }
         }
         group_sync<LANES>(bar_id);
