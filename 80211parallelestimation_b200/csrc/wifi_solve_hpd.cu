@@ -39,7 +39,13 @@ namespace wifi {
 constexpr int H_N1 = NSC + 1;                   // 54 rows of the bordered matrix
 constexpr int H_NLC = 7;                        // local columns (53 columns / 8)
 constexpr int H_US = 27 * 54 + 2;               // folded U' store: line m = row m (53-m entries) ++ row 52-m (m+1 entries)
-constexpr int H_RT = (NSC * NSC + 7) & ~7;      // 2816: keeps the per-group runs 64-byte aligned
+// The covariance image Rt[j * RtStride + i] = R[i][j].  FP32 arithmetic: zero-padded to 56 x 56 so that the per-frame set-up
+// of the register slice needs no bounds tests, with a row stride of 58 that makes the slice gather (lanes = 8 consecutive
+// j x 4 consecutive i) conflict-free (53, the dense stride, is a 2-way conflict): 77.4 -> 80.7 M frames/s.  FP64 arithmetic
+// keeps the dense image and the guarded set-up: the branch-free form has more loads in flight than the 168-register budget
+// holds (32 bytes of spills) and measured 3 % slower.
+template <typename T> struct RtStride { static constexpr int v = sizeof(T) == 4 ? 58 : NSC; };
+template <typename T> struct RtSize { static constexpr int v = ((sizeof(T) == 4 ? 56 : NSC) * RtStride<T>::v + 7) & ~7; };   // keeps the group runs 64-byte aligned
 
 // The published column is stored as 8 runs (run r = rows/columns i with i%8 == r, position i/8).  Runs are RS entries
 // apart with RS * sizeof(cx<T>) / 16 odd, so the 8 runs start in 8 different 16-byte bank groups and a 16-byte shared
@@ -128,9 +134,27 @@ struct HpdGroup {
         for (int q = 0; q < NQ; ++q) {
             const int K = K0 + q, kc = K & 7;              // kc: owner lane-column of column K
             if (L.pc == kc) {
+                if (PR == 4 && sizeof(T) == 4) {
+                    // local rows li and li + 2 are neighbours in their run: one 16-byte store for two rows (a finished row
+                    // that shares a store with a live one is published too and never read)
 #pragma unroll
-                for (int li = klr; li < NLR; ++li)
-                    if (live(li, klc)) L.rowp[bo + rowpos(li)] = a[li][klc];          // row PR li + pr
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int m = 0; m < 7; m += 2) {
+                            const int l0 = 2 * m + p, l1 = l0 + 2;
+                            if (l1 < NLR && l1 >= klr && live(l0, klc)) {
+                                *reinterpret_cast<float4 *>(&L.rowp[bo + rowpos(l0)]) =
+                                    make_float4((float)a[l0][klc].x, (float)a[l0][klc].y, (float)a[l1][klc].x, (float)a[l1][klc].y);
+                            } else {
+                                if (l0 >= klr && live(l0, klc)) L.rowp[bo + rowpos(l0)] = a[l0][klc];
+                                if (l1 < NLR && l1 >= klr && live(l1, klc)) L.rowp[bo + rowpos(l1)] = a[l1][klc];
+                            }
+                        }
+                } else {
+#pragma unroll
+                    for (int li = klr; li < NLR; ++li)
+                        if (live(li, klc)) L.rowp[bo + rowpos(li)] = a[li][klc];          // row PR li + pr
+                }
             }
             group_sync<LANES>(L.bar_id);
             const T inv = pivot_rcp(L.lb[bo + kc * RS + klc].x);   // the pivot a_KK of a Hermitian matrix is real
@@ -182,9 +206,14 @@ template <typename T> struct HpdGroup<T, 4, 14> {
     static __device__ __forceinline__ void run(cx<T> (&)[14][H_NLC], const HpdLane<T> &, int &) {}
 };
 
+template <typename C> __device__ __forceinline__ C shfl_cx(C v, int src)
+{
+    v.x = __shfl_sync(0xffffffffu, v.x, src); v.y = __shfl_sync(0xffffffffu, v.y, src);
+    return v;
+}
 template <typename T, typename TIO> __device__ __forceinline__ cx<T> widen(cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); }
 
-template <typename T, typename TIO, int PR, int FPC, int MINB>
+template <typename T, typename TIO, int PR, int FPC, int MINB, int VAR>
 __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     mmse_hpd_kernel(const cx<TIO> *__restrict__ R, const cx<TIO> *__restrict__ tx, const cx<TIO> *__restrict__ rx, int64_t frame_stride,
                     const TIO *__restrict__ sigma2, cx<TIO> *__restrict__ H, int64_t n_frames)
@@ -193,7 +222,8 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     constexpr int NLR = (H_N1 + PR - 1) / PR;              // local rows: 7 (PR = 8) or 14 (PR = 4)
     extern __shared__ __align__(16) unsigned char hpd_smem[];
     using S = HpdSmem;
-    cx<T> *Rt = (cx<T> *)hpd_smem;                         // Rt[j*53 + i] = R[i][j]
+    cx<T> *Rt = (cx<T> *)hpd_smem;                         // Rt[j * RTS + i] = R[i][j] (FP32: zero for i or j >= 53)
+    constexpr int RTS = RtStride<T>::v, H_RT = RtSize<T>::v;
     const int grp = threadIdx.x / LANES, lane = threadIdx.x % LANES;
     const int pr = lane >> 3, pc = lane & 7;
     cx<T> *gs = Rt + H_RT + grp * S::GROUP;
@@ -203,9 +233,14 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     constexpr int RS = RunStride<T>::v;
     const HpdLane<T> L = {lb, lb + pr * RS, lb + pc * RS, lb + (lane & 7) * RS + (lane >> 3), Us, lane, pr, pc, bar_id};
 
+    if (VAR) {
+        for (int e = threadIdx.x; e < H_RT; e += LANES * FPC) Rt[e] = mk<T>(0, 0);
+        if (lane < 3) { yb[NSC + lane] = mk<T>(0, 0); db[NSC + lane] = (T)0; }     // padding read by the branch-free set-up
+        __syncthreads();
+    }
     for (int e = threadIdx.x; e < NSC * NSC; e += LANES * FPC) {
         int i = e / NSC, j = e - i * NSC;
-        Rt[j * NSC + i] = widen<T, TIO>(R[e]);
+        Rt[j * RTS + i] = widen<T, TIO>(R[e]);
     }
     __syncthreads();
 
@@ -218,40 +253,63 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     // prefetch -> L2 prefetch: f64 32.9 -> 34.4 M frames/s, FP32 storage + FP64 arithmetic 33.8 -> 34.7 M, f32 77.4 -> 75.8 M.
     constexpr bool REGPF = sizeof(T) == 4;
     constexpr int NIN = (NSC + LANES - 1) / LANES;
+    // y_k = rx/tx and d_k = sigma2/|tx|^2 of sub-carrier k with ONE reciprocal of |tx|^2 (hardware seed + Newton steps, ~1 ulp)
+    auto set_inputs = [&](int k, cx<TIO> tv, cx<TIO> rv, TIO sg) {
+        const cx<T> t = widen<T, TIO>(tv), r = widen<T, TIO>(rv);
+        if (VAR) {
+            const T it = pivot_rcp(cabs2(t));
+            yb[k] = mk<T>((r.x * t.x + r.y * t.y) * it, (r.y * t.x - r.x * t.y) * it);
+            db[k] = (T)sg * it;
+        } else {
+            yb[k] = cdiv(r, t);
+            db[k] = (T)sg / cabs2(t);
+        }
+    };
     cx<TIO> tin[NIN], rin[NIN];
     TIO sin = (TIO)0;
-    auto load_inputs = [&](int64_t fr) {
+    if constexpr (REGPF) {
+        if (f < n_frames) {
 #pragma unroll
-        for (int q = 0; q < NIN; ++q) {
-            const int k = lane + q * LANES;
-            if (k < NSC) { tin[q] = ld_stream(tx + fr * frame_stride + k); rin[q] = ld_stream(rx + fr * frame_stride + k); }
-        }
-        sin = sigma2[fr];
-    };
-    if (REGPF && f < n_frames) load_inputs(f);
-    for (; f < n_frames; f += fstep) {
-        // ---- per-frame inputs: y = rx/tx, d = sigma2/|tx|^2 ----
-        if (!REGPF) load_inputs(f);
-#pragma unroll
-        for (int q = 0; q < NIN; ++q) {
-            const int k = lane + q * LANES;
-            if (k < NSC) {
-                cx<T> t = widen<T, TIO>(tin[q]), r = widen<T, TIO>(rin[q]);
-                yb[k] = cdiv(r, t);
-                db[k] = (T)sin / cabs2(t);
+            for (int q = 0; q < NIN; ++q) {
+                const int k = lane + q * LANES;
+                if (k < NSC) { tin[q] = ld_stream(tx + f * frame_stride + k); rin[q] = ld_stream(rx + f * frame_stride + k); }
             }
+            sin = sigma2[f];
         }
-        {
-            const int64_t fn = f + fstep;
-            if (REGPF) {
-                if (fn < n_frames) load_inputs(fn);
-            } else if (fn < n_frames && lane < 8) {
+    }
+    for (; f < n_frames; f += fstep) {
+        // ---- per-frame inputs ----
+        const int64_t fn = f + fstep;
+        if constexpr (REGPF) {
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) {
+                const int k = lane + q * LANES;
+                if (k < NSC) set_inputs(k, tin[q], rin[q], sin);
+            }
+            if (fn < n_frames) {
+#pragma unroll
+                for (int q = 0; q < NIN; ++q) {
+                    const int k = lane + q * LANES;
+                    if (k < NSC) { tin[q] = ld_stream(tx + fn * frame_stride + k); rin[q] = ld_stream(rx + fn * frame_stride + k); }
+                }
+                sin = sigma2[fn];
+            }
+        } else {
+            const TIO sg = sigma2[f];
+#pragma unroll
+            for (int q = 0; q < NIN; ++q) {
+                const int k = lane + q * LANES;
+                if (k < NSC) set_inputs(k, ld_stream(tx + f * frame_stride + k), ld_stream(rx + f * frame_stride + k), sg);
+            }
+            if (fn < n_frames && lane < 8) {
                 const cx<TIO> *p = (lane < 4 ? tx : rx) + fn * frame_stride;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + (lane & 3) * 128));
             }
         }
         group_sync<LANES>(bar_id);
         // local slice of the bordered matrix; only positions that can be on/below the diagonal are ever touched
+        // (branch-free: Rt, yb and db are zero-padded; only the positions of the tiles that straddle the diagonal test
+        // i == j, only the local row that holds row 53 takes the right-hand side)
         cx<T> a[NLR][H_NLC];
 #pragma unroll
         for (int li = 0; li < NLR; ++li) {
@@ -260,10 +318,17 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
             for (int lj = 0; lj < H_NLC; ++lj) {
                 if (PR * li + PR - 1 >= 8 * lj) {
                     const int j = 8 * lj + pc;
-                    cx<T> v = mk<T>(0, 0);
-                    if (j < NSC) {
-                        if (i < NSC) { v = Rt[j * NSC + i]; if (i == j) v.x += db[i]; }
-                        else if (i == NSC) v = cconj(yb[j]);
+                    cx<T> v;
+                    if (VAR) {
+                        v = Rt[j * RTS + i];
+                        if (PR * li <= 8 * lj + 7) v.x += (i == j) ? db[j] : (T)0;       // tile touches the diagonal
+                        if (li == NSC / PR) { const cx<T> yv = yb[j]; if (i == NSC) v = cconj(yv); }
+                    } else {
+                        v = mk<T>(0, 0);
+                        if (j < NSC) {
+                            if (i < NSC) { v = Rt[j * RTS + i]; if (i == j) v.x += db[i]; }
+                            else if (i == NSC) v = cconj(yb[j]);
+                        }
                     }
                     a[li][lj] = v;
                 }
@@ -283,15 +348,18 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
             const cx<T> *ub0 = Us + (lane <= 26 ? lane * 53 - 1 : (52 - lane) * 54);
             const cx<T> *ub1 = Us + (lane <= 20 ? (20 - lane) * 54 : 0);
             cx<T> y0 = ub0[NSC], y1 = (lane + 32 < NSC) ? ub1[NSC] : mk<T>(0, 0);
+            // (Solving four columns per round -- four shuffles issued together, the 4 x 4 diagonal block solved redundantly
+            // by every lane -- halves the serial chain but adds instructions; with 12 warps per SM in different phases the
+            // chain is already hidden and the kernel is issue-bound: measured 5.6 % slower in FP32, 3 % in FP64.)
 #pragma unroll 4
             for (int j = NSC - 1; j >= 32; --j) {
-                cx<T> zj = mk<T>(__shfl_sync(0xffffffffu, y1.x, j - 32), __shfl_sync(0xffffffffu, y1.y, j - 32));
+                cx<T> zj = shfl_cx(y1, j - 32);
                 cfms(y0, ub0[j], zj);
                 if (lane + 32 < j) cfms(y1, ub1[j], zj);
             }
 #pragma unroll 4
             for (int j = 31; j >= 1; --j) {
-                cx<T> zj = mk<T>(__shfl_sync(0xffffffffu, y0.x, j), __shfl_sync(0xffffffffu, y0.y, j));
+                cx<T> zj = shfl_cx(y0, j);
                 if (lane < j) cfms(y0, ub0[j], zj);
             }
             const bool second = lane + 32 < NSC;
@@ -302,13 +370,13 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
             // Bins whose noise term dominates the diagonal (d_k > R_kk: a bin with almost no transmit energy, the DC bin of the
             // inputs.h frame) have y_k ~ d_k z_k >> H_k, so y - d z cancels (measured 5.5e-10 at |y_dc| = 50 in FP64): they take
             // H_k = sum_j R_kj z_j instead, as a warp reduction (z_j lives in lanes j and j - 32).
-            unsigned m0 = __ballot_sync(0xffffffffu, d0 > Rt[lane * NSC + lane].x);
-            unsigned m1 = __ballot_sync(0xffffffffu, second && d1 > Rt[(lane + 32) * NSC + lane + 32].x);
+            unsigned m0 = __ballot_sync(0xffffffffu, d0 > Rt[lane * RTS + lane].x);
+            unsigned m1 = __ballot_sync(0xffffffffu, second && d1 > Rt[(lane + 32) * RTS + lane + 32].x);
             while (m0 | m1) {
                 const int k = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
                 if (m0) m0 &= m0 - 1; else m1 &= m1 - 1;
-                cx<T> acc = cmul(Rt[lane * NSC + k], y0);
-                if (second) cfma(acc, Rt[(lane + 32) * NSC + k], y1);
+                cx<T> acc = cmul(Rt[lane * RTS + k], y0);
+                if (second) cfma(acc, Rt[(lane + 32) * RTS + k], y1);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
@@ -324,13 +392,13 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
     }
 }
 
-template <typename T, typename TIO, int PR, int FPC, int MINB>
+template <typename T, typename TIO, int PR, int FPC, int MINB, int VAR = (sizeof(T) == 4)>
 static cudaError_t launch_hpd(const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H,
                               int64_t n_frames, cudaStream_t s)
 {
     using S = HpdSmem;
-    size_t smem = sizeof(cx<T>) * (H_RT + FPC * S::GROUP);
-    auto kern = mmse_hpd_kernel<T, TIO, PR, FPC, MINB>;
+    size_t smem = sizeof(cx<T>) * (RtSize<T>::v + FPC * S::GROUP);
+    auto kern = mmse_hpd_kernel<T, TIO, PR, FPC, MINB, VAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t need = (n_frames + FPC - 1) / FPC;
@@ -368,6 +436,7 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
         switch (cfg) {
         case 1: return launch_hpd<float, float, 4, 8, 1>(HPD_ARGS);
         case 2: return launch_hpd<float, float, 8, 8, 1>(HPD_ARGS);
+        case 10: return launch_hpd<float, float, 4, 12, 1, 0>(HPD_ARGS);
         default: return launch_hpd<float, float, 4, 12, 1>(HPD_ARGS);
         }
     }
