@@ -85,6 +85,22 @@ __device__ __forceinline__ double pivot_rcp(double x)
     return fma(r, fma(-x, r, 1.0), r);
 }
 
+// sign flip on the integer pipe (the FP64 pipe is the DMMA pipe)
+__device__ __forceinline__ double dneg(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// two Newton steps (2^-20 -> 2^-40 -> 2^-80): enough for FP64 once the seed has more than 14 good bits
+__device__ __forceinline__ double pivot_rcp2(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 // entries [lo, 8) of a 64-byte-aligned run of 8 complex values, with 16-byte shared loads
 template <int LO> __device__ __forceinline__ void load_run(const float2 *p, float2 (&v)[8])
 {
@@ -212,6 +228,119 @@ template <typename C> __device__ __forceinline__ C shfl_cx(C v, int src)
     return v;
 }
 template <typename T, typename TIO> __device__ __forceinline__ cx<T> widen(cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); }
+
+// R accessors of the back-substitution stage: the dense transposed image of mmse_hpd_kernel, the packed lower triangle of
+// mmse_hpd_dmma_kernel
+template <typename T> struct RtDense {
+    const cx<T> *Rt;
+    __device__ __forceinline__ T diag(int k) const { return Rt[k * RtStride<T>::v + k].x; }
+    __device__ __forceinline__ cx<T> at(int k, int l) const { return Rt[l * RtStride<T>::v + k]; }    // R[k][l]
+};
+template <typename TIO> struct RGlobal {                       // the caller's row-major R in global memory (rare path only)
+    const cx<TIO> *R;
+    __device__ __forceinline__ double diag(int k) const { return (double)R[k * NSC + k].x; }
+    __device__ __forceinline__ double2 at(int k, int l) const { const cx<TIO> v = R[k * NSC + l]; return mk<double>((double)v.x, (double)v.y); }
+};
+
+// Back-substitution with the unit-diagonal U' of the folded store on ONE warp (lane owns rows lane and lane + 32; entry 53 of
+// a row is the forward-substituted right-hand side), then H = y - D z, and H_k = sum_j R_kj z_j for the bins whose noise
+// term dominates the diagonal.
+template <typename T, typename TIO, bool BLOCKED = false, typename RA_t>
+__device__ __forceinline__ void hpd_backsub_store(const cx<T> *Us, const cx<T> *yb, const T *db, const RA_t RA, cx<TIO> *Hf, int lane)
+{
+    // lane owns rows i0 = lane and i1 = lane + 32; U'_ij lives at ub + j
+    const cx<T> *ub0 = Us + (lane <= 26 ? lane * 53 - 1 : (52 - lane) * 54);
+    const cx<T> *ub1 = Us + (lane <= 20 ? (20 - lane) * 54 : 0);
+    cx<T> y0 = ub0[NSC], y1 = (lane + 32 < NSC) ? ub1[NSC] : mk<T>(0, 0);
+    if (!BLOCKED) {
+        // (Solving four columns per round -- see below -- halves the serial chain but adds instructions; with 12 warps per SM
+        // in different phases the CUDA-core kernels are issue-bound and the chain is already hidden: measured 5.6 % slower
+        // in FP32, 3 % in FP64.  The DMMA kernel issues a third of the instructions and is latency-bound: it takes the
+        // blocked form.)
+#pragma unroll 4
+        for (int j = NSC - 1; j >= 32; --j) {
+            cx<T> zj = shfl_cx(y1, j - 32);
+            cfms(y0, ub0[j], zj);
+            if (lane + 32 < j) cfms(y1, ub1[j], zj);
+        }
+#pragma unroll 4
+        for (int j = 31; j >= 1; --j) {
+            cx<T> zj = shfl_cx(y0, j);
+            if (lane < j) cfms(y0, ub0[j], zj);
+        }
+    } else {
+        // Four columns per round: the four pending right-hand sides are broadcast by shuffles issued back to back, every lane
+        // solves the 4 x 4 unit-triangular diagonal block redundantly (its six coefficients are uniform loads that wait for
+        // nothing), then updates its own rows: the serial chain per column drops from shuffle + 2 FMAs to (shuffle + 8 FMAs)/4.
+        {   // column 52 on its own: 21 = 1 + 5 x 4 columns live in the second register
+            const cx<T> zj = shfl_cx(y1, NSC - 1 - 32);
+            cfms(y0, ub0[NSC - 1], zj);
+            if (lane + 32 < NSC - 1) cfms(y1, ub1[NSC - 1], zj);
+        }
+#pragma unroll 1
+        for (int jt = NSC - 2; jt >= 35; jt -= 4) {
+            // rows jt .. jt-3 are > 26: folded half of the U' store
+            const cx<T> *r1 = Us + (52 - (jt - 1)) * 54, *r2 = Us + (52 - (jt - 2)) * 54, *r3 = Us + (52 - (jt - 3)) * 54;
+            const cx<T> u10 = r1[jt], u20 = r2[jt], u21 = r2[jt - 1], u30 = r3[jt], u31 = r3[jt - 1], u32 = r3[jt - 2];
+            const cx<T> a0 = ub0[jt], a1 = ub0[jt - 1], a2 = ub0[jt - 2], a3 = ub0[jt - 3];
+            const cx<T> b0 = ub1[jt], b1 = ub1[jt - 1], b2 = ub1[jt - 2], b3 = ub1[jt - 3];
+            const cx<T> z0 = shfl_cx(y1, jt - 32);
+            cx<T> z1 = shfl_cx(y1, jt - 33), z2 = shfl_cx(y1, jt - 34), z3 = shfl_cx(y1, jt - 35);
+            cfms(z1, u10, z0);
+            cfms(z2, u20, z0); cfms(z3, u30, z0);
+            cfms(z2, u21, z1); cfms(z3, u31, z1);
+            cfms(z3, u32, z2);
+            cfms(y0, a0, z0); cfms(y0, a1, z1); cfms(y0, a2, z2); cfms(y0, a3, z3);
+            const int r = lane + 32;
+            if (r < jt) cfms(y1, b0, z0);
+            if (r < jt - 1) cfms(y1, b1, z1);
+            if (r < jt - 2) cfms(y1, b2, z2);
+            if (r < jt - 3) cfms(y1, b3, z3);
+        }
+#pragma unroll 1
+        for (int jt = 31; jt >= 3; jt -= 4) {
+            const cx<T> u10 = Us[us_off(jt - 1, jt)], u20 = Us[us_off(jt - 2, jt)], u21 = Us[us_off(jt - 2, jt - 1)];
+            const cx<T> u30 = Us[us_off(jt - 3, jt)], u31 = Us[us_off(jt - 3, jt - 1)], u32 = Us[us_off(jt - 3, jt - 2)];
+            // (entries at or left of the diagonal of my own row are loaded but never used; all stay inside the shared-memory block)
+            const cx<T> a0 = ub0[jt], a1 = ub0[jt - 1], a2 = ub0[jt - 2], a3 = ub0[jt - 3];
+            const cx<T> z0 = shfl_cx(y0, jt);
+            cx<T> z1 = shfl_cx(y0, jt - 1), z2 = shfl_cx(y0, jt - 2), z3 = shfl_cx(y0, jt - 3);
+            cfms(z1, u10, z0);
+            cfms(z2, u20, z0); cfms(z3, u30, z0);
+            cfms(z2, u21, z1); cfms(z3, u31, z1);
+            cfms(z3, u32, z2);
+            if (lane < jt) cfms(y0, a0, z0);
+            if (lane < jt - 1) cfms(y0, a1, z1);
+            if (lane < jt - 2) cfms(y0, a2, z2);
+            if (lane < jt - 3) cfms(y0, a3, z3);
+        }
+    }
+    const bool second = lane + 32 < NSC;
+    const T d0 = db[lane], d1 = second ? db[lane + 32] : (T)0;
+    cx<T> h0, h1 = mk<T>(0, 0);
+    { const cx<T> y = yb[lane]; h0 = mk<T>(y.x - d0 * y0.x, y.y - d0 * y0.y); }
+    if (second) { const cx<T> y = yb[lane + 32]; h1 = mk<T>(y.x - d1 * y1.x, y.y - d1 * y1.y); }
+    // Bins whose noise term dominates the diagonal (d_k > R_kk: a bin with almost no transmit energy, the DC bin of the
+    // inputs.h frame) have y_k ~ d_k z_k >> H_k, so y - d z cancels (measured 5.5e-10 at |y_dc| = 50 in FP64): they take
+    // H_k = sum_j R_kj z_j instead, as a warp reduction (z_j lives in lanes j and j - 32).
+    unsigned m0 = __ballot_sync(0xffffffffu, d0 > RA.diag(lane));
+    unsigned m1 = __ballot_sync(0xffffffffu, second && d1 > RA.diag(lane + 32));
+    while (m0 | m1) {
+        const int k = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
+        if (m0) m0 &= m0 - 1; else m1 &= m1 - 1;
+        cx<T> acc = cmul(RA.at(k, lane), y0);
+        if (second) cfma(acc, RA.at(k, lane + 32), y1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (k == lane) h0 = acc;
+        if (k == lane + 32) h1 = acc;
+    }
+    st_stream(Hf + lane, mk<TIO>((TIO)h0.x, (TIO)h0.y));
+    if (second) st_stream(Hf + lane + 32, mk<TIO>((TIO)h1.x, (TIO)h1.y));
+}
 
 template <typename T, typename TIO, int PR, int FPC, int MINB, int VAR>
 __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
@@ -343,53 +472,216 @@ __global__ void __launch_bounds__(PR * 8 * FPC, MINB)
         group_sync<LANES>(bar_id);
 
         // ---- back-substitution on the first warp of the group, then H = y - D z from registers ----
-        if (lane < 32) {
-            // lane owns rows i0 = lane and i1 = lane + 32; U'_ij lives at ub + j
-            const cx<T> *ub0 = Us + (lane <= 26 ? lane * 53 - 1 : (52 - lane) * 54);
-            const cx<T> *ub1 = Us + (lane <= 20 ? (20 - lane) * 54 : 0);
-            cx<T> y0 = ub0[NSC], y1 = (lane + 32 < NSC) ? ub1[NSC] : mk<T>(0, 0);
-            // (Solving four columns per round -- four shuffles issued together, the 4 x 4 diagonal block solved redundantly
-            // by every lane -- halves the serial chain but adds instructions; with 12 warps per SM in different phases the
-            // chain is already hidden and the kernel is issue-bound: measured 5.6 % slower in FP32, 3 % in FP64.)
-#pragma unroll 4
-            for (int j = NSC - 1; j >= 32; --j) {
-                cx<T> zj = shfl_cx(y1, j - 32);
-                cfms(y0, ub0[j], zj);
-                if (lane + 32 < j) cfms(y1, ub1[j], zj);
-            }
-#pragma unroll 4
-            for (int j = 31; j >= 1; --j) {
-                cx<T> zj = shfl_cx(y0, j);
-                if (lane < j) cfms(y0, ub0[j], zj);
-            }
-            const bool second = lane + 32 < NSC;
-            const T d0 = db[lane], d1 = second ? db[lane + 32] : (T)0;
-            cx<T> h0, h1 = mk<T>(0, 0);
-            { const cx<T> y = yb[lane]; h0 = mk<T>(y.x - d0 * y0.x, y.y - d0 * y0.y); }
-            if (second) { const cx<T> y = yb[lane + 32]; h1 = mk<T>(y.x - d1 * y1.x, y.y - d1 * y1.y); }
-            // Bins whose noise term dominates the diagonal (d_k > R_kk: a bin with almost no transmit energy, the DC bin of the
-            // inputs.h frame) have y_k ~ d_k z_k >> H_k, so y - d z cancels (measured 5.5e-10 at |y_dc| = 50 in FP64): they take
-            // H_k = sum_j R_kj z_j instead, as a warp reduction (z_j lives in lanes j and j - 32).
-            unsigned m0 = __ballot_sync(0xffffffffu, d0 > Rt[lane * RTS + lane].x);
-            unsigned m1 = __ballot_sync(0xffffffffu, second && d1 > Rt[(lane + 32) * RTS + lane + 32].x);
-            while (m0 | m1) {
-                const int k = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
-                if (m0) m0 &= m0 - 1; else m1 &= m1 - 1;
-                cx<T> acc = cmul(Rt[lane * RTS + k], y0);
-                if (second) cfma(acc, Rt[(lane + 32) * RTS + k], y1);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                }
-                if (k == lane) h0 = acc;
-                if (k == lane + 32) h1 = acc;
-            }
-            st_stream(H + f * NSC + lane, mk<TIO>((TIO)h0.x, (TIO)h0.y));
-            if (second) st_stream(H + f * NSC + lane + 32, mk<TIO>((TIO)h1.x, (TIO)h1.y));
-        }
+        if (lane < 32) hpd_backsub_store<T, TIO>(Us, yb, db, RtDense<T>{Rt}, H + f * NSC, lane);
         group_sync<LANES>(bar_id);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// FP64 arithmetic on the FP64 tensor path: the same un-pivoted L D L^H elimination of the bordered matrix, BLOCKED by two
+// columns, with the trailing update  A22 -= L (D L^H)  issued as DMMA.8x8x4 (mma.sync.m8n8k4.f64).
+//
+// A complex rank-2 update is a real rank-4 update -- exactly the k of the instruction -- in the half-embedded form
+//      C~ (2m x n) -= L~ (2m x 4) U~ (4 x n),   C~[2i + part][j] = Re/Im a_ij,
+//      L~ rows 2i, 2i+1 = [l0.re, -l0.im, l1.re, -l1.im], [l0.im, l0.re, l1.im, l1.re],   U~ rows = u0.re, u0.im, u1.re, u1.im,
+// with l_ip = a_ip / d_p and u_pj = conj(a_jp): no redundant flops (a full 2m x 2n embedding would double them).
+// A frame is held by two warps as 8 x 8 real tiles = 4 complex rows x 8 complex columns, lower triangle only: warp w owns the
+// tile rows I = 2t + w (t = 0..6), tile columns J <= t -- 28 accumulator tiles = 112 registers per lane, the same footprint
+// as the CUDA-core layout, and the identical static register structure for both warps.  One block step:
+//   (1) the 8 lanes per tile that hold columns K, K+1 write them to the panel buffer P; barrier;
+//   (2) lane i factors row i of the panel (both pivots' reciprocals are formed redundantly by every lane from broadcast
+//       loads), writes its rows of -L~ and its row of U~ already in fragment order, and its entries of rows K, K+1 of the
+//       U' store for the back-substitution; barrier;
+//   (3) each warp loads one A fragment per live tile row and one B fragment per live tile column (one conflict-free 8-byte
+//       load each: fragment (I) is the 256 contiguous bytes L~[32 I + lane]) and issues one DMMA per live tile.
+// One warp instruction carries 256 FMAs with two operand registers per lane, so the elimination needs ~3.5 k instructions
+// per warp and frame instead of ~6.7 k, and the FP64 pipe is fed by 28 instructions per block step while the other warps'
+// panel work proceeds.  Tiles are grouped by h = K / 8 (four block steps touch the same tiles: t, J >= h) so that every
+// register index is static; positions above the diagonal inside a straddling tile, finished rows and the padding rows /
+// columns (54, 55 / 53..55) receive garbage that never reaches a live element (an accumulator element only ever feeds
+// itself; panel rows <= K+1 and columns >= 53 are written as zeros).
+constexpr int DM_LANES = 64;
+constexpr int DM_PL = 116;          // plane stride of -L~ in doubles: 112 rows + 4, so the four planes start 8 banks apart
+struct DmSmem {                                  // per group, in units of double2
+    static constexpr int US = 0;                 // folded U' store, as above
+    static constexpr int YB = US + H_US;         // [56]
+    static constexpr int DB = YB + 56;           // double[56]
+    static constexpr int PB = DB + 28;           // panel columns: P[p][i], p = 0, 1, i < 56
+    static constexpr int LT = PB + 112;          // -L~ : double[4][DM_PL], plane k = column k of the A operand
+    static constexpr int UT = LT + 232;          // U~  : double[56][4]
+    static constexpr int GROUP = UT + 112;       // 2000
+};
+constexpr int DM_RF = 2 * 28 * 32;          // R in accumulator-fragment order: [warp of the pair][tile t (t + 1) / 2 + J][lane] -> (c0, c1)
+
+struct DmLane {
+    double *Pd;         // panel buffer as doubles: Pd[p * 112 + 2 i + part]
+    double2 *Pc;        // the same as complex: Pc[p * 56 + i]
+    double *Ld, *Ud;    // -L~ and U~ as doubles
+    double2 *Us;
+    int w, l32, gl, bar_id;     // warp of the pair, lane in the warp, lane in the pair (= panel row)
+};
+
+template <int HH>
+struct DmGroup {
+    static __device__ __forceinline__ void run(double (&acc)[7][7][2], const DmLane &L)
+    {
+        constexpr int NQ = HH == 6 ? 3 : 4;
+#pragma unroll 1
+        for (int q = 0; q < NQ; ++q) {
+            const int K = 8 * HH + 2 * q;
+            // (1) columns K, K+1 live in tile column HH, column pair q of the accumulator fragment: lanes with (lane & 3) == q
+            if ((L.l32 & 3) == q) {
+                double *p0 = L.Pd + 8 * L.w + (L.l32 >> 2);           // 2 i + part = 8 I + (lane >> 2), I = 2 t + w
+#pragma unroll
+                for (int t = HH; t < 7; ++t) {
+                    p0[16 * t] = acc[t][HH][0];
+                    p0[16 * t + 112] = acc[t][HH][1];
+                }
+            }
+            group_sync<DM_LANES>(L.bar_id);
+            // (2) panel row i = lane of the pair.  Finished rows / columns and the padding are NOT masked: whatever they put
+            // into -L~ and U~ only reaches accumulator rows / columns that are never read again.
+            if (L.gl < 56) {
+                const int i = L.gl;
+                const double2 pk = L.Pc[K], c1 = L.Pc[K + 1], e1 = L.Pc[56 + K + 1];
+                const double2 a0 = L.Pc[i];
+                double2 a1 = L.Pc[56 + i];
+                // both pivots' reciprocals from ONE reciprocal chain: with det = d_K e - |c|^2 (the 2 x 2 leading minor),
+                // 1/d_K = det / (d_K det) and 1/d'_(K+1) = d_K / det = d_K^2 / (d_K det)
+                const double d0 = pk.x;
+                const double det = K == NSC - 1 ? 1.0 : fma(e1.x, d0, -fma(c1.x, c1.x, c1.y * c1.y));   // (no column 53)
+                const double r = pivot_rcp2(d0 * det);
+                const double ninv0 = -(det * r), ninv1 = -(d0 * d0 * r);
+                const double2 t1 = mk<double>(c1.x * ninv0, -c1.y * ninv0);         // -conj(a_(K+1)K) / d_K
+                cfma(a1, a0, t1);                                                    // column K+1 after step K
+                const double2 nl0 = mk<double>(a0.x * ninv0, a0.y * ninv0), nl1 = mk<double>(a1.x * ninv1, a1.y * ninv1);   // -l
+                // rows K, K+1 of U' = D^-1 L^H (entry 53 = forward-substituted right-hand side)
+                if (i > K && i < H_N1) L.Us[us_off(K, i)] = mk<double>(dneg(nl0.x), nl0.y);
+                if (K + 1 < NSC && i > K + 1 && i < H_N1) L.Us[us_off(K + 1, i)] = mk<double>(dneg(nl1.x), nl1.y);
+                // -L~ in four planes (k = 0..3) of rows 2i, 2i+1: a lane's stores and the fragment loads are conflict-free
+                double2 *lp = reinterpret_cast<double2 *>(L.Ld + 2 * i);
+                lp[0] = mk<double>(nl0.x, nl0.y);
+                lp[DM_PL / 2] = mk<double>(dneg(nl0.y), nl0.x);
+                lp[DM_PL] = mk<double>(nl1.x, nl1.y);
+                lp[3 * DM_PL / 2] = mk<double>(dneg(nl1.y), nl1.x);
+                *reinterpret_cast<double4 *>(L.Ud + 4 * i) = make_double4(a0.x, dneg(a0.y), a1.x, dneg(a1.y));
+            }
+            group_sync<DM_LANES>(L.bar_id);
+            if (K == NSC - 1) break;        // column 53 does not exist and nothing is left to update
+            // (3) fragments and the tile updates
+            double A[7], B[7];
+#pragma unroll
+            for (int t = HH; t < 7; ++t) A[t] = L.Ld[(L.l32 & 3) * DM_PL + 8 * (2 * t + L.w) + (L.l32 >> 2)];
+#pragma unroll
+            for (int J = HH; J < 7; ++J) B[J] = L.Ud[32 * J + L.l32];
+#pragma unroll
+            for (int t = HH; t < 7; ++t)
+#pragma unroll
+                for (int J = HH; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+        }
+        DmGroup<HH + 1>::run(acc, L);
+    }
+};
+template <> struct DmGroup<7> {
+    static __device__ __forceinline__ void run(double (&)[7][7][2], const DmLane &) {}
+};
+
+template <typename TIO, int FPC>
+__global__ void __launch_bounds__(DM_LANES * FPC, 1)
+    mmse_hpd_dmma_kernel(const cx<TIO> *__restrict__ R, const cx<TIO> *__restrict__ tx, const cx<TIO> *__restrict__ rx, int64_t frame_stride,
+                         const TIO *__restrict__ sigma2, cx<TIO> *__restrict__ H, int64_t n_frames)
+{
+    using S = DmSmem;
+    extern __shared__ __align__(16) unsigned char hpd_smem[];
+    double2 *Rf = (double2 *)hpd_smem;
+    const int grp = threadIdx.x / DM_LANES, gl = threadIdx.x % DM_LANES, w = gl >> 5, l32 = gl & 31;
+    double2 *gs = Rf + DM_RF + grp * S::GROUP;
+    double2 *Us = gs + S::US, *yb = gs + S::YB;
+    double *db = (double *)(gs + S::DB);
+    const DmLane L = {(double *)(gs + S::PB), gs + S::PB, (double *)(gs + S::LT), (double *)(gs + S::UT), Us, w, l32, gl, grp + 1};
+
+    // R once per CTA, already in the order the accumulator fragments want it: the per-frame set-up is one conflict-free
+    // 16-byte load per tile (elements above the diagonal carry the true R values and are never used; padding is zero)
+    for (int e = threadIdx.x; e < DM_RF; e += DM_LANES * FPC) {
+        const int el = e & 31, tl = (e >> 5) % 28, ew = e / (32 * 28);
+        int t = 0;
+        while ((t + 1) * (t + 2) / 2 <= tl) ++t;
+        const int J = tl - t * (t + 1) / 2;
+        const int i = 4 * (2 * t + ew) + (el >> 3), pt = (el >> 2) & 1, j0 = 8 * J + 2 * (el & 3);
+        double2 v = mk<double>(0, 0);
+        if (i < NSC) {
+            if (j0 < NSC) { const cx<TIO> r0 = R[i * NSC + j0]; v.x = (double)(pt ? r0.y : r0.x); }
+            if (j0 + 1 < NSC) { const cx<TIO> r1 = R[i * NSC + j0 + 1]; v.y = (double)(pt ? r1.y : r1.x); }
+        }
+        Rf[e] = v;
+    }
+    if (gl < 3) { yb[NSC + gl] = mk<double>(0, 0); db[NSC + gl] = 0.0; }
+    for (int e = gl; e < S::GROUP - S::PB; e += DM_LANES) gs[S::PB + e] = mk<double>(0, 0);
+    __syncthreads();
+
+    // accumulator element (tile t, J) of this lane: complex row 4 (2t + w) + (l32 >> 3), part (l32 >> 2) & 1, columns 8 J + 2 (l32 & 3), +1
+    const int part = (l32 >> 2) & 1, rsub = l32 >> 3, csub = 2 * (l32 & 3);
+    const int64_t fstep = (int64_t)gridDim.x * FPC;
+    for (int64_t f = (int64_t)blockIdx.x * FPC + grp; f < n_frames; f += fstep) {
+        // ---- per-frame inputs: y = rx/tx, d = sigma2/|tx|^2 ----
+        if (gl < NSC) {
+            const cx<double> t = widen<double, TIO>(ld_stream(tx + f * frame_stride + gl)), r = widen<double, TIO>(ld_stream(rx + f * frame_stride + gl));
+            yb[gl] = cdiv(r, t);
+            db[gl] = (double)sigma2[f] / cabs2(t);
+        }
+        {
+            const int64_t fn = f + fstep;
+            if (fn < n_frames && gl < 8) {
+                const cx<TIO> *p = (gl < 4 ? tx : rx) + fn * frame_stride;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + (gl & 3) * 128));
+            }
+        }
+        group_sync<DM_LANES>(L.bar_id);
+        // ---- accumulator tiles of the bordered matrix [A; y^H], lower triangle ----
+        double acc[7][7][2];
+        const double2 *rf = Rf + w * (28 * 32) + l32;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const int i = 4 * (2 * t + w) + rsub;
+#pragma unroll
+            for (int J = 0; J <= t; ++J) {
+                const int j0 = 8 * J + csub, j1 = j0 + 1;
+                const double2 v = rf[(t * (t + 1) / 2 + J) * 32];
+                double v0 = v.x, v1 = v.y;
+                if (J == t) {                                            // the diagonal runs through tile column t only
+                    const double dd = part ? 0.0 : db[i];                // (zero beyond row 52)
+                    if (i == j0) v0 += dd;
+                    if (i == j1) v1 += dd;
+                }
+                if (t == 6) {                                            // rows 52..55 (w = 1): row 53 is the right-hand side
+                    const double2 y0 = yb[j0], y1 = yb[j1];              // zero beyond column 52
+                    if (i == NSC) { v0 = part ? -y0.y : y0.x; v1 = part ? -y1.y : y1.x; }
+                }
+                acc[t][J][0] = v0;
+                acc[t][J][1] = v1;
+            }
+        }
+        // ---- blocked elimination ----
+        DmGroup<0>::run(acc, L);
+        // ---- back-substitution on the first warp of the pair, then H = y - D z ----
+        if (gl < 32) hpd_backsub_store<double, TIO, true>(Us, yb, db, RGlobal<TIO>{R}, H + f * NSC, gl);
+        group_sync<DM_LANES>(L.bar_id);
+    }
+}
+
+template <typename TIO, int FPC>
+static cudaError_t launch_hpd_dmma(const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H,
+                                   int64_t n_frames, cudaStream_t s)
+{
+    size_t smem = sizeof(double2) * (DM_RF + FPC * DmSmem::GROUP);
+    auto kern = mmse_hpd_dmma_kernel<TIO, FPC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t need = (n_frames + FPC - 1) / FPC;
+    unsigned grid = (unsigned)std::min<int64_t>(need, 148);
+    kern<<<grid, DM_LANES * FPC, smem, s>>>((const cx<TIO> *)R, (const cx<TIO> *)tx, (const cx<TIO> *)rx, frame_stride,
+                                            (const TIO *)sigma2, (cx<TIO> *)H, n_frames);
+    return cudaGetLastError();
 }
 
 template <typename T, typename TIO, int PR, int FPC, int MINB, int VAR = (sizeof(T) == 4)>
@@ -429,6 +721,9 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
     if (dt == WIFI_F32 && wide) {
         switch (cfg) {
         case 1: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
+        case 20: return launch_hpd_dmma<float, 6>(HPD_ARGS);
+        case 21: return launch_hpd_dmma<float, 4>(HPD_ARGS);
+        case 22: return launch_hpd_dmma<float, 2>(HPD_ARGS);
         default: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
         }
     }
@@ -442,6 +737,9 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
     }
     switch (cfg) {
     case 1: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
+    case 20: return launch_hpd_dmma<double, 6>(HPD_ARGS);
+    case 21: return launch_hpd_dmma<double, 4>(HPD_ARGS);
+    case 22: return launch_hpd_dmma<double, 2>(HPD_ARGS);
     default: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
     }
 #undef HPD_ARGS
