@@ -229,8 +229,8 @@ template <typename C> __device__ __forceinline__ C shfl_cx(C v, int src)
 }
 template <typename T, typename TIO> __device__ __forceinline__ cx<T> widen(cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); }
 
-// R accessors of the back-substitution stage: the dense transposed image of mmse_hpd_kernel, the packed lower triangle of
-// mmse_hpd_dmma_kernel
+// R accessors of the back-substitution stage: the dense transposed image of mmse_hpd_kernel; the caller's global array for
+// mmse_hpd_dmma_kernel (whose shared-memory image is in fragment order)
 template <typename T> struct RtDense {
     const cx<T> *Rt;
     __device__ __forceinline__ T diag(int k) const { return Rt[k * RtStride<T>::v + k].x; }
@@ -245,75 +245,26 @@ template <typename TIO> struct RGlobal {                       // the caller's r
 // Back-substitution with the unit-diagonal U' of the folded store on ONE warp (lane owns rows lane and lane + 32; entry 53 of
 // a row is the forward-substituted right-hand side), then H = y - D z, and H_k = sum_j R_kj z_j for the bins whose noise
 // term dominates the diagonal.
-template <typename T, typename TIO, bool BLOCKED = false, typename RA_t>
+template <typename T, typename TIO, typename RA_t>
 __device__ __forceinline__ void hpd_backsub_store(const cx<T> *Us, const cx<T> *yb, const T *db, const RA_t RA, cx<TIO> *Hf, int lane)
 {
     // lane owns rows i0 = lane and i1 = lane + 32; U'_ij lives at ub + j
     const cx<T> *ub0 = Us + (lane <= 26 ? lane * 53 - 1 : (52 - lane) * 54);
     const cx<T> *ub1 = Us + (lane <= 20 ? (20 - lane) * 54 : 0);
     cx<T> y0 = ub0[NSC], y1 = (lane + 32 < NSC) ? ub1[NSC] : mk<T>(0, 0);
-    if (!BLOCKED) {
-        // (Solving four columns per round -- see below -- halves the serial chain but adds instructions; with 12 warps per SM
-        // in different phases the CUDA-core kernels are issue-bound and the chain is already hidden: measured 5.6 % slower
-        // in FP32, 3 % in FP64.  The DMMA kernel issues a third of the instructions and is latency-bound: it takes the
-        // blocked form.)
+    // (Solving four columns per round -- four shuffles issued together, the 4 x 4 diagonal block solved redundantly by every
+    // lane -- halves the serial chain but adds FP64 instructions: measured 5.6 % slower in FP32, 3 % in FP64 on the CUDA-core
+    // kernels (issue-bound) and 5 % slower on the DMMA kernel, whose FP64 pipe is shared with the tile updates.)
 #pragma unroll 4
-        for (int j = NSC - 1; j >= 32; --j) {
-            cx<T> zj = shfl_cx(y1, j - 32);
-            cfms(y0, ub0[j], zj);
-            if (lane + 32 < j) cfms(y1, ub1[j], zj);
-        }
+    for (int j = NSC - 1; j >= 32; --j) {
+        cx<T> zj = shfl_cx(y1, j - 32);
+        cfms(y0, ub0[j], zj);
+        if (lane + 32 < j) cfms(y1, ub1[j], zj);
+    }
 #pragma unroll 4
-        for (int j = 31; j >= 1; --j) {
-            cx<T> zj = shfl_cx(y0, j);
-            if (lane < j) cfms(y0, ub0[j], zj);
-        }
-    } else {
-        // Four columns per round: the four pending right-hand sides are broadcast by shuffles issued back to back, every lane
-        // solves the 4 x 4 unit-triangular diagonal block redundantly (its six coefficients are uniform loads that wait for
-        // nothing), then updates its own rows: the serial chain per column drops from shuffle + 2 FMAs to (shuffle + 8 FMAs)/4.
-        {   // column 52 on its own: 21 = 1 + 5 x 4 columns live in the second register
-            const cx<T> zj = shfl_cx(y1, NSC - 1 - 32);
-            cfms(y0, ub0[NSC - 1], zj);
-            if (lane + 32 < NSC - 1) cfms(y1, ub1[NSC - 1], zj);
-        }
-#pragma unroll 1
-        for (int jt = NSC - 2; jt >= 35; jt -= 4) {
-            // rows jt .. jt-3 are > 26: folded half of the U' store
-            const cx<T> *r1 = Us + (52 - (jt - 1)) * 54, *r2 = Us + (52 - (jt - 2)) * 54, *r3 = Us + (52 - (jt - 3)) * 54;
-            const cx<T> u10 = r1[jt], u20 = r2[jt], u21 = r2[jt - 1], u30 = r3[jt], u31 = r3[jt - 1], u32 = r3[jt - 2];
-            const cx<T> a0 = ub0[jt], a1 = ub0[jt - 1], a2 = ub0[jt - 2], a3 = ub0[jt - 3];
-            const cx<T> b0 = ub1[jt], b1 = ub1[jt - 1], b2 = ub1[jt - 2], b3 = ub1[jt - 3];
-            const cx<T> z0 = shfl_cx(y1, jt - 32);
-            cx<T> z1 = shfl_cx(y1, jt - 33), z2 = shfl_cx(y1, jt - 34), z3 = shfl_cx(y1, jt - 35);
-            cfms(z1, u10, z0);
-            cfms(z2, u20, z0); cfms(z3, u30, z0);
-            cfms(z2, u21, z1); cfms(z3, u31, z1);
-            cfms(z3, u32, z2);
-            cfms(y0, a0, z0); cfms(y0, a1, z1); cfms(y0, a2, z2); cfms(y0, a3, z3);
-            const int r = lane + 32;
-            if (r < jt) cfms(y1, b0, z0);
-            if (r < jt - 1) cfms(y1, b1, z1);
-            if (r < jt - 2) cfms(y1, b2, z2);
-            if (r < jt - 3) cfms(y1, b3, z3);
-        }
-#pragma unroll 1
-        for (int jt = 31; jt >= 3; jt -= 4) {
-            const cx<T> u10 = Us[us_off(jt - 1, jt)], u20 = Us[us_off(jt - 2, jt)], u21 = Us[us_off(jt - 2, jt - 1)];
-            const cx<T> u30 = Us[us_off(jt - 3, jt)], u31 = Us[us_off(jt - 3, jt - 1)], u32 = Us[us_off(jt - 3, jt - 2)];
-            // (entries at or left of the diagonal of my own row are loaded but never used; all stay inside the shared-memory block)
-            const cx<T> a0 = ub0[jt], a1 = ub0[jt - 1], a2 = ub0[jt - 2], a3 = ub0[jt - 3];
-            const cx<T> z0 = shfl_cx(y0, jt);
-            cx<T> z1 = shfl_cx(y0, jt - 1), z2 = shfl_cx(y0, jt - 2), z3 = shfl_cx(y0, jt - 3);
-            cfms(z1, u10, z0);
-            cfms(z2, u20, z0); cfms(z3, u30, z0);
-            cfms(z2, u21, z1); cfms(z3, u31, z1);
-            cfms(z3, u32, z2);
-            if (lane < jt) cfms(y0, a0, z0);
-            if (lane < jt - 1) cfms(y0, a1, z1);
-            if (lane < jt - 2) cfms(y0, a2, z2);
-            if (lane < jt - 3) cfms(y0, a3, z3);
-        }
+    for (int j = 31; j >= 1; --j) {
+        cx<T> zj = shfl_cx(y0, j);
+        if (lane < j) cfms(y0, ub0[j], zj);
     }
     const bool second = lane + 32 < NSC;
     const T d0 = db[lane], d1 = second ? db[lane + 32] : (T)0;
@@ -521,63 +472,80 @@ struct DmLane {
     int w, l32, gl, bar_id;     // warp of the pair, lane in the warp, lane in the pair (= panel row)
 };
 
+// (1) columns K, K+1 live in tile column HH = K / 8, column pair q = (K & 7) / 2 of the accumulator fragment
+template <int HH>
+__device__ __forceinline__ void dm_extract(const double (&acc)[7][7][2], const DmLane &L, int q)
+{
+    if ((L.l32 & 3) == q) {
+        double *p0 = L.Pd + 8 * L.w + (L.l32 >> 2);           // 2 i + part = 8 I + (lane >> 2), I = 2 t + w
+#pragma unroll
+        for (int t = HH; t < 7; ++t) {
+            p0[16 * t] = acc[t][HH][0];
+            p0[16 * t + 112] = acc[t][HH][1];
+        }
+    }
+}
+
+// (2) panel row i = lane of the pair.  Finished rows / columns and the padding are NOT masked: whatever they put into -L~ and
+// U~ only reaches accumulator rows / columns that are never read again.
+__device__ __forceinline__ void dm_panel(const DmLane &L, int K)
+{
+    {
+        // (lanes 56..63 repeat row 55: no branch, so that the compiler can interleave this chain with the DMMAs around it)
+        const int i = L.gl < 56 ? L.gl : 55;
+        const double2 pk = L.Pc[K], c1 = L.Pc[K + 1], e1 = L.Pc[56 + K + 1];
+        const double2 a0 = L.Pc[i];
+        double2 a1 = L.Pc[56 + i];
+        // both pivots' reciprocals from ONE reciprocal chain: with det = d_K e - |c|^2 (the 2 x 2 leading minor),
+        // 1/d_K = det / (d_K det) and 1/d'_(K+1) = d_K / det = d_K^2 / (d_K det)
+        const double d0 = pk.x;
+        const double det = K == NSC - 1 ? 1.0 : fma(e1.x, d0, -fma(c1.x, c1.x, c1.y * c1.y));   // (there is no column 53)
+        const double r = pivot_rcp2(d0 * det);
+        const double ninv0 = -(det * r), ninv1 = -(d0 * d0 * r);
+        const double2 t1 = mk<double>(c1.x * ninv0, -c1.y * ninv0);         // -conj(a_(K+1)K) / d_K
+        cfma(a1, a0, t1);                                                    // column K+1 after step K
+        const double2 nl0 = mk<double>(a0.x * ninv0, a0.y * ninv0), nl1 = mk<double>(a1.x * ninv1, a1.y * ninv1);   // -l
+        // rows K, K+1 of U' = D^-1 L^H (entry 53 = forward-substituted right-hand side)
+        if (i > K && i < H_N1) L.Us[us_off(K, i)] = mk<double>(dneg(nl0.x), nl0.y);
+        if (K + 1 < NSC && i > K + 1 && i < H_N1) L.Us[us_off(K + 1, i)] = mk<double>(dneg(nl1.x), nl1.y);
+        // -L~ in four planes (k = 0..3) of rows 2i, 2i+1: a lane's stores and the fragment loads are conflict-free
+        double2 *lp = reinterpret_cast<double2 *>(L.Ld + 2 * i);
+        lp[0] = mk<double>(nl0.x, nl0.y);
+        lp[DM_PL / 2] = mk<double>(dneg(nl0.y), nl0.x);
+        lp[DM_PL] = mk<double>(nl1.x, nl1.y);
+        lp[3 * DM_PL / 2] = mk<double>(dneg(nl1.y), nl1.x);
+        *reinterpret_cast<double4 *>(L.Ud + 4 * i) = make_double4(a0.x, dneg(a0.y), a1.x, dneg(a1.y));
+    }
+}
+
+// Block steps are grouped by the tile column HH of the NEXT panel: the trailing update of step K = 8 HH - 2 + 2 q touches rows
+// and columns >= K + 2 = 8 HH + 2 q, i.e. the tiles t, J >= HH whatever q is, so one compiled body serves the group.  The update
+// is split: the tiles of column HH -- they hold the next panel -- go first and are extracted at once; the next panel is then
+// factored (barrier, FP64 chain, barrier) while the DMMAs of the remaining tiles, whose fragments are already in registers,
+// drain through the same pipe.
 template <int HH>
 struct DmGroup {
     static __device__ __forceinline__ void run(double (&acc)[7][7][2], const DmLane &L)
     {
-        constexpr int NQ = HH == 6 ? 3 : 4;
+        constexpr int Q0 = HH == 0 ? 1 : 0, Q1 = HH == 6 ? 3 : 4;
 #pragma unroll 1
-        for (int q = 0; q < NQ; ++q) {
-            const int K = 8 * HH + 2 * q;
-            // (1) columns K, K+1 live in tile column HH, column pair q of the accumulator fragment: lanes with (lane & 3) == q
-            if ((L.l32 & 3) == q) {
-                double *p0 = L.Pd + 8 * L.w + (L.l32 >> 2);           // 2 i + part = 8 I + (lane >> 2), I = 2 t + w
-#pragma unroll
-                for (int t = HH; t < 7; ++t) {
-                    p0[16 * t] = acc[t][HH][0];
-                    p0[16 * t + 112] = acc[t][HH][1];
-                }
-            }
-            group_sync<DM_LANES>(L.bar_id);
-            // (2) panel row i = lane of the pair.  Finished rows / columns and the padding are NOT masked: whatever they put
-            // into -L~ and U~ only reaches accumulator rows / columns that are never read again.
-            if (L.gl < 56) {
-                const int i = L.gl;
-                const double2 pk = L.Pc[K], c1 = L.Pc[K + 1], e1 = L.Pc[56 + K + 1];
-                const double2 a0 = L.Pc[i];
-                double2 a1 = L.Pc[56 + i];
-                // both pivots' reciprocals from ONE reciprocal chain: with det = d_K e - |c|^2 (the 2 x 2 leading minor),
-                // 1/d_K = det / (d_K det) and 1/d'_(K+1) = d_K / det = d_K^2 / (d_K det)
-                const double d0 = pk.x;
-                const double det = K == NSC - 1 ? 1.0 : fma(e1.x, d0, -fma(c1.x, c1.x, c1.y * c1.y));   // (no column 53)
-                const double r = pivot_rcp2(d0 * det);
-                const double ninv0 = -(det * r), ninv1 = -(d0 * d0 * r);
-                const double2 t1 = mk<double>(c1.x * ninv0, -c1.y * ninv0);         // -conj(a_(K+1)K) / d_K
-                cfma(a1, a0, t1);                                                    // column K+1 after step K
-                const double2 nl0 = mk<double>(a0.x * ninv0, a0.y * ninv0), nl1 = mk<double>(a1.x * ninv1, a1.y * ninv1);   // -l
-                // rows K, K+1 of U' = D^-1 L^H (entry 53 = forward-substituted right-hand side)
-                if (i > K && i < H_N1) L.Us[us_off(K, i)] = mk<double>(dneg(nl0.x), nl0.y);
-                if (K + 1 < NSC && i > K + 1 && i < H_N1) L.Us[us_off(K + 1, i)] = mk<double>(dneg(nl1.x), nl1.y);
-                // -L~ in four planes (k = 0..3) of rows 2i, 2i+1: a lane's stores and the fragment loads are conflict-free
-                double2 *lp = reinterpret_cast<double2 *>(L.Ld + 2 * i);
-                lp[0] = mk<double>(nl0.x, nl0.y);
-                lp[DM_PL / 2] = mk<double>(dneg(nl0.y), nl0.x);
-                lp[DM_PL] = mk<double>(nl1.x, nl1.y);
-                lp[3 * DM_PL / 2] = mk<double>(dneg(nl1.y), nl1.x);
-                *reinterpret_cast<double4 *>(L.Ud + 4 * i) = make_double4(a0.x, dneg(a0.y), a1.x, dneg(a1.y));
-            }
-            group_sync<DM_LANES>(L.bar_id);
-            if (K == NSC - 1) break;        // column 53 does not exist and nothing is left to update
-            // (3) fragments and the tile updates
+        for (int q = Q0; q < Q1; ++q) {
+            // fragments of step K = 8 HH - 2 + 2 q (panel already factored and published)
             double A[7], B[7];
 #pragma unroll
             for (int t = HH; t < 7; ++t) A[t] = L.Ld[(L.l32 & 3) * DM_PL + 8 * (2 * t + L.w) + (L.l32 >> 2)];
 #pragma unroll
             for (int J = HH; J < 7; ++J) B[J] = L.Ud[32 * J + L.l32];
 #pragma unroll
-            for (int t = HH; t < 7; ++t)
+            for (int t = HH; t < 7; ++t) dmma_m8n8k4(acc[t][HH][0], acc[t][HH][1], A[t], B[HH]);
+            dm_extract<HH>(acc, L, q);
+            group_sync<DM_LANES>(L.bar_id);
+            dm_panel(L, 8 * HH + 2 * q);
 #pragma unroll
-                for (int J = HH; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+            for (int t = HH + 1; t < 7; ++t)
+#pragma unroll
+                for (int J = HH + 1; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+            group_sync<DM_LANES>(L.bar_id);
         }
         DmGroup<HH + 1>::run(acc, L);
     }
@@ -626,8 +594,9 @@ __global__ void __launch_bounds__(DM_LANES * FPC, 1)
         // ---- per-frame inputs: y = rx/tx, d = sigma2/|tx|^2 ----
         if (gl < NSC) {
             const cx<double> t = widen<double, TIO>(ld_stream(tx + f * frame_stride + gl)), r = widen<double, TIO>(ld_stream(rx + f * frame_stride + gl));
-            yb[gl] = cdiv(r, t);
-            db[gl] = (double)sigma2[f] / cabs2(t);
+            const double it = pivot_rcp(cabs2(t));            // one reciprocal (~1 ulp) serves rx/tx and sigma2/|tx|^2
+            yb[gl] = mk<double>((r.x * t.x + r.y * t.y) * it, (r.y * t.x - r.x * t.y) * it);
+            db[gl] = (double)sigma2[f] * it;
         }
         {
             const int64_t fn = f + fstep;
@@ -661,10 +630,14 @@ __global__ void __launch_bounds__(DM_LANES * FPC, 1)
                 acc[t][J][1] = v1;
             }
         }
-        // ---- blocked elimination ----
+        // ---- blocked elimination: panel 0, then the look-ahead loop ----
+        dm_extract<0>(acc, L, 0);
+        group_sync<DM_LANES>(L.bar_id);
+        dm_panel(L, 0);
+        group_sync<DM_LANES>(L.bar_id);
         DmGroup<0>::run(acc, L);
         // ---- back-substitution on the first warp of the pair, then H = y - D z ----
-        if (gl < 32) hpd_backsub_store<double, TIO, true>(Us, yb, db, RGlobal<TIO>{R}, H + f * NSC, gl);
+        if (gl < 32) hpd_backsub_store<double, TIO>(Us, yb, db, RGlobal<TIO>{R}, H + f * NSC, gl);
         group_sync<DM_LANES>(L.bar_id);
     }
 }
@@ -716,15 +689,13 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
     g_last_launches = 1;
     const int cfg = hpd_cfg();
 #define HPD_ARGS R, tx, rx, frame_stride, sigma2, H, n_frames, s
-    // measured on B200, 256 Ki frames (gpurun_out/hpd_probe6.log): f32 <4,12> 77.9 M frames/s (<8,8> 60.2, <4,8> 68.9);
-    // f64 <8,6> 34.1 M (<8,4> 31.7); FP32 storage + FP64 arithmetic <8,6> 35.4 M
+    // measured on B200, 256 Ki frames: f32 <4,12> 80.9 M frames/s (<8,8> 60.2, <4,8> 68.9); FP64 arithmetic: DMMA kernel
+    // 38.5 M (5 frames per CTA 31.7, 4: 31.9, 2: 22.6), CUDA-core <8,6> 34.5 M (<8,4> 31.7)
     if (dt == WIFI_F32 && wide) {
         switch (cfg) {
         case 1: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
-        case 20: return launch_hpd_dmma<float, 6>(HPD_ARGS);
-        case 21: return launch_hpd_dmma<float, 4>(HPD_ARGS);
-        case 22: return launch_hpd_dmma<float, 2>(HPD_ARGS);
-        default: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
+        case 10: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
+        default: return launch_hpd_dmma<float, 6>(HPD_ARGS);
         }
     }
     if (dt == WIFI_F32) {
@@ -737,10 +708,8 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
     }
     switch (cfg) {
     case 1: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
-    case 20: return launch_hpd_dmma<double, 6>(HPD_ARGS);
-    case 21: return launch_hpd_dmma<double, 4>(HPD_ARGS);
-    case 22: return launch_hpd_dmma<double, 2>(HPD_ARGS);
-    default: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
+    case 10: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
+    default: return launch_hpd_dmma<double, 6>(HPD_ARGS);
     }
 #undef HPD_ARGS
 }
