@@ -491,8 +491,9 @@ __device__ __forceinline__ void dm_extract(const double (&acc)[7][7][2], const D
 __device__ __forceinline__ void dm_panel(const DmLane &L, int K)
 {
     {
-        // (lanes 56..63 repeat row 55: no branch, so that the compiler can interleave this chain with the DMMAs around it)
-        const int i = L.gl < 56 ? L.gl : 55;
+        // lane g of the pair takes row K + 1 + g (rows <= K are finished); lanes past row 55 repeat it -- no branch, so that the
+        // compiler can interleave this chain with the DMMAs around it.  From K = 22 on, the first warp covers every live row.
+        const int i = K + 1 + L.gl < 56 ? K + 1 + L.gl : 55;
         const double2 pk = L.Pc[K], c1 = L.Pc[K + 1], e1 = L.Pc[56 + K + 1];
         const double2 a0 = L.Pc[i];
         double2 a1 = L.Pc[56 + i];
@@ -540,11 +541,22 @@ struct DmGroup {
             for (int t = HH; t < 7; ++t) dmma_m8n8k4(acc[t][HH][0], acc[t][HH][1], A[t], B[HH]);
             dm_extract<HH>(acc, L, q);
             group_sync<DM_LANES>(L.bar_id);
-            dm_panel(L, 8 * HH + 2 * q);
+            const int Kn = 8 * HH + 2 * q;
+            // the second warp's rows (K + 33 ..) are all finished from K = 22 on: it skips the panel's FP64 work (the FP64 pipe
+            // is the DMMA pipe).  The tile updates are repeated in both branches so that the panel chain and the DMMAs stay in
+            // one basic block.
+            if (HH < 2 || L.w == 0 || Kn < 22) {
+                dm_panel(L, Kn);
 #pragma unroll
-            for (int t = HH + 1; t < 7; ++t)
+                for (int t = HH + 1; t < 7; ++t)
 #pragma unroll
-                for (int J = HH + 1; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+                    for (int J = HH + 1; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+            } else {
+#pragma unroll
+                for (int t = HH + 1; t < 7; ++t)
+#pragma unroll
+                    for (int J = HH + 1; J <= t; ++J) dmma_m8n8k4(acc[t][J][0], acc[t][J][1], A[t], B[J]);
+            }
             group_sync<DM_LANES>(L.bar_id);
         }
         DmGroup<HH + 1>::run(acc, L);
@@ -636,8 +648,10 @@ __global__ void __launch_bounds__(DM_LANES * FPC, 1)
         dm_panel(L, 0);
         group_sync<DM_LANES>(L.bar_id);
         DmGroup<0>::run(acc, L);
-        // ---- back-substitution on the first warp of the pair, then H = y - D z ----
-        if (gl < 32) hpd_backsub_store<double, TIO>(Us, yb, db, RGlobal<TIO>{R}, H + f * NSC, gl);
+        // ---- back-substitution on one warp of the pair, then H = y - D z ----
+        // (on the SECOND warp: the first one carries every panel factorization from K = 22 on, this balances the FP64 work of
+        // the pair's two schedulers)
+        if (w == 1) hpd_backsub_store<double, TIO>(Us, yb, db, RGlobal<TIO>{R}, H + f * NSC, l32);
         group_sync<DM_LANES>(L.bar_id);
     }
 }
