@@ -67,7 +67,8 @@ typedef enum {
 
 /* flags of wifi_mmse_perframe_batch */
 #define WIFI_SOLVE_PIVOT 0      /* LU with partial pivoting + back-substitution, H = R z (any non-singular R + D) */
-#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted L D L^H, H = y - D z (growth factor 1) */
+#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted L D L^H, H = y - D z (growth factor 1); FP64
+                                 * arithmetic runs the trailing updates on the FP64 tensor path (DMMA) */
 #define WIFI_SOLVE_WIDE 2       /* with WIFI_SOLVE_HPD and WIFI_F32: FP32 storage, FP64 arithmetic inside the solve (sigma2/|x|^2
                                  * is below the FP32 resolution of R: the plain FP32 HPD solve is accurate to ~4e-3, the pivoted
                                  * one to ~1e-1; WIDE to 1e-7).  For frames that share |tx_k|^2 see wifi_mmse_eig_*. */
