@@ -304,6 +304,40 @@ def test_mmse_perframe_f64(ctx, wifi, oracle, flags, n):
             assert rel_err(got[lo], ref[lo]) < 5e-10
 
 
+_CUDA_CORE_SOLVE = r"""
+import importlib, sys
+import numpy as np, torch
+sys.path[:0] = [%r, %r]
+import synth
+from oracle.pyoracle import Oracle
+wifi = importlib.import_module("80211parallelestimation_b200")
+ctx, o = wifi.WifiContext(0), Oracle()
+fr = synth.make_frames(61, seed=71, sigma2="perframe")
+tx, rx, s2 = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy(), fr["sigma2"]
+dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+for R in (synth.channel_covariance(), synth.random_hpd(np.random.default_rng(5))):
+    ref = o.mmse_perframe(R, tx, rx, s2)
+    got = ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2), flags=wifi.SOLVE_HPD).cpu().numpy()
+    assert synth.rel_err(got, ref) < 5e-10, synth.rel_err(got, ref)
+    t32, r32, s32, R32 = tx.astype(np.complex64), rx.astype(np.complex64), s2.astype(np.float32), R.astype(np.complex64)
+    ref32 = o.mmse_perframe(R32.astype(complex), t32.astype(complex), r32.astype(complex), s32.astype(np.float64))
+    got32 = ctx.mmse_perframe(dev(R32), dev(t32), dev(r32), dev(s32), flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE).cpu().numpy()
+    assert synth.rel_err(got32, ref32) < 1e-6, synth.rel_err(got32, ref32)
+print("ok")
+"""
+
+
+def test_mmse_perframe_cuda_core_variant():
+    """WIFI_HPD_CFG=10 selects the CUDA-core L D L^H kernel that the DMMA kernel replaced for FP64 arithmetic (kept for A/B
+    timing); the variant is chosen once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WIFI_HPD_CFG="10")
+    r = subprocess.run([sys.executable, "-c", _CUDA_CORE_SOLVE % (root, os.path.join(root, "tests"))], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:]
+
+
 def test_mmse_perframe_kat(ctx, wifi, gold):
     k = gold["mmse_kat"]
     for fl in (wifi.SOLVE_PIVOT, wifi.SOLVE_HPD):
