@@ -22,6 +22,7 @@ template <typename T>
 __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ctl)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;      // (every caller launches a multiple of 32 threads)
     int singular = 0;
     for (int k = 0; k < n; ++k) {
         // 1. pivot search down column k (warp 0, shuffle arg-max on |a|^2)
@@ -55,24 +56,28 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
         // 3. multipliers of the rows below
         for (int i = k + 1 + tid; i < n; i += nt) lcol[i] = a[i * ld + k];
         __syncthreads();
-        // 4. eliminate column k from the rows below
-        const int w = ncols - (k + 1), h = n - (k + 1);
-        for (int e = tid; e < h * w; e += nt) {
-            int i = k + 1 + e / w, j = k + 1 + (e % w);
-            cx<T> v = a[i * ld + j];
-            cfms(v, lcol[i], a[k * ld + j]);
-            a[i * ld + j] = v;
+        // 4. eliminate column k from the rows below.  A warp walks along a row (lane = column: conflict-free with the odd row
+        // stride), warps take rows round-robin; the multiplier is a broadcast load and the pivot-row value stays in a register
+        // for all the rows of a column (the flat e / w, e % w indexing this replaces spent more on integer division than on FMAs).
+        for (int j = k + 1 + tx; j < ncols; j += 32) {
+            const cx<T> u = a[k * ld + j];
+            for (int i = k + 1 + ty; i < n; i += ny) {
+                cx<T> v = a[i * ld + j];
+                cfms(v, lcol[i], u);
+                a[i * ld + j] = v;
+            }
         }
         __syncthreads();
     }
     // back-substitution (unit upper-triangular U): rows above k lose u_ik * x_k
-    const int m = ncols - n;
     for (int k = n - 1; k >= 1; --k) {
-        for (int e = tid; e < k * m; e += nt) {
-            int i = e / m, j = n + (e - i * m);
-            cx<T> v = a[i * ld + j];
-            cfms(v, a[i * ld + k], a[k * ld + j]);
-            a[i * ld + j] = v;
+        for (int j = n + tx; j < ncols; j += 32) {
+            const cx<T> x = a[k * ld + j];
+            for (int i = ty; i < k; i += ny) {
+                cx<T> v = a[i * ld + j];
+                cfms(v, a[i * ld + k], x);
+                a[i * ld + j] = v;
+            }
         }
         __syncthreads();
     }

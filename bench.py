@@ -306,6 +306,18 @@ def extras_block(wifi, ctx, torch, peaks, mp, n_frames, steps, warmup):
             lambda: ctx.mmse_perframe(Rp, tx0[:npv], rx0[:npv], s2[:npv], flags=wifi.SOLVE_PIVOT, out=Hp[:npv]), npv, 159 * cbytes, 441949,
             nom, meas)
         del tx0, rx0, Hm, Hp
+        # utils.c routines, batched: 53 x 53 complex multiply() and inverse() through the mirror of the
+        # reference interface (allocation of the result and, for inverse, the singularity check included)
+        nb = 8192
+        g = torch.Generator(device="cuda").manual_seed(7)
+        cdt = torch.complex64 if prec == "f32" else torch.complex128
+        A = torch.randn(nb, NSC, NSC, dtype=cdt, device="cuda", generator=g)
+        A = A @ A.conj().transpose(1, 2) / NSC + torch.eye(NSC, dtype=cdt, device="cuda")       # Hermitian PD, well conditioned
+        out["utils_multiply_53_" + prec] = rate(lambda: ctx.multiply(A, A), nb, 3 * NSC * NSC * cbytes, 8 * NSC ** 3, nom, meas)
+        out["utils_inverse_53_" + prec] = rate(lambda: ctx.inverse(A), nb, 2 * NSC * NSC * cbytes, 8 * NSC ** 3, nom, meas)
+        for k in ("utils_multiply_53_", "utils_inverse_53_"):
+            out[k + prec]["note"] = "frames_per_s = matrices/s; the reference: multiply() 9.9 ms, inverse() 13 s per 53 x 53 matrix on one core (SURVEY 8a)"
+        del A
         torch.cuda.empty_cache()
     return out
 
