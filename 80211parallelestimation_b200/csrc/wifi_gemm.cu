@@ -130,6 +130,17 @@ cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, cons
 // ------------------------------------------------------------------------------------------
 // batched small-matrix utils (utils.h:38-60)
 // ------------------------------------------------------------------------------------------
+// one complex element global -> shared without a register round trip: the staging loops are pure latency otherwise (a dozen
+// dependent load -> store iterations per thread: ~19 k cycles per 53 x 53 pair, more than the product itself)
+template <typename C> __device__ __forceinline__ void stage_async(C *dst, const C *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "n"((int)sizeof(C)) : "memory");
+}
+__device__ __forceinline__ void stage_wait()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // multiply utils.c:16-31: one CTA per matrix pair, k ascending like the reference's inner loop.  Both operands are staged in
 // shared memory; a thread owns a 4 x 4 set of outputs -- rows tr + Sr i, columns tc + Sc j (Sr = ceil(r1 / 4), Sc = ceil(c2 / 4):
 // strided, so that the B loads of neighbouring threads are neighbouring addresses and the A loads are broadcasts) -- and does
@@ -142,8 +153,9 @@ __global__ void __launch_bounds__(256) cmatmul_kernel(const cx<T> *__restrict__ 
     cx<T> *sa = (cx<T> *)mm_smem, *sb = sa + r1 * c1;
     const cx<T> *Ab = A + (int64_t)blockIdx.x * r1 * c1, *Bb = B + (int64_t)blockIdx.x * c1 * c2;
     cx<T> *Cb = C + (int64_t)blockIdx.x * r1 * c2;
-    for (int e = threadIdx.x; e < r1 * c1; e += blockDim.x) sa[e] = Ab[e];
-    for (int e = threadIdx.x; e < c1 * c2; e += blockDim.x) sb[e] = Bb[e];
+    for (int e = threadIdx.x; e < r1 * c1; e += blockDim.x) stage_async(sa + e, Ab + e);
+    for (int e = threadIdx.x; e < c1 * c2; e += blockDim.x) stage_async(sb + e, Bb + e);
+    stage_wait();
     __syncthreads();
     const int Sr = (r1 + 3) >> 2, Sc = (c2 + 3) >> 2;
     if ((int)threadIdx.x >= Sr * Sc) return;
@@ -186,6 +198,69 @@ __global__ void __launch_bounds__(256) cmatmul_kernel(const cx<T> *__restrict__ 
     }
 }
 
+// FP64 multiply on the FP64 tensor path.  C = A B as the real product C~ (2 r1 x c2) = A~ (2 r1 x 2 c1) B~ (2 c1 x c2) in the
+// half-embedded form (rows 2i, 2i+1 of C~ = Re, Im of row i; A~ rows = [re, -im | im, re] per complex entry, B~ rows = Re, Im
+// of row p): the flop count of the complex product, no redundancy.  Both operands are staged in shared memory as complex
+// values, zero-padded to the tile grid (4 complex rows x 8 complex columns per 8 x 8 real tile, 2 complex k per DMMA); a warp
+// takes whole tile rows, builds its A fragment from one 16-byte load (select + sign by lane) and reads the B fragments as
+// plain 8-byte loads of the complex array.  k runs ascending like the reference's inner loop.
+__device__ __forceinline__ void mm_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) cmatmul_dmma_kernel(const double2 *__restrict__ A, int r1, int c1, const double2 *__restrict__ B, int c2,
+                                                           double2 *__restrict__ C)
+{
+    extern __shared__ __align__(16) unsigned char mm_smem[];
+    const int R1P = (r1 + 3) & ~3, C1P = (c1 + 1) & ~1, C2P = (c2 + 7) & ~7;
+    double2 *sa = (double2 *)mm_smem, *sb = sa + R1P * C1P;
+    const double2 *Ab = A + (int64_t)blockIdx.x * r1 * c1, *Bb = B + (int64_t)blockIdx.x * c1 * c2;
+    double2 *Cb = C + (int64_t)blockIdx.x * r1 * c2;
+    for (int e = threadIdx.x; e < R1P * C1P; e += blockDim.x) {
+        const int i = e / C1P, p = e - i * C1P;
+        if (i < r1 && p < c1) stage_async(sa + e, Ab + i * c1 + p);
+        else sa[e] = make_double2(0.0, 0.0);
+    }
+    for (int e = threadIdx.x; e < C1P * C2P; e += blockDim.x) {
+        const int p = e / C2P, j = e - p * C2P;
+        if (p < c1 && j < c2) stage_async(sb + e, Bb + p * c2 + j);
+        else sb[e] = make_double2(0.0, 0.0);
+    }
+    stage_wait();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int r = lane >> 2, q = lane & 3, part = r & 1, kk = q & 1;
+    const int ntc = C2P >> 3, nks = C1P >> 1;
+    const double *sbd = (const double *)sb + (size_t)((q >> 1) * C2P + r) * 2 + kk;       // B~[k = q][col = r] of tile column 0, k-step 0
+    for (int I = w; 4 * I < R1P; I += nw) {
+        const int i = 4 * I + (r >> 1);
+        const double2 *arow = sa + i * C1P + (q >> 1);
+        double acc[8][2];
+#pragma unroll
+        for (int J = 0; J < 8; ++J) acc[J][0] = acc[J][1] = 0.0;
+        for (int ks = 0; ks < nks; ++ks) {
+            const double2 a = arow[2 * ks];
+            const double av = part == kk ? a.x : (part ? a.y : -a.y);
+            const double *bp = sbd + (size_t)ks * 4 * C2P;
+#pragma unroll
+            for (int J = 0; J < 8; ++J)
+                if (J < ntc) mm_dmma(acc[J][0], acc[J][1], av, bp[16 * J]);
+        }
+        // a lane holds Re (part 0) or Im (part 1) of columns 8J + 2q, +1 of row i: pair up with the lane that holds the other part
+#pragma unroll
+        for (int J = 0; J < 8; ++J) {
+            if (J < ntc) {
+                const double send = part ? acc[J][0] : acc[J][1];
+                const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                const double2 out = part ? make_double2(recv, acc[J][1]) : make_double2(acc[J][0], recv);
+                const int col = 8 * J + 2 * q + part;
+                if (i < r1 && col < c2) Cb[i * c2 + col] = out;
+            }
+        }
+    }
+}
+
 cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const void *B, int c2, void *C, int64_t batch, cudaStream_t s)
 {
     g_last_launches = 0;
@@ -197,6 +272,14 @@ cudaError_t launch_cmatmul(wifi_dtype dt, const void *A, int r1, int c1, const v
         e = cudaFuncSetAttribute(cmatmul_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cmatmul_kernel<float><<<(unsigned)batch, 256, smem, s>>>((const float2 *)A, r1, c1, (const float2 *)B, c2, (float2 *)C);
+    } else if ((int64_t)r1 * c1 * c2 >= 4096 && c1 > 0) {
+        const int R1P = (r1 + 3) & ~3, C1P = (c1 + 1) & ~1, C2P = (c2 + 7) & ~7;
+        size_t smem = sizeof(double2) * ((size_t)R1P * C1P + (size_t)C1P * C2P);
+        e = cudaFuncSetAttribute(cmatmul_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // whole tile rows per warp: as many warps as keep the rounds full (14 tile rows at order 53 -> 7 warps x 2 rounds)
+        const int ntr = R1P / 4, rounds = (ntr + 7) / 8, warps = (ntr + rounds - 1) / rounds;
+        cmatmul_dmma_kernel<<<(unsigned)batch, 32 * warps, smem, s>>>((const double2 *)A, r1, c1, (const double2 *)B, c2, (double2 *)C);
     } else {
         size_t smem = sizeof(double2) * ((size_t)r1 * c1 + (size_t)c1 * c2);
         e = cudaFuncSetAttribute(cmatmul_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -61,7 +61,13 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
         // for all the rows of a column (the flat e / w, e % w indexing this replaces spent more on integer division than on FMAs).
         for (int j = k + 1 + tx; j < ncols; j += 32) {
             const cx<T> u = a[k * ld + j];
-            for (int i = k + 1 + ty; i < n; i += ny) {
+            int i = k + 1 + ty;
+            for (; i + 3 * ny < n; i += 4 * ny) {          // four independent rows in flight
+                cx<T> v0 = a[i * ld + j], v1 = a[(i + ny) * ld + j], v2 = a[(i + 2 * ny) * ld + j], v3 = a[(i + 3 * ny) * ld + j];
+                cfms(v0, lcol[i], u); cfms(v1, lcol[i + ny], u); cfms(v2, lcol[i + 2 * ny], u); cfms(v3, lcol[i + 3 * ny], u);
+                a[i * ld + j] = v0; a[(i + ny) * ld + j] = v1; a[(i + 2 * ny) * ld + j] = v2; a[(i + 3 * ny) * ld + j] = v3;
+            }
+            for (; i < n; i += ny) {
                 cx<T> v = a[i * ld + j];
                 cfms(v, lcol[i], u);
                 a[i * ld + j] = v;
@@ -73,7 +79,13 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
     for (int k = n - 1; k >= 1; --k) {
         for (int j = n + tx; j < ncols; j += 32) {
             const cx<T> x = a[k * ld + j];
-            for (int i = ty; i < k; i += ny) {
+            int i = ty;
+            for (; i + 3 * ny < k; i += 4 * ny) {
+                cx<T> v0 = a[i * ld + j], v1 = a[(i + ny) * ld + j], v2 = a[(i + 2 * ny) * ld + j], v3 = a[(i + 3 * ny) * ld + j];
+                cfms(v0, a[i * ld + k], x); cfms(v1, a[(i + ny) * ld + k], x); cfms(v2, a[(i + 2 * ny) * ld + k], x); cfms(v3, a[(i + 3 * ny) * ld + k], x);
+                a[i * ld + j] = v0; a[(i + ny) * ld + j] = v1; a[(i + 2 * ny) * ld + j] = v2; a[(i + 3 * ny) * ld + j] = v3;
+            }
+            for (; i < k; i += ny) {
                 cx<T> v = a[i * ld + j];
                 cfms(v, a[i * ld + k], x);
                 a[i * ld + j] = v;

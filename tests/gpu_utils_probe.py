@@ -1,0 +1,34 @@
+"""Timing + accuracy probe of the batched utils (GPU box; not a pytest file)."""
+import importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+wifi = importlib.import_module("80211parallelestimation_b200")
+ctx = wifi.WifiContext(0)
+nb = 8192
+g = torch.Generator(device="cuda").manual_seed(7)
+for cdt in (torch.complex64, torch.complex128):
+    for n in (53, 64, 17):
+        A = torch.randn(nb, n, n, dtype=cdt, device="cuda", generator=g); B = torch.randn(nb, n, n, dtype=cdt, device="cuda", generator=g)
+        ref = (A[:64].to(torch.complex128) @ B[:64].to(torch.complex128))
+        got = ctx.multiply(A, B)
+        err = float((got[:64].to(torch.complex128) - ref).abs().max() / ref.abs().max())
+        for _ in range(3): ctx.multiply(A, B)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): ctx.multiply(A, B)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("multiply %s n=%d: err %.2e | %.3f ms = %.3e matrices/s = %.2f TFLOP/s" % (str(cdt)[6:], n, err, ms, nb / ms * 1e3, nb * 8 * n ** 3 / ms / 1e9), flush=True)
+    A = torch.randn(nb, 53, 53, dtype=cdt, device="cuda", generator=g)
+    A = A @ A.conj().transpose(1, 2) / 53 + torch.eye(53, dtype=cdt, device="cuda")
+    Y = ctx.inverse(A)
+    err = float((Y[:64] @ A[:64] - torch.eye(53, dtype=cdt, device="cuda")).abs().max())
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): ctx.inverse(A)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("inverse %s n=53: |YA-I| %.2e | %.3f ms = %.3e matrices/s" % (str(cdt)[6:], err, ms, nb / ms * 1e3), flush=True)
