@@ -38,6 +38,14 @@ def main():
                 m = 1 << 17
                 cdt = torch.complex64 if prec == "f32" else torch.complex128
                 ctx.frontend(torch.randn(m, 1200, dtype=cdt, device="cuda"), torch.randn(m, 160, dtype=cdt, device="cuda"))
+            if (want("cmatmul") or want("cinverse")) and rep == 0:
+                g = torch.Generator(device="cuda").manual_seed(7)
+                cdt = torch.complex64 if prec == "f32" else torch.complex128
+                A = torch.randn(4096, 53, 53, dtype=cdt, device="cuda", generator=g)
+                A = A @ A.conj().transpose(1, 2) / 53 + torch.eye(53, dtype=cdt, device="cuda")
+                if want("cmatmul"): ctx.multiply(A, A)
+                if want("cinverse"): ctx.inverse(A)
+                del A
         torch.cuda.synchronize()
         del fr, tx0, rx0, H, outs, eq
         torch.cuda.empty_cache()
