@@ -510,6 +510,23 @@ def test_inverse_53(ctx, wifi, gold, oracle):
         ctx.inverse(dev(batch))
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("shape", [(17, 33, 9), (64, 64, 64), (5, 64, 64), (64, 3, 64), (53, 53, 1), (1, 53, 53), (40, 30, 50), (53, 53, 53)])
+def test_multiply_rectangular(ctx, oracle, prec, shape):
+    """multiply() (utils.c:16-31) on shapes that exercise the zero-padded tile grid of the FP64 tensor-path kernel (rows not a
+    multiple of 4, inner dimension odd or tiny, columns not a multiple of 8), the 4 x 4 register tiles of the FP32 kernel and
+    the small-product fallback; batch of 3, against the oracle's long-double product."""
+    r1, c1, c2 = shape
+    rng = np.random.default_rng(r1 * 10007 + c1 * 101 + c2)
+    A = (rng.standard_normal((3, r1, c1)) + 1j * rng.standard_normal((3, r1, c1))).astype(CDT[prec])
+    B = (rng.standard_normal((3, c1, c2)) + 1j * rng.standard_normal((3, c1, c2))).astype(CDT[prec])
+    got = host(ctx.multiply(dev(A), dev(B)))
+    assert got.shape == (3, r1, c2)
+    for b in range(3):
+        ref = oracle.multiply(A[b].astype(np.complex128), B[b].astype(np.complex128))
+        assert rel_err(got[b], ref, floor=1e-2) < (1e-12 if prec == "f64" else TOL["f32"])
+
+
 # ------------------------------------------------------------------ host-pointer entry points (numpy in, numpy out)
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_host_entry_points(ctx, wifi, oracle, prec):
