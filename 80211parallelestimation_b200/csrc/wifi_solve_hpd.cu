@@ -28,6 +28,10 @@
 // TIO is the storage type of R/tx/rx/sigma2/H and T the arithmetic type: <float,float>, <double,double>, and
 // <double,float> = WIFI_SOLVE_WIDE (FP32 I/O, FP64 arithmetic: d_f is below the FP32 resolution of R).
 //
+// Two kernels: mmse_hpd_kernel (the layout above; the default for FP32 arithmetic) and mmse_hpd_dmma_kernel further down
+// (FP64 arithmetic: the same elimination blocked by two columns with the trailing updates on the FP64 tensor path, DESIGN.md
+// 4.2a; WIFI_HPD_CFG=10 selects mmse_hpd_kernel<double, ...> instead for A/B timing).  Both share the back-substitution stage.
+//
 // Replaces the two inverse() calls of main.c:186,201 (utils.c:141-170, O(n^5)) for the intended formula.
 #include <algorithm>
 #include <cstdlib>
