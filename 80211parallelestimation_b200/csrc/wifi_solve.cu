@@ -18,8 +18,12 @@ namespace wifi {
 // backward error, and H = R z then loses ~cond(A) more digits (measured: 1e-7 vs 1e-11 in FP64).
 // lcol: n elements of scratch, ctl: 2 ints of scratch.  Every thread of the CTA must call.
 // Returns 1 (to all threads) if a pivot column was exactly zero.
-template <typename T>
-__device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ctl)
+// IDENT (the right-hand side is the identity, ncols = 2n; inverse()): the right half is kept in PIVOT ORDER and starts as zero --
+// storage column n + t belongs to the original row index of the t-th pivot row, whose 1 enters when that row is chosen --
+// so that after k steps only columns n .. n+k can be non-zero and the elimination skips the rest (a quarter of the flops of
+// eliminating [A | I] densely).  orig[] (n ints, initialised to 0..n-1 by the caller) returns that column order.
+template <typename T, bool IDENT = false>
+__device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ctl, int *orig = nullptr)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;      // (every caller launches a multiple of 32 threads)
@@ -46,9 +50,12 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
         if (ctl[1]) { singular = 1; }
         // 2. swap rows k <-> p and scale the pivot row (columns >= k)
         const cx<T> inv = crecip(a[p * ld + k]);
+        const int jend = IDENT ? n + k + 1 : ncols;          // columns that can be non-zero after this step
         __syncthreads();   // everyone has read the pivot before it is overwritten
-        for (int j = k + tid; j < ncols; j += nt) {
+        if (IDENT && tid == 0) { const int t = orig[k]; orig[k] = orig[p]; orig[p] = t; }
+        for (int j = k + tid; j < jend; j += nt) {
             cx<T> top = a[k * ld + j], piv = a[p * ld + j];
+            if (IDENT && j == n + k) piv = mk<T>((T)1, (T)0);      // the pivot row's own identity entry enters here
             a[k * ld + j] = cmul(piv, inv);
             if (p != k) a[p * ld + j] = top;
         }
@@ -59,7 +66,7 @@ __device__ int gj_solve(cx<T> *a, int n, int ld, int ncols, cx<T> *lcol, int *ct
         // 4. eliminate column k from the rows below.  A warp walks along a row (lane = column: conflict-free with the odd row
         // stride), warps take rows round-robin; the multiplier is a broadcast load and the pivot-row value stays in a register
         // for all the rows of a column (the flat e / w, e % w indexing this replaces spent more on integer division than on FMAs).
-        for (int j = k + 1 + tx; j < ncols; j += 32) {
+        for (int j = k + 1 + tx; j < jend; j += 32) {
             const cx<T> u = a[k * ld + j];
             int i = k + 1 + ty;
             for (; i + 3 * ny < n; i += 4 * ny) {          // four independent rows in flight
@@ -254,16 +261,18 @@ __global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__re
     __shared__ int ctl[2];
     const cx<T> *Ab = A + (int64_t)blockIdx.x * n * n;
     cx<T> *Yb = Y + (int64_t)blockIdx.x * n * n;
+    __shared__ int orig[WIFI_MAX_ORDER];
     for (int e = threadIdx.x; e < n * n; e += INV_THREADS) {
         int i = e / n, j = e - i * n;
         a[i * ld + j] = Ab[e];
-        a[i * ld + n + j] = mk<T>(i == j ? (T)1 : (T)0, (T)0);
+        a[i * ld + n + j] = mk<T>(0, 0);          // the identity enters pivot by pivot (gj_solve<T, true>)
     }
+    if (threadIdx.x < n) orig[threadIdx.x] = threadIdx.x;
     __syncthreads();
-    int sing = gj_solve<T>(a, n, ld, 2 * n, lcol, ctl);
+    int sing = gj_solve<T, true>(a, n, ld, 2 * n, lcol, ctl, orig);
     for (int e = threadIdx.x; e < n * n; e += INV_THREADS) {
-        int i = e / n, j = e - i * n;
-        Yb[e] = a[i * ld + n + j];
+        int i = e / n, t = e - i * n;
+        Yb[i * n + orig[t]] = a[i * ld + n + t];
     }
     if (threadIdx.x == 0 && info) info[blockIdx.x] = sing;
 }
