@@ -8,6 +8,7 @@
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
+#include <cstdlib>
 
 namespace wifi {
 
@@ -277,6 +278,122 @@ __global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__re
     if (threadIdx.x == 0 && info) info[blockIdx.x] = sing;
 }
 
+// Register-resident batched inverse for 32 < n <= 64: in-place Gauss-Jordan with implicit partial pivoting.
+// Every step of the in-place form updates the WHOLE n x n matrix (the right half of [A | I] moves into the columns the left
+// half vacates), so a thread can own a fixed 4 x 4 tile in registers for all n steps: no shrinking window, no row swaps.
+// Thread layout: tile row i = ty + 16 m, tile column j = tx + 16 mc; a warp holds all 16 ty of two adjacent tx, so the owners
+// of a column are one half-warp.  Step k (pivot row r, pivot p):
+//   A. the half-warp that owns column k picks r among the rows not used yet -- ONE redux.sync max over a 32-bit key (the top
+//      26 bits of |a|^2, then 63 - row so that ties go to the lowest row) --, gets p from its owner, publishes the scaled
+//      column c_i = a_ik / p (c_r = -1 / p) and clears its column;
+//   B. the 16 threads that own row r publish it as it is (entry k := 1) and clear it;
+//   C. every thread does a_ij -= c_i row_j on its tile: 8 shared loads for 16 complex FMAs.
+// This leaves a_rj / p in row r, 1 / p at (r, k) and -a_ik / p in column k: the in-place Gauss-Jordan step.  Two barriers
+// per step; column / row / pivot row index are double-buffered on the parity of k.  The physical result holds A^-1 with
+// both index sets permuted: Y[kof[i]][rowof[j]] = a_ij, rowof[k] = pivot row of step k, kof = its inverse.  Padded rows and
+// columns (>= n) are zero and never chosen.
+__device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
+{
+    __shared__ cx<T> colv[2][WIFI_MAX_ORDER], rowv[2][WIFI_MAX_ORDER];
+    __shared__ cx<T> pivv;
+    __shared__ int rowof[WIFI_MAX_ORDER], kof[WIFI_MAX_ORDER], ctl[2][2];
+    const int lane = threadIdx.x & 31, ty = lane & 15, tx = ((threadIdx.x >> 5) << 1) | (lane >> 4);
+    const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const cx<T> *Ab = A + (int64_t)blockIdx.x * n * n;
+    cx<T> *Yb = Y + (int64_t)blockIdx.x * n * n;
+    const cx<T> zero = mk<T>((T)0, (T)0);
+    cx<T> a[4][4];
+    unsigned used = 0;           // bit m: row ty + 16 m has been a pivot row (or is padding)
+    bool live[4];                // tile column c holds real columns
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (ty + 16 * m >= n) used |= 1u << m;
+        live[m] = tx + 16 * m < n;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ty + 16 * m, j = tx + 16 * c;
+            a[m][c] = (i < n && j < n) ? Ab[i * n + j] : zero;
+        }
+    }
+    if (threadIdx.x < WIFI_MAX_ORDER) { rowof[threadIdx.x] = threadIdx.x; kof[threadIdx.x] = threadIdx.x; }
+    int singular = 0;
+#pragma unroll
+    for (int mc = 0; mc < 4; ++mc) {
+#pragma unroll 1
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = 16 * mc + kk, b = k & 1;
+            if (k >= n) break;
+            if (tx == kk) {                                           // A: one half-warp, the owners of column k
+                unsigned key = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const unsigned km = 0x80000000u | (pivot_bits(cabs2(a[m][mc])) & 0x7fffffc0u) | (unsigned)(63 - (ty + 16 * m));
+                    if (!((used >> m) & 1u) && km > key) key = km;
+                }
+                const int bi = 63 - (int)(__reduce_max_sync(hmask, key) & 63u);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) if (ty + 16 * m == bi) pivv = a[m][mc];      // (a runtime register index would put the tile in local memory)
+                __syncwarp(hmask);
+                const cx<T> piv = pivv;
+                const T den = cabs2(piv), rden = (T)1 / den;
+                const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int i = ty + 16 * m;
+                    colv[b][i] = (i == bi) ? mk<T>(-inv.x, -inv.y) : cmul(a[m][mc], inv);
+                    a[m][mc] = zero;
+                }
+                if (ty == 0) { ctl[b][0] = bi; ctl[b][1] = (den > (T)0) ? 0 : 1; }
+            }
+            __syncthreads();
+            const int r = ctl[b][0];
+            singular |= ctl[b][1];
+            if (ty == (r & 15)) {                                     // B: the owners of row r
+                const int mr = r >> 4;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (m == mr) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int j = tx + 16 * c;
+                            rowv[b][j] = (j == k) ? mk<T>((T)1, (T)0) : a[m][c];
+                            a[m][c] = zero;
+                        }
+                    }
+                }
+                used |= 1u << mr;
+                if (tx == 0) { rowof[k] = r; kof[r] = k; }
+            }
+            __syncthreads();
+            cx<T> cr[4];                                              // C
+#pragma unroll
+            for (int m = 0; m < 4; ++m) cr[m] = colv[b][ty + 16 * m];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (live[c]) {
+                    const cx<T> rw = rowv[b][tx + 16 * c];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) cfms(a[m][c], cr[m], rw);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ty + 16 * m, j = tx + 16 * c;
+            if (i < n && j < n) Yb[kof[i] * n + rowof[j]] = a[m][c];
+        }
+    }
+    if (threadIdx.x == 0 && info) info[blockIdx.x] = singular;
+}
+
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s)
 {
     g_last_launches = 0;
@@ -284,6 +401,11 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     g_last_launches = 1;
     const int ld = 2 * order + 1;
     cudaError_t e;
+    if (order > 32 && !getenv("WIFI_INV_SMEM")) {               // register-resident Gauss-Jordan (WIFI_INV_SMEM=1: the shared-memory LU)
+        if (dt == WIFI_F32) cinverse_reg_kernel<float, 4><<<(unsigned)batch, INV_THREADS, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
+        else cinverse_reg_kernel<double, 2><<<(unsigned)batch, INV_THREADS, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
+        return cudaGetLastError();
+    }
     if (dt == WIFI_F32) {
         size_t smem = sizeof(float2) * ((size_t)order * ld + order);
         e = cudaFuncSetAttribute(cinverse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -32,3 +32,9 @@ for cdt in (torch.complex64, torch.complex128):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print("inverse %s n=53: |YA-I| %.2e | %.3f ms = %.3e matrices/s" % (str(cdt)[6:], err, ms, nb / ms * 1e3), flush=True)
+    for n in (33, 47, 53, 64):                                   # general (non-Hermitian) matrices: the pivot order is not the identity
+        G = torch.randn(256, n, n, dtype=cdt, device="cuda", generator=g)
+        Yg = ctx.inverse(G)
+        ref = torch.linalg.inv(G.to(torch.complex128))
+        print("inverse %s n=%d general: |YG-I| %.2e, rel. to torch.linalg.inv(f64) %.2e" % (str(cdt)[6:], n,
+              float((Yg @ G - torch.eye(n, dtype=cdt, device="cuda")).abs().max()), float((Yg.to(torch.complex128) - ref).abs().max() / ref.abs().max())), flush=True)
