@@ -3,7 +3,8 @@
 //   gj_solve            CTA-cooperative LU with partial pivoting + back-substitution on [A | B] held in shared
 //                       memory; the pivot arg-max is a warp-shuffle reduction.
 //   filter_form_kernel  W = R (R + diag d)^-1 in double-double, once per batch (main.c:183-201 intent).
-//   cinverse_kernel     batched inverse, one CTA per matrix (order <= 64).
+//   cinverse_reg_kernel batched inverse, orders 33..64: in-place Gauss-Jordan with implicit pivoting, the matrix in registers.
+//   cinverse_kernel     batched inverse, orders <= 32 (and WIFI_INV_SMEM=1): the shared-memory LU, one CTA per matrix.
 //   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
 #include "wifi_common.cuh"
@@ -292,6 +293,22 @@ __global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__re
 // per step; column / row / pivot row index are double-buffered on the parity of k.  The physical result holds A^-1 with
 // both index sets permuted: Y[kof[i]][rowof[j]] = a_ij, rowof[k] = pivot row of step k, kof = its inverse.  Padded rows and
 // columns (>= n) are zero and never chosen.
+// 1 / d from the hardware's approximate reciprocal refined by Newton steps, inline (the IEEE division is a ~30-instruction
+// subroutine call on the one-warp critical path of every step; measured: same throughput either way, the call-free form is
+// kept).  ~1 ulp; 0, denormal or infinite d give inf / NaN, which a singular (flagged) or out-of-range matrix produced before.
+__device__ __forceinline__ float pivot_rcp(float d)
+{
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(d));
+    return fmaf(x, fmaf(-d, x, 1.0f), x);
+}
+__device__ __forceinline__ double pivot_rcp(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    x = fma(x, fma(-d, x, 1.0), x);
+    return fma(x, fma(-d, x, 1.0), x);
+}
 __device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
 
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
                 for (int m = 0; m < 4; ++m) if (ty + 16 * m == bi) pivv = a[m][mc];      // (a runtime register index would put the tile in local memory)
                 __syncwarp(hmask);
                 const cx<T> piv = pivv;
-                const T den = cabs2(piv), rden = (T)1 / den;
+                const T den = cabs2(piv), rden = pivot_rcp(den);
                 const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
@@ -359,12 +376,12 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
                     if (m == mr) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const int j = tx + 16 * c;
-                            rowv[b][j] = (j == k) ? mk<T>((T)1, (T)0) : a[m][c];
+                            rowv[b][tx + 16 * c] = a[m][c];
                             a[m][c] = zero;
                         }
                     }
                 }
+                if (tx == kk) rowv[b][k] = mk<T>((T)1, (T)0);       // (phase A left 0 there; same thread, program order)
                 used |= 1u << mr;
                 if (tx == 0) { rowof[k] = r; kof[r] = k; }
             }

@@ -511,6 +511,24 @@ def test_inverse_53(ctx, wifi, gold, oracle):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [17, 32, 33, 47, 53, 64])
+def test_inverse_general_orders(ctx, oracle, prec, n):
+    """inverse() (utils.c:141-170) on general, non-Hermitian matrices whose large entries sit OFF the diagonal (a cyclic
+    shift plus noise: the pivot order is a non-trivial permutation), at the orders either side of the switch between the
+    shared-memory LU (<= 32) and the register-resident Gauss-Jordan kernel (33..64, partly filled 4 x 4 tiles at 33/47/53);
+    batch of 5 against the oracle's long-double pivoted inverse."""
+    rng = np.random.default_rng(1000 + n)
+    shift = np.roll(np.eye(n), 1 + n // 3, axis=1)
+    A = np.stack([3 * shift + (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n) for _ in range(5)]).astype(CDT[prec])
+    Y = host(ctx.inverse(dev(A)))
+    assert Y.shape == A.shape
+    for b in range(5):
+        a = A[b].astype(np.complex128)
+        assert rel_err(Y[b], oracle.inverse_gj(a), floor=1e-2) < (1e-11 if prec == "f64" else TOL["f32"])
+        assert np.abs(Y[b].astype(np.complex128) @ a - np.eye(n)).max() < (1e-12 if prec == "f64" else 2e-5)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("shape", [(17, 33, 9), (64, 64, 64), (5, 64, 64), (64, 3, 64), (53, 53, 1), (1, 53, 53), (40, 30, 50), (53, 53, 53)])
 def test_multiply_rectangular(ctx, oracle, prec, shape):
     """multiply() (utils.c:16-31) on shapes that exercise the zero-padded tile grid of the FP64 tensor-path kernel (rows not a
