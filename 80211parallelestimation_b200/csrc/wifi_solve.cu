@@ -312,8 +312,10 @@ __device__ __forceinline__ double pivot_rcp(double d)
 __device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
 
-template <typename T, int MINB>
-__global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
+// TC = tile columns per thread: 4 (256 threads, 16 x 16; the default) or 2 (512 threads, 16 x 32: half the registers, twice the
+// warps -- measured 15 % slower in FP64, selectable with WIFI_INV_TC2=1).
+template <typename T, int TC, int MINB>
+__global__ void __launch_bounds__(16 * (WIFI_MAX_ORDER / TC), MINB) cinverse_reg_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
 {
     __shared__ cx<T> colv[2][WIFI_MAX_ORDER], rowv[2][WIFI_MAX_ORDER];
     __shared__ cx<T> pivv;
@@ -322,27 +324,29 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
     const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
     const cx<T> *Ab = A + (int64_t)blockIdx.x * n * n;
     cx<T> *Yb = Y + (int64_t)blockIdx.x * n * n;
+    constexpr int NTX = WIFI_MAX_ORDER / TC;          // threads along a row; tile column c holds column tx + NTX c
     const cx<T> zero = mk<T>((T)0, (T)0);
-    cx<T> a[4][4];
+    cx<T> a[4][TC];
     unsigned used = 0;           // bit m: row ty + 16 m has been a pivot row (or is padding)
-    bool live[4];                // tile column c holds real columns
+    bool live[TC];               // tile column c holds real columns
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         if (ty + 16 * m >= n) used |= 1u << m;
-        live[m] = tx + 16 * m < n;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = ty + 16 * m, j = tx + 16 * c;
+        for (int c = 0; c < TC; ++c) {
+            const int i = ty + 16 * m, j = tx + NTX * c;
             a[m][c] = (i < n && j < n) ? Ab[i * n + j] : zero;
         }
     }
+#pragma unroll
+    for (int c = 0; c < TC; ++c) live[c] = tx + NTX * c < n;
     if (threadIdx.x < WIFI_MAX_ORDER) { rowof[threadIdx.x] = threadIdx.x; kof[threadIdx.x] = threadIdx.x; }
     int singular = 0;
 #pragma unroll
-    for (int mc = 0; mc < 4; ++mc) {
+    for (int mc = 0; mc < TC; ++mc) {
 #pragma unroll 1
-        for (int kk = 0; kk < 16; ++kk) {
-            const int k = 16 * mc + kk, b = k & 1;
+        for (int kk = 0; kk < NTX; ++kk) {
+            const int k = NTX * mc + kk, b = k & 1;
             if (k >= n) break;
             if (tx == kk) {                                           // A: one half-warp, the owners of column k
                 unsigned key = 0;
@@ -375,8 +379,8 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
                 for (int m = 0; m < 4; ++m) {
                     if (m == mr) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            rowv[b][tx + 16 * c] = a[m][c];
+                        for (int c = 0; c < TC; ++c) {
+                            rowv[b][tx + NTX * c] = a[m][c];
                             a[m][c] = zero;
                         }
                     }
@@ -390,9 +394,9 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
 #pragma unroll
             for (int m = 0; m < 4; ++m) cr[m] = colv[b][ty + 16 * m];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < TC; ++c) {
                 if (live[c]) {
-                    const cx<T> rw = rowv[b][tx + 16 * c];
+                    const cx<T> rw = rowv[b][tx + NTX * c];
 #pragma unroll
                     for (int m = 0; m < 4; ++m) cfms(a[m][c], cr[m], rw);
                 }
@@ -403,8 +407,8 @@ __global__ void __launch_bounds__(INV_THREADS, MINB) cinverse_reg_kernel(const c
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = ty + 16 * m, j = tx + 16 * c;
+        for (int c = 0; c < TC; ++c) {
+            const int i = ty + 16 * m, j = tx + NTX * c;
             if (i < n && j < n) Yb[kof[i] * n + rowof[j]] = a[m][c];
         }
     }
@@ -419,8 +423,9 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     const int ld = 2 * order + 1;
     cudaError_t e;
     if (order > 32 && !getenv("WIFI_INV_SMEM")) {               // register-resident Gauss-Jordan (WIFI_INV_SMEM=1: the shared-memory LU)
-        if (dt == WIFI_F32) cinverse_reg_kernel<float, 4><<<(unsigned)batch, INV_THREADS, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
-        else cinverse_reg_kernel<double, 2><<<(unsigned)batch, INV_THREADS, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
+        if (dt == WIFI_F32) cinverse_reg_kernel<float, 4, 4><<<(unsigned)batch, 256, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
+        else if (getenv("WIFI_INV_TC2")) cinverse_reg_kernel<double, 2, 2><<<(unsigned)batch, 512, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
+        else cinverse_reg_kernel<double, 4, 2><<<(unsigned)batch, 256, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
         return cudaGetLastError();
     }
     if (dt == WIFI_F32) {
