@@ -281,14 +281,14 @@ __global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__re
 
 // Register-resident batched inverse for 32 < n <= 64: in-place Gauss-Jordan with implicit partial pivoting.
 // Every step of the in-place form updates the WHOLE n x n matrix (the right half of [A | I] moves into the columns the left
-// half vacates), so a thread can own a fixed 4 x 4 tile in registers for all n steps: no shrinking window, no row swaps.
-// Thread layout: tile row i = ty + 16 m, tile column j = tx + 16 mc; a warp holds all 16 ty of two adjacent tx, so the owners
+// half vacates), so a thread can own a fixed 4 x TC tile in registers for all n steps: no shrinking window, no row swaps.
+// Thread layout (NTX = 64 / TC threads along a row): tile row i = ty + 16 m, tile column j = tx + NTX c; a warp holds all 16 ty of two adjacent tx, so the owners
 // of a column are one half-warp.  Step k (pivot row r, pivot p):
 //   A. the half-warp that owns column k picks r among the rows not used yet -- ONE redux.sync max over a 32-bit key (the top
 //      26 bits of |a|^2, then 63 - row so that ties go to the lowest row) --, gets p from its owner, publishes the scaled
 //      column c_i = a_ik / p (c_r = -1 / p) and clears its column;
 //   B. the 16 threads that own row r publish it as it is (entry k := 1) and clear it;
-//   C. every thread does a_ij -= c_i row_j on its tile: 8 shared loads for 16 complex FMAs.
+//   C. every thread does a_ij -= c_i row_j on its tile: 4 + TC shared loads for 4 TC complex FMAs.
 // This leaves a_rj / p in row r, 1 / p at (r, k) and -a_ik / p in column k: the in-place Gauss-Jordan step.  Two barriers
 // per step; column / row / pivot row index are double-buffered on the parity of k.  The physical result holds A^-1 with
 // both index sets permuted: Y[kof[i]][rowof[j]] = a_ij, rowof[k] = pivot row of step k, kof = its inverse.  Padded rows and
@@ -312,8 +312,8 @@ __device__ __forceinline__ double pivot_rcp(double d)
 __device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
 
-// TC = tile columns per thread: 4 (256 threads, 16 x 16; the default) or 2 (512 threads, 16 x 32: half the registers, twice the
-// warps -- measured 15 % slower in FP64, selectable with WIFI_INV_TC2=1).
+// TC = tile columns per thread: 8 (128 threads, 16 x 8: the FP32 default), 4 (256 threads, 16 x 16: the FP64 default) or 2 (512
+// threads, 16 x 32: half the registers, twice the warps -- measured 15 % slower in FP64, selectable with WIFI_INV_TC2=1).
 template <typename T, int TC, int MINB>
 __global__ void __launch_bounds__(16 * (WIFI_MAX_ORDER / TC), MINB) cinverse_reg_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
 {
@@ -423,7 +423,9 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     const int ld = 2 * order + 1;
     cudaError_t e;
     if (order > 32 && !getenv("WIFI_INV_SMEM")) {               // register-resident Gauss-Jordan (WIFI_INV_SMEM=1: the shared-memory LU)
-        if (dt == WIFI_F32) cinverse_reg_kernel<float, 4, 4><<<(unsigned)batch, 256, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
+        // FP32: 4 x 8 tiles, 128 threads, 96 registers, 5 CTAs/SM (9.4 M matrices/s; 4 x 4 tiles with 256 threads, WIFI_INV_TC4=1: 9.0 M)
+        if (dt == WIFI_F32 && !getenv("WIFI_INV_TC4")) cinverse_reg_kernel<float, 8, 5><<<(unsigned)batch, 128, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
+        else if (dt == WIFI_F32) cinverse_reg_kernel<float, 4, 4><<<(unsigned)batch, 256, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
         else if (getenv("WIFI_INV_TC2")) cinverse_reg_kernel<double, 2, 2><<<(unsigned)batch, 512, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
         else cinverse_reg_kernel<double, 4, 2><<<(unsigned)batch, 256, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
         return cudaGetLastError();

@@ -163,7 +163,8 @@ int wifi_couter_batch(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int 
                       void *res, int64_t batch);
 /* identity utils.c:84-93 */
 int wifi_cidentity_batch(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch);
-/* inverse utils.c:141-170 replaced by partial-pivoting Gauss-Jordan; info[b] (device int, may be NULL) = 1 if singular */
+/* inverse utils.c:141-170 replaced by elimination with partial pivoting (in-place Gauss-Jordan in registers for orders 33..64,
+   LU + back-substitution in shared memory below); info[b] (device int, may be NULL) = 1 if singular */
 int wifi_cinverse_batch(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info);
 
 /* ---- synthetic frames of the inputs.h shape, generated on the device ---- */
