@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "80211parallelestimation_b200", "libwifi_b200.so")
-KEEP = ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "DMMA", "FFMA", "DFMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "MUFU")
+KEEP = ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "DMMA", "FFMA", "DFMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "MUFU", "CREDUX", "REDUX", "LDL", "STL")
 
 HEADER = """SASS evidence (cuobjdump -sass libwifi_b200.so, sm_100a): per kernel, counts of the mnemonics that show which hardware path it uses.
 UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st (tensor memory), UBLKCP = cp.async.bulk (TMA bulk copy), UBLKPF = cp.async.bulk.prefetch.L2,
