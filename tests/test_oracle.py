@@ -158,3 +158,45 @@ def test_reference_mmse_as_written_is_nan_documented():
     assert np.array_equal(ryy, 2 * o.identity(6, 9.6172e-08))
     inv = o.inverse_cofactor(ryy)
     assert np.isnan(inv).any()
+
+
+def _inplace_gauss_jordan(A):
+    """numpy restatement of cinverse_reg_kernel (csrc/wifi_solve.cu): in-place Gauss-Jordan with IMPLICIT partial pivoting --
+    no row is ever moved; step k picks its pivot row r among the rows not used yet with the kernel's 32-bit key (|a|^2 as
+    float32 bits with the low 6 bits dropped, then 63 - row so that ties go to the lowest row), scales the column by 1/pivot
+    (c_r = -1/pivot), publishes row r with entry k := 1, clears both and updates every entry; the result is un-permuted on
+    the way out, Y[kof[i]][rowof[j]] = a[i][j]."""
+    a = np.array(A, np.complex128)
+    n = a.shape[0]
+    used = np.zeros(n, bool)
+    rowof, kof = np.zeros(n, int), np.zeros(n, int)
+    for k in range(n):
+        v = (np.abs(a[:, k]) ** 2).astype(np.float32).view(np.uint32).astype(np.int64)
+        key = np.where(used, -1, ((v & 0x7FFFFFC0) | (63 - np.arange(n))))
+        r = int(np.argmax(key))
+        inv = 1.0 / a[r, k]
+        c = a[:, k] * inv
+        c[r] = -inv
+        row = a[r, :].copy()
+        row[k] = 1.0
+        a[:, k] = 0
+        a[r, :] = 0
+        a -= np.outer(c, row)
+        used[r] = True
+        rowof[k], kof[r] = r, k
+    Y = np.empty_like(a)
+    Y[np.ix_(kof, rowof)] = a
+    return Y, rowof
+
+
+@pytest.mark.parametrize("n", [33, 53, 64])
+def test_inplace_gauss_jordan_restatement(oracle, n):
+    """The algorithm of the register-resident batched inverse (the replacement of utils.c:141-170 for orders 33..64), restated
+    on the CPU, against the oracle's long-double pivoted inverse: pins the implicit-pivoting bookkeeping (rowof / kof) and the
+    quantised pivot key on matrices whose pivot order is a non-trivial permutation."""
+    rng = np.random.default_rng(n)
+    A = 3 * np.roll(np.eye(n), 1 + n // 3, axis=1) + (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) / np.sqrt(n)
+    Y, rowof = _inplace_gauss_jordan(A)
+    assert sorted(rowof) == list(range(n)) and not np.array_equal(rowof, np.arange(n))
+    assert rel_err(Y, oracle.inverse_gj(A), floor=1e-2) < 1e-12
+    assert np.abs(Y @ A - np.eye(n)).max() < 1e-13
