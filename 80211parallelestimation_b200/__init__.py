@@ -7,7 +7,7 @@ All compute happens in hand-written sm_100a CUDA kernels in libwifi_b200.so (C-A
 PyTorch is only used for device memory / streams by callers that pass CUDA tensors.
 """
 from . import _lib
-from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, AS_WRITTEN, INTENDED)
+from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, SOLVE_FAST32, AS_WRITTEN, INTENDED)
 from .api import (WifiContext, WifiError, default_context,
                   WiFi_channel_estimation_LT_LS, WiFi_channel_estimation_PS_Linear, WiFi_channel_estimation_PS_Cubic,
                   WiFi_channel_estimation_PS_Sinc, WiFi_channel_estimation_PS_MMSE, WiFi_Equalization,

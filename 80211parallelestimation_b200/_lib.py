@@ -10,6 +10,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_SINGULAR, ERR_NO_DEVICE, ERR_STATE = r
 PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB = 1, 2, 4, 8
 SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE = 0, 1, 2
 SOLVE_WIDE = SOLVE_REFINE
+SOLVE_FAST32 = 4
 AS_WRITTEN, INTENDED = 0, 1
 
 _vp, _i, _i64, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint64
@@ -33,6 +34,8 @@ SIGNATURES = {
     "wifi_mmse_filter_set": [_vp, _vp],
     "wifi_mmse_shared_apply_batch": [_vp, _i, _vp, _vp, _i64],
     "wifi_mmse_shared_batch": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
+    "wifi_mmse_filter_fold_tx": [_vp, _vp],
+    "wifi_mmse_shared_rx_batch": [_vp, _i, _vp, _i64, _vp, _i64],
     "wifi_mmse_perframe_batch": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
     "wifi_mmse_eig_prepare": [_vp, _vp, _vp],
     "wifi_mmse_perframe_eig_batch": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
@@ -54,6 +57,9 @@ SIGNATURES = {
     "wifi_frontend_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_filter_form_host": [_vp, _vp, _vp, _vp],
     "wifi_mmse_shared_host": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
+    "wifi_mmse_filter_fold_tx_host": [_vp, _vp],
+    "wifi_mmse_shared_rx_host": [_vp, _i, _vp, _i64, _vp, _i64],
+    "wifi_pcie_probe": [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_d)],
     "wifi_mmse_perframe_host": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
     "wifi_mmse_perframe_eig_host": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
@@ -64,6 +70,7 @@ SIGNATURES = {
     "wifi_couter_host": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
     "wifi_cidentity_host": [_vp, _i, _vp, _i, _d, _i64],
     "wifi_cinverse_host": [_vp, _i, _vp, _i, _vp, _i64, _vp],
+    "wifi_set_host_chunk_bytes": [_vp, C.c_size_t],
     "wifi_host_alloc": [C.POINTER(_vp), C.c_size_t],
     "wifi_host_free": [_vp],
     "wifi_default_ctx": [],

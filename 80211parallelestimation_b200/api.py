@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, AS_WRITTEN, INTENDED)
+from ._lib import (F32, F64, PS_LINEAR, PS_CUBIC, PS_SINC, PS_MATLAB, SOLVE_PIVOT, SOLVE_HPD, SOLVE_REFINE, SOLVE_WIDE, SOLVE_FAST32, AS_WRITTEN, INTENDED)
 
 NSC, NBLK, FRAME = 53, 15, 795
 
@@ -114,6 +114,10 @@ class WifiContext:
         if device_call:
             import torch
             self.lib.wifi_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+
+    def set_host_chunk_bytes(self, nbytes):
+        """Per-array staging target of one chunk of the host-pointer pipeline (default 48 MiB)."""
+        self._ck(self.lib.wifi_set_host_chunk_bytes(self.h, int(nbytes)))
 
     def synchronize(self):
         self._ck(self.lib.wifi_synchronize(self.h))
@@ -241,8 +245,38 @@ class WifiContext:
         self._ck(fn(self.h, dt, tx.ptr, rx.ptr, frame_stride, _ptr(H), n_frames))
         return H
 
+    def mmse_filter_fold_tx(self, tx_block):
+        """Shared, known tx block vector [53]: fold rx/tx into the installed filter (W' = W diag(1/tx)) for mmse_shared_rx."""
+        if _is_torch(tx_block):
+            import torch
+            t = tx_block.to(torch.complex128).contiguous()
+            self._sync_stream(True)
+            self._ck(self.lib.wifi_mmse_filter_fold_tx(self.h, t.data_ptr()))
+        else:
+            t = np.ascontiguousarray(np.asarray(tx_block, np.complex128))
+            self._ck(self.lib.wifi_mmse_filter_fold_tx_host(self.h, t.ctypes.data))
+
+    def mmse_shared_rx(self, rx_symbols, frame_stride=NSC, n_frames=None, out=None):
+        """Shared-filter PS_MMSE for frames that share their (known) tx block vector: H = rx W'^T, only rx is read."""
+        rx = _Arg(rx_symbols)
+        if n_frames is None:
+            n_frames = rx.size // frame_stride
+        H = out if out is not None else rx.empty_like((n_frames, NSC))
+        self._sync_stream(rx.device)
+        fn = self.lib.wifi_mmse_shared_rx_batch if rx.device else self.lib.wifi_mmse_shared_rx_host
+        self._ck(fn(self.h, rx.dt, rx.ptr, frame_stride, _ptr(H), n_frames))
+        return H
+
+    def pcie_probe(self, h_src, h_dst):
+        """Wall time (ms) of one pinned H2D copy of h_src and one D2H copy into h_dst issued together (either may be None)."""
+        ms = C.c_double()
+        self._ck(self.lib.wifi_pcie_probe(self.h, _ptr(h_src), _ptr(h_dst), h_src.nbytes if h_src is not None else 0,
+                                          h_dst.nbytes if h_dst is not None else 0, C.byref(ms)))
+        return ms.value
+
     def mmse_perframe(self, R, tx_symbols, rx_symbols, sigma2, frame_stride=NSC, n_frames=None, flags=SOLVE_HPD, out=None):
-        """Per-frame PS_MMSE: A_f = R + diag(sigma2_f/|tx|^2), A_f z = rx/tx, H = R z."""
+        """Per-frame PS_MMSE: A_f = R + diag(sigma2_f/|tx|^2), A_f z = rx/tx, H = R z.  complex64 arrays are solved in FP64
+        arithmetic (1e-4-accurate); SOLVE_FAST32 opts into FP32 arithmetic (~4e-3 with SOLVE_HPD, ~1e-1 with SOLVE_PIVOT)."""
         r, tx, rx = _Arg(R), _Arg(tx_symbols), _Arg(rx_symbols)
         dev, dt = _same(r, tx, rx)
         if n_frames is None:

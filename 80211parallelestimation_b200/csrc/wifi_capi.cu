@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <mutex>
@@ -22,6 +23,7 @@ struct wifi_ctx {
     cudaStream_t stream;
     InterpTables tab;
     FilterImages img;
+    FilterImages img_rx;     // W diag(1/tx) for a shared, known tx block vector (wifi_mmse_filter_fold_tx): applied to rx directly
     FilterImages eig[2];     // eigen-domain per-frame MMSE: G = V^H M^-1/2 and G2 = M^1/2 V as shared-filter operands
     double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc; double eig_Rdd, eig_md;
     void *eig_u[2]; size_t eig_u_bytes[2];   // [n][53] scratch between the two products, one per pipeline stream (the two
@@ -31,7 +33,6 @@ struct wifi_ctx {
     char err[512];
     int64_t launches;
     int timing;
-    int force_simt;
     cudaEvent_t ev0, ev1;
     int ev_valid;
     // host-pointer pipeline
@@ -39,6 +40,7 @@ struct wifi_ctx {
     void *stage[2];
     size_t stage_bytes[2];
     cudaEvent_t hev[2];
+    size_t chunk_bytes;      // per-array staging target per chunk of the *_host pipeline (wifi_set_host_chunk_bytes)
 };
 
 static size_t esize(wifi_dtype dt) { return dt == WIFI_F32 ? sizeof(float2) : sizeof(double2); }
@@ -111,11 +113,11 @@ static bool alloc_images(FilterImages &im)
 {
     const size_t nW = (size_t)WIFI_NSC * WIFI_NSC;
     im.valid = 0;
-    return cudaMalloc(&im.W64, nW * sizeof(double2)) == cudaSuccess && cudaMalloc(&im.W32, nW * sizeof(float2)) == cudaSuccess &&
+    return cudaMalloc(&im.W64, nW * sizeof(double2)) == cudaSuccess &&
            cudaMalloc(&im.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess && cudaMalloc(&im.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
            cudaMalloc(&im.B64, 112 * WIFI_DMMA_BS * sizeof(double)) == cudaSuccess;
 }
-static void free_images(FilterImages &im) { cudaFree(im.W64); cudaFree(im.W32); cudaFree(im.Bhi); cudaFree(im.Blo); cudaFree(im.B64); }
+static void free_images(FilterImages &im) { cudaFree(im.W64); cudaFree(im.Bhi); cudaFree(im.Blo); cudaFree(im.B64); }
 
 extern "C" {
 
@@ -131,29 +133,16 @@ int wifi_create(int device, wifi_ctx **out)
     wifi_ctx *ctx = (wifi_ctx *)calloc(1, sizeof(wifi_ctx));
     if (!ctx) return WIFI_ERR_NOMEM;
     ctx->device = device;
-    { const char *g = getenv("WIFI_B200_GEMM"); ctx->force_simt = (g && strcmp(g, "simt") == 0); }
+    ctx->chunk_bytes = (size_t)48 << 20;   // 1 Mi frames e2e: 18.2 ms at 48 MB, 18.9 at 16, 22.4 at 4 (the pass is H2D-bound)
     if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return WIFI_ERR_CUDA; }
-    {
-        // The pilot gather of the PS estimators touches 8 isolated complex values per frame; with the default L2 fetch
-        // granularity every one of them drags a 128-byte line out of HBM (measured 929 B/frame instead of 256).
-        const char *g = getenv("WIFI_B200_L2FETCH");
-        int gran = g ? atoi(g) : 32;
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
-    }
     double w[4 * WIFI_NSC * 4];
     float wf[4 * WIFI_NSC * 4];
     build_tables(w);
     for (int i = 0; i < 4 * WIFI_NSC * 4; ++i) wf[i] = (float)w[i];
-    const size_t nW = (size_t)WIFI_NSC * WIFI_NSC;
     bool ok = cudaMalloc(&ctx->tab.w64, sizeof(w)) == cudaSuccess && cudaMalloc(&ctx->tab.w32, sizeof(wf)) == cudaSuccess &&
               cudaMemcpy(ctx->tab.w64, w, sizeof(w), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(ctx->tab.w32, wf, sizeof(wf), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMalloc(&ctx->img.W64, nW * sizeof(double2)) == cudaSuccess &&
-              cudaMalloc(&ctx->img.W32, nW * sizeof(float2)) == cudaSuccess &&
-              cudaMalloc(&ctx->img.Bhi, 112 * 112 * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&ctx->img.Blo, 112 * 112 * sizeof(float)) == cudaSuccess &&
-              cudaMalloc(&ctx->img.B64, 112 * WIFI_DMMA_BS * sizeof(double)) == cudaSuccess &&
-              alloc_images(ctx->eig[0]) && alloc_images(ctx->eig[1]) &&
+              alloc_images(ctx->img) && alloc_images(ctx->img_rx) && alloc_images(ctx->eig[0]) && alloc_images(ctx->eig[1]) &&
               cudaMalloc(&ctx->eig_lam, 64 * sizeof(double)) == cudaSuccess && cudaMalloc(&ctx->eig_p, 64 * sizeof(double2)) == cudaSuccess &&
               cudaMalloc(&ctx->eig_scal, 4 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
@@ -174,8 +163,7 @@ int wifi_destroy(wifi_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->tab.w64); cudaFree(ctx->tab.w32);
-    cudaFree(ctx->img.W64); cudaFree(ctx->img.W32); cudaFree(ctx->img.Bhi); cudaFree(ctx->img.Blo); cudaFree(ctx->img.B64);
-    free_images(ctx->eig[0]); free_images(ctx->eig[1]);
+    free_images(ctx->img); free_images(ctx->img_rx); free_images(ctx->eig[0]); free_images(ctx->eig[1]);
     cudaFree(ctx->eig_lam); cudaFree(ctx->eig_p); cudaFree(ctx->eig_scal); cudaFree(ctx->eig_u[0]); cudaFree(ctx->eig_u[1]);
     cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -249,10 +237,9 @@ int wifi_frontend_batch(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const 
 // ---- MMSE ---------------------------------------------------------------------------------------
 static int install_images(wifi_ctx *ctx, FilterImages &im, cudaStream_t s)
 {
-    CK(launch_filter_install_simt(im, s));
     CK(launch_filter_install_tc(im, s));
     CK(launch_filter_install_dmma(im, s));
-    ctx->launches += 3;
+    ctx->launches += 2;
     im.valid = 1;
     return WIFI_OK;
 }
@@ -288,8 +275,8 @@ static int gemm_with(wifi_ctx *ctx, const FilterImages &im, wifi_dtype dt, const
                      int64_t n, cudaStream_t s)
 {
     Timed t(ctx, s);
-    if (ctx->force_simt) CK(launch_mmse_shared_simt(dt, im, a, rx, frame_stride, H, n, s));
-    else if (dt == WIFI_F32) CK(launch_mmse_shared_tc(im, a, rx, frame_stride, H, n, s));
+    // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: DMMA (tcgen05 has no FP64 kind)
+    if (dt == WIFI_F32) CK(launch_mmse_shared_tc(im, a, rx, frame_stride, H, n, s));
     else CK(launch_mmse_shared_dmma(im, a, rx, frame_stride, H, n, s));
     return WIFI_OK;
 }
@@ -310,23 +297,14 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
     void *U = ctx->eig_u[slot];
     int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, U, n, s);            // u = (rx/tx) G^T
     if (rc) return rc;
-    if (dt == WIFI_F32 && !ctx->force_simt) {
-        // one kernel: v = s (.) (u - p z_d) in the converter stage, c = v G2^T on tcgen05, H = rx/tx - c in the epilogue
-        Timed t(ctx, s);
+    // one kernel: v = s (.) (u - p z_d) in the converter / producer stage, c = v G2^T on the tensor cores, H = rx/tx - c in the epilogue
+    Timed t(ctx, s);
+    if (dt == WIFI_F32)
         CK(launch_mmse_shared_tc_resid(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p,
                                        ctx->eig_Rdd, ctx->eig_md, H, n, s));
-        return WIFI_OK;
-    }
-    if (dt == WIFI_F64 && !ctx->force_simt) {
-        Timed t(ctx, s);
+    else
         CK(launch_mmse_shared_dmma_eig(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd,
                                        ctx->eig_md, H, n, s));
-        return WIFI_OK;
-    }
-    { Timed t(ctx, s); CK(launch_eig_mid(dt, U, tx, rx, frame_stride, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_scal, n, s)); }
-    rc = gemm_with(ctx, ctx->eig[1], dt, U, nullptr, WIFI_NSC, H, n, s);               // c = v G2^T
-    if (rc) return rc;
-    { Timed t(ctx, s); CK(launch_eig_fin(dt, H, U, tx, rx, frame_stride, ctx->eig_scal, n, s)); }
     return WIFI_OK;
 }
 
@@ -334,13 +312,29 @@ static int mmse_shared(wifi_ctx *ctx, wifi_dtype dt, const void *a, const void *
                        cudaStream_t s)
 {
     if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
-    Timed t(ctx, s);
-    // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: DMMA (tcgen05 has no FP64 kind).
-    // WIFI_B200_GEMM=simt selects the CUDA-core kernels for A/B measurements (all are sm_100a kernels).
-    if (ctx->force_simt) CK(launch_mmse_shared_simt(dt, ctx->img, a, rx, frame_stride, H, n, s));
-    else if (dt == WIFI_F32) CK(launch_mmse_shared_tc(ctx->img, a, rx, frame_stride, H, n, s));
-    else CK(launch_mmse_shared_dmma(ctx->img, a, rx, frame_stride, H, n, s));
-    return WIFI_OK;
+    return gemm_with(ctx, ctx->img, dt, a, rx, frame_stride, H, n, s);
+}
+
+// Shared, known tx block vector (training symbols): rx/tx = diag(1/tx) rx, so the divide folds into the filter once,
+// W' = W diag(1/tx), and the per-frame work is the plain product H = rx W'^T -- 848 instead of 1 272 bytes per frame (FP32).
+int wifi_mmse_filter_fold_tx(wifi_ctx *ctx, const void *tx_block_f64)
+{
+    ENTER();
+    NEED(tx_block_f64);
+    if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
+    {
+        Timed t(ctx, ctx->stream);
+        CK(launch_filter_fold(ctx->img.W64, tx_block_f64, ctx->img_rx.W64, ctx->stream));
+    }
+    return install_images(ctx, ctx->img_rx, ctx->stream);
+}
+
+int wifi_mmse_shared_rx_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx, int64_t frame_stride, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    if (!ctx->img_rx.valid) return fail(ctx, WIFI_ERR_STATE, "no tx-folded filter installed: call wifi_mmse_filter_fold_tx first");
+    return gemm_with(ctx, ctx->img_rx, dt, rx, nullptr, frame_stride, H, n, ctx->stream);
 }
 
 int wifi_mmse_shared_apply_batch(wifi_ctx *ctx, wifi_dtype dt, const void *H_ls, void *H, int64_t n)
@@ -360,13 +354,10 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                          const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check);
 
-// R_f = H_ls H_ls^H: closed form (wifi_ls.cu mmse_rank1_kernel); WIFI_B200_CCONV=solve keeps the general pivoted solve of
-// R_f + D for A/B checks (C convention only)
+// R_f = H_ls H_ls^H: closed form (wifi_ls.cu mmse_rank1_kernel)
 static int mmse_cconv(wifi_ctx *ctx, wifi_dtype dt, int matlab, const void *tx, const void *rx, int64_t frame_stride, const void *ow2,
                       const void *hls, void *H, int64_t n, cudaStream_t s)
 {
-    static const int use_solve = [] { const char *e = getenv("WIFI_B200_CCONV"); return e && !strcmp(e, "solve"); }();
-    if (use_solve && !matlab) return mmse_perframe(ctx, dt, nullptr, tx, rx, frame_stride, ow2, hls, H, n, WIFI_SOLVE_PIVOT, s, false);
     Timed t(ctx, s);
     CK(launch_mmse_rank1(dt, matlab, tx, rx, frame_stride, ow2, hls, H, n, s));
     return WIFI_OK;
@@ -409,10 +400,11 @@ static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void
     if (check) CK(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s));
     {
         Timed t(ctx, s);
+        const int fast32 = (flags & WIFI_SOLVE_FAST32) ? 1 : 0;      // FP32 arithmetic is an explicit opt-in (4e-3 / 1e-1 accuracy)
         if ((flags & WIFI_SOLVE_HPD) && !hls)
-            CK(launch_mmse_perframe_hpd(dt, R, tx, rx, frame_stride, sigma2, H, n, (flags & WIFI_SOLVE_WIDE) ? 1 : 0, s));
+            CK(launch_mmse_perframe_hpd(dt, R, tx, rx, frame_stride, sigma2, H, n, fast32, s));
         else
-            CK(launch_mmse_perframe_pivot(dt, R, tx, rx, frame_stride, sigma2, hls, H, n, check ? ctx->d_info : nullptr, s));
+            CK(launch_mmse_perframe_pivot(dt, R, tx, rx, frame_stride, sigma2, hls, H, n, check ? ctx->d_info : nullptr, fast32, s));
     }
     return WIFI_OK;
 }
@@ -543,6 +535,12 @@ int wifi_measure_peak(wifi_ctx *ctx, int which, double *value)
 }
 
 // ---- host-pointer pipeline ------------------------------------------------------------------------------
+int wifi_set_host_chunk_bytes(wifi_ctx *ctx, size_t bytes)
+{
+    if (!ctx || bytes < 4096) return WIFI_ERR_INVALID;
+    ctx->chunk_bytes = bytes;
+    return WIFI_OK;
+}
 int wifi_host_alloc(void **p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? WIFI_OK : WIFI_ERR_NOMEM; }
 int wifi_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? WIFI_OK : WIFI_ERR_CUDA; }
 
@@ -558,12 +556,6 @@ struct Arr {
     size_t pitch_bytes;  // host distance between consecutive frames
 };
 
-static size_t chunk_bytes()
-{
-    static const size_t v = [] { const char *e = getenv("WIFI_B200_HOST_CHUNK_MB"); long mb = e ? atol(e) : 48; return (size_t)(mb > 0 ? mb : 48) << 20; }();
-    return v;
-}
-#define CHUNK_BYTES chunk_bytes()   // per-array staging target per chunk (WIFI_B200_HOST_CHUNK_MB, default 48: 1 Mi frames e2e 18.2 ms at 48 MB, 18.9 at 16, 22.4 at 4 -- the pass is H2D-bound at ~49 GB/s)
 
 // Runs `body(dev_ptrs, n_chunk, stream)` over chunks of frames; arrays are staged compactly (pitch = row_bytes).
 template <typename Body>
@@ -572,7 +564,7 @@ int host_pipeline(wifi_ctx *ctx, int64_t n_frames, const std::vector<Arr> &arrs,
     if (n_frames == 0) return WIFI_OK;
     size_t max_row = 1, sum_row = 0;
     for (auto &a : arrs) { max_row = std::max(max_row, a.row_bytes); sum_row += (a.row_bytes + 255) / 256 * 256; }
-    int64_t chunk = std::max<int64_t>(1, (int64_t)(CHUNK_BYTES / max_row));
+    int64_t chunk = std::max<int64_t>(1, (int64_t)(ctx->chunk_bytes / max_row));
     chunk = std::min(chunk, n_frames);
     if (chunk > 1 && (chunk & 1)) --chunk;                      // keep 16-byte alignment of [n][53] float2 chunks
     std::vector<size_t> off(arrs.size());
@@ -628,6 +620,14 @@ Arr out_arr(void *p, size_t row) { return Arr{nullptr, p, row, row}; }
 }  // namespace
 
 extern "C" {
+
+// small utils: one shot through the ctx stream
+#define UTIL_STAGE(total_bytes)                                                   \
+    if (ctx->stage_bytes[0] < (total_bytes)) {                                    \
+        cudaFree(ctx->stage[0]); ctx->stage[0] = nullptr; ctx->stage_bytes[0] = 0; \
+        CK(cudaMalloc(&ctx->stage[0], (total_bytes)));                            \
+        ctx->stage_bytes[0] = (total_bytes);                                      \
+    }
 
 int wifi_lt_ls_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, void *H, int64_t n)
 {
@@ -727,6 +727,53 @@ int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const vo
                          });
 }
 
+int wifi_mmse_filter_fold_tx_host(wifi_ctx *ctx, const void *tx_block_f64)
+{
+    ENTER();
+    NEED(tx_block_f64);
+    const size_t nb = sizeof(double2) * WIFI_NSC;
+    UTIL_STAGE(nb);
+    CK(cudaMemcpyAsync(ctx->stage[0], tx_block_f64, nb, cudaMemcpyHostToDevice, ctx->stream));
+    return wifi_mmse_filter_fold_tx(ctx, ctx->stage[0]);
+}
+
+int wifi_mmse_shared_rx_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx, int64_t frame_stride, void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    if (!ctx->img_rx.valid) return fail(ctx, WIFI_ERR_STATE, "no tx-folded filter installed: call wifi_mmse_filter_fold_tx first");
+    CK(cudaStreamSynchronize(ctx->stream));   // the filter images were built on the ctx stream
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(rx, row, pitch), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return gemm_with(ctx, ctx->img_rx, dt, d[0], nullptr, WIFI_NSC, d[1], nc, s);
+                         });
+}
+
+// PCIe ceiling of this GPU under the same conditions as the *_host pipeline: one H2D copy of h2d_bytes and one D2H copy of
+// d2h_bytes, pinned host buffers, issued together on the pipeline's two streams; *ms = host wall time until both are done.
+int wifi_pcie_probe(wifi_ctx *ctx, const void *h_src, void *h_dst, size_t h2d_bytes, size_t d2h_bytes, double *ms)
+{
+    ENTER();
+    NEED(ms && (h2d_bytes == 0 || h_src) && (d2h_bytes == 0 || h_dst));
+    const size_t need[2] = {h2d_bytes, d2h_bytes};
+    for (int b = 0; b < 2; ++b)
+        if (ctx->stage_bytes[b] < need[b]) {
+            cudaFree(ctx->stage[b]); ctx->stage[b] = nullptr; ctx->stage_bytes[b] = 0;
+            if (cudaMalloc(&ctx->stage[b], need[b]) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "probe cudaMalloc(%zu) failed", need[b]);
+            ctx->stage_bytes[b] = need[b];
+        }
+    CK(cudaStreamSynchronize(ctx->hstream[0])); CK(cudaStreamSynchronize(ctx->hstream[1]));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (h2d_bytes) CK(cudaMemcpyAsync(ctx->stage[0], h_src, h2d_bytes, cudaMemcpyHostToDevice, ctx->hstream[0]));
+    if (d2h_bytes) CK(cudaMemcpyAsync(h_dst, ctx->stage[1], d2h_bytes, cudaMemcpyDeviceToHost, ctx->hstream[1]));
+    CK(cudaStreamSynchronize(ctx->hstream[0])); CK(cudaStreamSynchronize(ctx->hstream[1]));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *ms = 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec);
+    return WIFI_OK;
+}
+
 int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                             const void *sigma2, void *H, int64_t n, int flags)
 {
@@ -781,14 +828,6 @@ int wifi_mmse_matlab_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, c
                              return mmse_cconv(ctx, dt, 1, d[0], d[1], 4 * WIFI_NSC, d[2], d[3], d[4], nc, s);
                          });
 }
-
-// small utils: one shot through the ctx stream
-#define UTIL_STAGE(total_bytes)                                                   \
-    if (ctx->stage_bytes[0] < (total_bytes)) {                                    \
-        cudaFree(ctx->stage[0]); ctx->stage[0] = nullptr; ctx->stage_bytes[0] = 0; \
-        CK(cudaMalloc(&ctx->stage[0], (total_bytes)));                            \
-        ctx->stage_bytes[0] = (total_bytes);                                      \
-    }
 
 int wifi_cmatmul_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int r1, int c1, const void *B, int r2, int c2, void *C, int64_t batch)
 {

@@ -19,8 +19,8 @@
 // eig_prepare_kernel   one CTA, FP64: scaled matrix, cyclic Jacobi with a round-robin parallel ordering (27 disjoint
 //                      rotations per round, 53 rounds per sweep), builds the two 53 x 53 "filters" W1 (= G, rows = eigen
 //                      index) and W2 (= G2, columns = eigen index) for the shared-filter GEMM kernels, l, p and the scalars.
-// eig_mid_kernel       warp per frame, between the two GEMMs: beta, gamma, z_d by warp reductions, v = s (.) (u - p z_d) in place.
-// eig_fin_kernel       flat, after the second GEMM: H = rx/tx - c, null bin from the value eig_mid stashed.
+// The per-frame middle (beta, gamma, z_d, v = s (.) (u - p z_d)) and the final H = rx/tx - c are fused into the second product's
+// kernel (wifi_gemm_tc.cu MID/RESID modes, wifi_gemm_dmma.cu EIG mode); the stand-alone mid / fin passes they replaced are gone.
 #include <algorithm>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
@@ -198,132 +198,6 @@ cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, v
     if (e != cudaSuccess) return e;
     eig_prepare_kernel<<<1, EG_THREADS, smem, s>>>((const double2 *)R64, absx2, (double2 *)W1, (double2 *)W2, lam, (double2 *)p, scal, info);
     g_last_launches = 1;
-    return cudaGetLastError();
-}
-
-// 1/x: FP32 with the hardware approximation + one Newton step (the IEEE '/' is ~12 instructions and a slow-path branch; the
-// mid pass was issue-bound at 76 % with eight of them per lane), FP64 exact
-__device__ __forceinline__ float rcp_t(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
-
-// ---- between the two products: v = s (.) (u - p z_d), in place; the null bin's H is stashed in v[52] ----
-template <typename T>
-__global__ void __launch_bounds__(256) eig_mid_kernel(cx<T> *__restrict__ U, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx,
-                                                      int64_t frame_stride, const T *__restrict__ sigma2, const double *__restrict__ lam,
-                                                      const double2 *__restrict__ p, const double *__restrict__ scal, int64_t n_frames)
-{
-    const int lane = threadIdx.x & 31;
-    const int dc = (int)scal[2];
-    const T Rdd = (T)scal[0], md = (T)scal[1];
-    // this lane's eigen indices: lane and lane + 32
-    const T l0 = (T)lam[lane], l1 = lane + 32 < NSC ? (T)lam[lane + 32] : (T)0;
-    const cx<T> p0 = mk<T>((T)p[lane].x, (T)p[lane].y);
-    const cx<T> p1 = lane + 32 < NSC ? mk<T>((T)p[lane + 32].x, (T)p[lane + 32].y) : mk<T>(0, 0);
-    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const bool second = lane + 32 < NSC;
-    int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // the next frame's inputs are loaded while the current one is reduced (the kernel is otherwise a chain of HBM latency ->
-    // shuffle reductions -> stores per warp: 0.38 ms per 1 Mi frames without the prefetch against 0.14 ms of HBM time)
-    cx<T> nu0 = mk<T>(0, 0), nu1 = mk<T>(0, 0), ntd = mk<T>(1, 0), nrd = mk<T>(0, 0);
-    T ns2 = 1;
-    if (f < n_frames) {
-        nu0 = U[f * NSC + lane]; if (second) nu1 = U[f * NSC + lane + 32];
-        ns2 = sigma2[f];
-        if (dc >= 0) { ntd = tx[f * frame_stride + dc]; nrd = rx[f * frame_stride + dc]; }
-    }
-    for (; f < n_frames; f += wstride) {
-        cx<T> *u = U + f * NSC;
-        const T s2 = ns2;
-        const cx<T> u0 = nu0, u1 = nu1, td = ntd, rd = nrd;
-        {
-            const int64_t fn = f + wstride;
-            if (fn < n_frames) {
-                nu0 = U[fn * NSC + lane]; if (second) nu1 = U[fn * NSC + lane + 32];
-                ns2 = sigma2[fn];
-                if (dc >= 0) { ntd = tx[fn * frame_stride + dc]; nrd = rx[fn * frame_stride + dc]; }
-            }
-        }
-        const T i0 = rcp_t(l0 + s2), i1 = rcp_t(l1 + s2);
-        cx<T> zd = mk<T>(0, 0);
-        if (dc >= 0) {                                             // warp-uniform
-            // beta = sum conj(p_i) u_i / (l_i + s2), gamma = sum |p_i|^2 / (l_i + s2)   (p is zero beyond the eigen pairs)
-            T br = (p0.x * u0.x + p0.y * u0.y) * i0 + (p1.x * u1.x + p1.y * u1.y) * i1;
-            T bi = (p0.x * u0.y - p0.y * u0.x) * i0 + (p1.x * u1.y - p1.y * u1.x) * i1;
-            T ga = (p0.x * p0.x + p0.y * p0.y) * i0 + (p1.x * p1.x + p1.y * p1.y) * i1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                br += __shfl_xor_sync(0xffffffffu, br, o);
-                bi += __shfl_xor_sync(0xffffffffu, bi, o);
-                ga += __shfl_xor_sync(0xffffffffu, ga, o);
-            }
-            const T itd = rcp_t(td.x * td.x + td.y * td.y);
-            const cx<T> yd = mk<T>((rd.x * td.x + rd.y * td.y) * itd, (rd.y * td.x - rd.x * td.y) * itd);
-            const T q = Rdd - ga, iden = rcp_t(s2 * md + q);
-            const cx<T> dlt = mk<T>(yd.x - br, yd.y - bi);
-            zd = mk<T>(dlt.x * iden, dlt.y * iden);
-            if (lane == 0) u[NSC - 1] = mk<T>(br + dlt.x * (q * iden), bi + dlt.y * (q * iden));    // H_d, picked up by the last pass
-        }
-        // v_i = s_i (u_i - p_i z_d),  s_i = s2 / (l_i + s2)
-        const cx<T> w0 = csub(u0, cmul(p0, zd)), w1 = csub(u1, cmul(p1, zd));
-        u[lane] = mk<T>(w0.x * (s2 * i0), w0.y * (s2 * i0));
-        if (lane + 32 < NSC && !(dc >= 0 && lane + 32 == NSC - 1)) u[lane + 32] = mk<T>(w1.x * (s2 * i1), w1.y * (s2 * i1));
-    }
-}
-
-// ---- after the second product (H holds c = G2 v): H = rx/tx - c, null bin from the stash; one thread per value ----
-template <typename T>
-__global__ void __launch_bounds__(256) eig_fin_kernel(cx<T> *__restrict__ H, const cx<T> *__restrict__ V, const cx<T> *__restrict__ tx,
-                                                      const cx<T> *__restrict__ rx, int64_t frame_stride, const double *__restrict__ scal,
-                                                      int64_t n_elems)
-{
-    const int dc = (int)scal[2];
-    const int64_t e0 = (int64_t)blockIdx.x * 256;
-    const int64_t fb = e0 / NSC;                                   // one 64-bit division per thread, 32-bit arithmetic below
-    const unsigned rem = (unsigned)(e0 - fb * NSC) + threadIdx.x;
-    const int64_t e = e0 + threadIdx.x;
-    if (e >= n_elems) return;
-    const unsigned q = rem / NSC, k = rem - q * NSC;
-    const int64_t f = fb + q;
-    cx<T> h;
-    if ((int)k == dc) h = V[f * NSC + NSC - 1];
-    else h = csub(cdiv(ld_stream(rx + f * frame_stride + k), ld_stream(tx + f * frame_stride + k)), H[e]);
-    st_stream(H + e, h);
-}
-
-cudaError_t launch_eig_mid(wifi_dtype dt, void *U, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
-                           const double *lam, const void *p, const double *scal, int64_t n_frames, cudaStream_t s)
-{
-    g_last_launches = 0;
-    if (n_frames == 0) return cudaSuccess;
-    g_last_launches = 1;
-    const unsigned grid = (unsigned)std::min<int64_t>((n_frames + 7) / 8, 148 * 8);
-    if (dt == WIFI_F32)
-        eig_mid_kernel<float><<<grid, 256, 0, s>>>((float2 *)U, (const float2 *)tx, (const float2 *)rx, frame_stride, (const float *)sigma2, lam,
-                                                   (const double2 *)p, scal, n_frames);
-    else
-        eig_mid_kernel<double><<<grid, 256, 0, s>>>((double2 *)U, (const double2 *)tx, (const double2 *)rx, frame_stride, (const double *)sigma2,
-                                                    lam, (const double2 *)p, scal, n_frames);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_eig_fin(wifi_dtype dt, void *H, const void *V, const void *tx, const void *rx, int64_t frame_stride, const double *scal,
-                           int64_t n_frames, cudaStream_t s)
-{
-    g_last_launches = 0;
-    if (n_frames == 0) return cudaSuccess;
-    g_last_launches = 1;
-    const int64_t n_elems = n_frames * NSC;
-    const unsigned grid = (unsigned)((n_elems + 255) / 256);
-    if (dt == WIFI_F32)
-        eig_fin_kernel<float><<<grid, 256, 0, s>>>((float2 *)H, (const float2 *)V, (const float2 *)tx, (const float2 *)rx, frame_stride, scal, n_elems);
-    else
-        eig_fin_kernel<double><<<grid, 256, 0, s>>>((double2 *)H, (const double2 *)V, (const double2 *)tx, (const double2 *)rx, frame_stride, scal,
-                                                    n_elems);
     return cudaGetLastError();
 }
 

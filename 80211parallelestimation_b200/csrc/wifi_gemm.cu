@@ -1,130 +1,24 @@
-// wifi_gemm.cu -- shared-filter PS_MMSE as one GEMM over all frames, plus the small batched matrix utils.
-//
-//   H[n][53] = H_ls[n][53] * W^T          (multiply utils.c:16-31 of the 53x53 filter with every frame's LS vector)
-//
-// mmse_shared_simt_kernel: CUDA-core version (both dtypes): W^T and a 64-frame tile of H_ls (optionally formed
-// in place as rx/tx, main.c:83 arithmetic) staged in shared memory, register tile 7 rows x 2 frames per thread,
-// result staged back through shared memory so global stores are one contiguous run.
-// The FP32 tensor-core path (3xTF32 on tcgen05, accumulators in TMEM) is in wifi_gemm_tc.cu.
+// wifi_gemm.cu -- the small batched complex matrix utils of utils.h:38-60 (multiply, hermitian, addition, multiplyVxVeqM,
+// identity).  The shared-filter PS_MMSE GEMM over all frames lives in wifi_gemm_tc.cu (FP32: 3xTF32 on tcgen05) and
+// wifi_gemm_dmma.cu (FP64: DMMA); the CUDA-core version they replaced (0.998 ms per 1 Mi frames against 0.23) is gone.
 #include <algorithm>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
 namespace wifi {
 
-// ------------------------------------------------------------------------------------------
-// filter images
-// ------------------------------------------------------------------------------------------
-__global__ void filter_install_kernel(const double2 *__restrict__ W, float2 *__restrict__ W32)
+// W' = W diag(1/tx): the LS divide by a shared, known tx block vector folded into the 53 x 53 filter (FP64, once per batch)
+__global__ void filter_fold_kernel(const double2 *__restrict__ W, const double2 *__restrict__ tx, double2 *__restrict__ Wout)
 {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < NSC * NSC) W32[e] = make_float2((float)W[e].x, (float)W[e].y);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < NSC * NSC) Wout[e] = cmul(W[e], crecip(tx[e % NSC]));
 }
 
-cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s)
+cudaError_t launch_filter_fold(const void *W64, const void *tx64, void *Wout64, cudaStream_t s)
 {
-    filter_install_kernel<<<(NSC * NSC + 255) / 256, 256, 0, s>>>((const double2 *)img.W64, (float2 *)img.W32);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// SIMT shared-filter kernel
-// ------------------------------------------------------------------------------------------
-constexpr int MS_THREADS = 256;
-constexpr int MS_TILE = 64;             // frames per CTA iteration
-constexpr int MS_RPW = 7;               // filter rows per warp (8 warps x 7 = 56 >= 53)
-constexpr int MS_WLD = 56;              // Wt[j][r] row length
-constexpr int MS_HLD = MS_TILE + 1;     // hT[j][f] row length (odd: conflict-light transposed stores)
-
-template <typename T, bool FUSED>
-__global__ void __launch_bounds__(MS_THREADS) mmse_shared_simt_kernel(const cx<T> *__restrict__ W, const cx<T> *__restrict__ a_in,
-                                                                      const cx<T> *__restrict__ rx, int64_t frame_stride,
-                                                                      cx<T> *__restrict__ H, int64_t n_frames)
-{
-    extern __shared__ __align__(16) unsigned char ms_smem[];
-    cx<T> *Wt = (cx<T> *)ms_smem;              // [53][56]   Wt[j][r] = W[r][j]
-    cx<T> *hT = Wt + NSC * MS_WLD;             // [53][65]   hT[j][f] = H_ls[f][j]; reused as output staging
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int e = threadIdx.x; e < NSC * MS_WLD; e += MS_THREADS) {
-        int j = e / MS_WLD, r = e - j * MS_WLD;
-        Wt[e] = r < NSC ? W[r * NSC + j] : mk<T>(0, 0);
-    }
-
-    const int64_t n_tiles = (n_frames + MS_TILE - 1) / MS_TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t f0 = tile * MS_TILE;
-        const int nf = (int)min((int64_t)MS_TILE, n_frames - f0);
-        __syncthreads();   // previous tile's staging fully drained (and Wt visible on the first pass)
-        for (int e = threadIdx.x; e < MS_TILE * NSC; e += MS_THREADS) {
-            int f = e / NSC, j = e - f * NSC;
-            cx<T> v = mk<T>(0, 0);
-            if (f < nf) {
-                if (FUSED) {
-                    int64_t off = (f0 + f) * frame_stride + j;
-                    v = cdiv(ld_stream(rx + off), ld_stream(a_in + off));     // per-block LS  rx/tx
-                } else {
-                    v = ld_stream(a_in + (f0 + f) * NSC + j);
-                }
-            }
-            hT[j * MS_HLD + f] = v;
-        }
-        __syncthreads();
-
-        cx<T> acc[MS_RPW][2];
-#pragma unroll
-        for (int r = 0; r < MS_RPW; ++r) acc[r][0] = acc[r][1] = mk<T>(0, 0);
-        const int r0 = warp * MS_RPW;
-#pragma unroll 4
-        for (int j = 0; j < NSC; ++j) {
-            cx<T> h0 = hT[j * MS_HLD + lane], h1 = hT[j * MS_HLD + lane + 32];
-#pragma unroll
-            for (int r = 0; r < MS_RPW; ++r) {
-                cx<T> w = Wt[j * MS_WLD + r0 + r];           // warp-uniform address: broadcast
-                cfma(acc[r][0], w, h0);
-                cfma(acc[r][1], w, h1);
-            }
-        }
-        __syncthreads();   // everyone is done reading hT
-        // stage the result row-major [f][53] so the global write below is one contiguous run
-        cx<T> *stage = hT;
-#pragma unroll
-        for (int r = 0; r < MS_RPW; ++r)
-            if (r0 + r < NSC) {
-                stage[lane * NSC + r0 + r] = acc[r][0];
-                stage[(lane + 32) * NSC + r0 + r] = acc[r][1];
-            }
-        __syncthreads();
-        for (int e = threadIdx.x; e < nf * NSC; e += MS_THREADS) st_stream(H + f0 * NSC + e, stage[e]);
-    }
-}
-
-template <typename T, bool FUSED>
-static cudaError_t launch_simt(const void *W, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
-                               cudaStream_t s)
-{
-    size_t smem = sizeof(cx<T>) * (NSC * MS_WLD + NSC * MS_HLD);
-    static_assert(NSC * MS_HLD >= MS_TILE * NSC, "staging must fit");
-    cudaError_t e = cudaFuncSetAttribute(mmse_shared_simt_kernel<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int64_t n_tiles = (n_frames + MS_TILE - 1) / MS_TILE;
-    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148 * (sizeof(T) == 4 ? 4 : 2));
-    mmse_shared_simt_kernel<T, FUSED><<<grid, MS_THREADS, smem, s>>>((const cx<T> *)W, (const cx<T> *)a, (const cx<T> *)rx,
-                                                                     frame_stride, (cx<T> *)H, n_frames);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *a, const void *rx, int64_t frame_stride,
-                                    void *H, int64_t n_frames, cudaStream_t s)
-{
-    g_last_launches = 0;
-    if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    if (dt == WIFI_F32)
-        return rx ? launch_simt<float, true>(img.W32, a, rx, frame_stride, H, n_frames, s)
-                  : launch_simt<float, false>(img.W32, a, nullptr, NSC, H, n_frames, s);
-    return rx ? launch_simt<double, true>(img.W64, a, rx, frame_stride, H, n_frames, s)
-              : launch_simt<double, false>(img.W64, a, nullptr, NSC, H, n_frames, s);
+    filter_fold_kernel<<<(NSC * NSC + 255) / 256, 256, 0, s>>>((const double2 *)W64, (const double2 *)tx64, (double2 *)Wout64);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -7,20 +7,11 @@
 // the same ceiling as DFMA -- but one warp instruction carries 256 FMAs with two operand registers per lane, so the
 // pipe is fed without the LDS/issue pressure that held the CUDA-core kernel at 9.8 TFLOP/s.
 //
-// One persistent CTA per SM, 8 warps.  The filter image Bt[n][k] (n-major, row stride 116 doubles so the 8 rows a
-// fragment load touches fall in different bank groups) is copied to shared memory once.  Every warp owns tiles of 8
-// frames end to end -- there is no CTA-wide barrier after start-up, so the warps drift apart and one warp's global loads
-// overlap the other warps' DMMAs:
-//   * tx/rx of the warp's NEXT tile (8 x 53 complex each, contiguous when frames are dense) are loaded into registers
-//     before the DMMA loop of the current tile and consumed after it, so HBM latency hides behind ~380 DMMAs;
-//   * LS divide, write the interleaved (re, im) row -- which IS the real embedding of the A operand -- into the warp's
-//     private A buffer (row stride 108, k = 106, 107 zero);
-//   * 27 k-steps x 14 n8 tiles DMMA.8x8x4, accumulators (28 doubles) in registers;
-//   * a lane's accumulator pair is one complex output (re, im): 16-byte streaming stores straight from registers.
+// One persistent CTA per SM.  The filter image Bt[n][k] (n-major, row stride 116 doubles so the 8 rows a fragment load
+// touches fall in different bank groups) is copied to shared memory once; the kernel is warp-specialised (below).  The
+// symmetric version it replaced (every warp load -> convert -> DMMA -> store, 0.90-1.06 G frames/s against 1.19) is gone.
 // Replaces multiply() utils.c:16-31 applied per frame (main.c:201-207 intent) in the FP64 mode.
 #include <algorithm>
-#include <cstdlib>
-#include <cstring>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -30,9 +21,6 @@ constexpr int DM_K = 108;               // 106 padded to a multiple of 4
 constexpr int DM_N = 112;               // 106 padded to a multiple of 8
 constexpr int DM_BS = WIFI_DMMA_BS;     // Bt row stride (doubles): 116 = 4 mod 16
 constexpr int DM_AS = 108;              // A row stride (doubles): 12 mod 16
-constexpr int DM_WARPS = 8;
-constexpr int DM_ROWS = 8;              // frames per warp tile (one m8 fragment)
-constexpr int DM_NLD = (DM_ROWS * NSC + 31) / 32;   // 14 complex values per lane and input
 constexpr int DM_NT = DM_N / 8;         // 14
 constexpr int DM_KT = DM_K / 4;         // 27
 
@@ -60,104 +48,6 @@ cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s)
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// raw inputs of one 8-frame tile, spread over the warp: element e = 32 u + lane  ->  frame e / 53, sub-carrier e % 53
-template <bool FUSED> struct DmRaw {
-    double2 t[DM_NLD];
-    double2 r[FUSED ? DM_NLD : 1];
-};
-
-template <bool FUSED>
-__device__ __forceinline__ void dm_load_raw(DmRaw<FUSED> &raw, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
-                                            int64_t frame_stride, int64_t f0, int nf, int lane)
-{
-#pragma unroll
-    for (int u = 0; u < DM_NLD; ++u) {
-        const int e = u * 32 + lane;
-        const int f = e / NSC, k = e - f * NSC;
-        raw.t[u] = make_double2(FUSED ? 1.0 : 0.0, 0.0);
-        if (FUSED) raw.r[u] = make_double2(0.0, 0.0);
-        if (e < DM_ROWS * NSC && f < nf) {
-            const int64_t off = (f0 + f) * frame_stride + k;
-            raw.t[u] = ld_stream(a_in + off);
-            if (FUSED) raw.r[u] = ld_stream(rx + off);
-        }
-    }
-}
-
-template <bool FUSED>
-__global__ void __launch_bounds__(DM_WARPS * 32, 1)
-    mmse_shared_dmma_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
-                            int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames)
-{
-    extern __shared__ __align__(16) unsigned char dm_smem[];
-    double *Bt = (double *)dm_smem;                                   // [112][116]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *As = Bt + DM_N * DM_BS + warp * (DM_ROWS * DM_AS);        // [8][108], private to the warp
-    const int g = lane >> 2, q = lane & 3;                            // fragment row / position in the group of 4
-
-    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
-    const int64_t tstep = (int64_t)gridDim.x * DM_WARPS;
-    int64_t tile = (int64_t)blockIdx.x * DM_WARPS + warp;
-    DmRaw<FUSED> raw;
-    if (tile < n_tiles) dm_load_raw<FUSED>(raw, a_in, rx, frame_stride, tile * DM_ROWS, (int)min((int64_t)DM_ROWS, n_frames - tile * DM_ROWS), lane);
-    {
-        const double2 *src = (const double2 *)Bt_g;
-        double2 *dst = (double2 *)Bt;
-        for (int e = threadIdx.x; e < DM_N * DM_BS / 2; e += DM_WARPS * 32) dst[e] = src[e];
-        if (lane < DM_ROWS) { As[lane * DM_AS + 106] = 0.0; As[lane * DM_AS + 107] = 0.0; }
-    }
-    __syncthreads();
-    // Warps w and w + 4 share a scheduler and its FP64 pipe.  Started together they stay in lockstep (both convert, then
-    // both issue DMMAs); offset by about half a tile period they alternate and the pipe never waits for a conversion.
-    if (warp >= 4 && tile + tstep < n_tiles) __nanosleep(2500);
-
-    for (; tile < n_tiles; tile += tstep) {
-        const int64_t f0 = tile * DM_ROWS;
-        const int nf = (int)min((int64_t)DM_ROWS, n_frames - f0);
-        // ---- y = rx/tx (or H_ls) of this tile, held in registers since the previous iteration -> A rows ----
-#pragma unroll
-        for (int u = 0; u < DM_NLD; ++u) {
-            const int e = u * 32 + lane;
-            const int f = e / NSC, k = e - f * NSC;
-            if (e < DM_ROWS * NSC) {
-                double2 y = raw.t[u];
-                if (FUSED) {                                          // per-block LS rx/tx (main.c:83); rows >= nf: 0/1 = 0
-                    const double2 t = raw.t[u], r = raw.r[u];
-                    const double inv = 1.0 / (t.x * t.x + t.y * t.y);  // one division: the FP64 pipe is the DMMA pipe
-                    y = make_double2((r.x * t.x + r.y * t.y) * inv, (r.y * t.x - r.x * t.y) * inv);
-                }
-                *reinterpret_cast<double2 *>(As + f * DM_AS + 2 * k) = y;
-            }
-        }
-        __syncwarp();
-        // ---- next tile's inputs: in flight during the DMMA loop below ----
-        if (tile + tstep < n_tiles)
-            dm_load_raw<FUSED>(raw, a_in, rx, frame_stride, (tile + tstep) * DM_ROWS, (int)min((int64_t)DM_ROWS, n_frames - (tile + tstep) * DM_ROWS), lane);
-
-        // ---- 8 x 112 x 108 product on the FP64 tensor path ----
-        double c[DM_NT][2];
-#pragma unroll
-        for (int j = 0; j < DM_NT; ++j) c[j][0] = c[j][1] = 0.0;
-        const double *ap = As + g * DM_AS + q;
-        const double *bp = Bt + g * DM_BS + q;
-#pragma unroll 3
-        for (int kt = 0; kt < DM_KT; ++kt) {
-            const double a0 = ap[kt * 4];
-#pragma unroll
-            for (int j = 0; j < DM_NT; ++j) dmma884(c[j][0], c[j][1], a0, bp[j * 8 * DM_BS + kt * 4]);
-        }
-        __syncwarp();                                                 // all lanes are done with this tile's A rows
-
-        // ---- a lane's accumulator pair = one complex output: H[f0 + g][4 j + q] ----
-        if (g < nf) {
-            double2 *out = H + (f0 + g) * NSC + q;
-#pragma unroll
-            for (int j = 0; j < DM_NT; ++j)
-                if (4 * j + q < NSC) st_stream(out + 4 * j, make_double2(c[j][0], c[j][1]));
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,27 +347,9 @@ cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, cons
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    static const int variant = [] { const char *e = getenv("WIFI_B200_DMMA"); return (e && !strcmp(e, "symmetric")) ? 0 : 1; }();
-    cudaError_t e;
-    if (variant == 1) {
-        const DmEig none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0.0, 0.0, -1};
-        return rx ? launch_ws<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
-                  : launch_ws<false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
-    }
-    const size_t smem = sizeof(double) * (DM_N * DM_BS + DM_WARPS * DM_ROWS * DM_AS);
-    const int64_t n_tiles = (n_frames + DM_ROWS - 1) / DM_ROWS;
-    const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + DM_WARPS - 1) / DM_WARPS, 148);
-    if (rx) {
-        e = cudaFuncSetAttribute(mmse_shared_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mmse_shared_dmma_kernel<true><<<grid, DM_WARPS * 32, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
-                                                                        (double2 *)H, n_frames);
-    } else {
-        e = cudaFuncSetAttribute(mmse_shared_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mmse_shared_dmma_kernel<false><<<grid, DM_WARPS * 32, smem, s>>>(img.B64, (const double2 *)a, nullptr, NSC, (double2 *)H, n_frames);
-    }
-    return cudaGetLastError();
+    const DmEig none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0.0, 0.0, -1};
+    return rx ? launch_ws<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+              : launch_ws<false, false>(img, a, nullptr, frame_stride, H, n_frames, none, s);
 }
 
 }  // namespace wifi

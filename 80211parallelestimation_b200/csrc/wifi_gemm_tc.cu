@@ -568,7 +568,7 @@ cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const 
     g_last_launches = 1;
     const TcResid none = {nullptr, nullptr, 0, nullptr, -1, nullptr, nullptr, nullptr, 0.f, 0.f};
     return rx ? launch_tc<true, false, false>(img, a, rx, frame_stride, H, n_frames, none, s)
-              : launch_tc<false, false, false>(img, a, nullptr, NSC, H, n_frames, none, s);
+              : launch_tc<false, false, false>(img, a, nullptr, frame_stride, H, n_frames, none, s);
 }
 
 // H = rx/tx - v W^T (W = img), null bin `dc` from v[f][52]: the second product of the eigen-domain per-frame MMSE.

@@ -17,7 +17,6 @@ struct InterpTables {
 // shared MMSE filter operand images (built by filter_install from W, 53x53 double2 row-major)
 struct FilterImages {
     double *W64;     // [53][53] double2, row-major (the FP64 truth)
-    float *W32;      // [53][53] float2 (rounded)
     float *Bhi;      // tf32 "hi" image of the real embedding, UMMA canonical K-major no-swizzle layout [112 x 112]
     float *Blo;      // tf32 "lo" image (W - hi)
     double *B64;     // real embedding for the FP64 DMMA path, Bt[112][WIFI_DMMA_BS] (n-major, k contiguous, rows padded)
@@ -42,15 +41,13 @@ cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot
 cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s);
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);
 cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info,
+                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info, int fast32,
                                        cudaStream_t s);
 cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                     const void *sigma2, void *H, int64_t n_frames, int wide, cudaStream_t s);
+                                     const void *sigma2, void *H, int64_t n_frames, int fast32, cudaStream_t s);
 
-// shared-filter GEMM + small matrix utils (wifi_gemm.cu)
-cudaError_t launch_filter_install_simt(FilterImages &img, cudaStream_t s);   // W64 -> W32
-cudaError_t launch_mmse_shared_simt(wifi_dtype dt, const FilterImages &img, const void *tx_or_hls, const void *rx,
-                                    int64_t frame_stride, void *H, int64_t n_frames, cudaStream_t s);  // rx == NULL: apply only
+// shared-filter GEMM (wifi_gemm_tc.cu, wifi_gemm_dmma.cu) + small matrix utils (wifi_gemm.cu)
+cudaError_t launch_filter_fold(const void *W64, const void *tx64, void *Wout64, cudaStream_t s);   // W diag(1/tx)
 cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // W64 -> Bhi/Blo (UMMA canonical layout)
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                   int64_t n_frames, cudaStream_t s);             // FP32 I/O, 3xTF32 on tcgen05
@@ -80,10 +77,6 @@ cudaError_t launch_error_stats(wifi_dtype dt, const void *H, const void *Href, i
 // eigen-domain per-frame MMSE (wifi_eig.cu)
 cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, void *W2, double *lam, void *p, double *scal, int *info,
                                cudaStream_t s);
-cudaError_t launch_eig_mid(wifi_dtype dt, void *U, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
-                           const double *lam, const void *p, const double *scal, int64_t n_frames, cudaStream_t s);
-cudaError_t launch_eig_fin(wifi_dtype dt, void *H, const void *V, const void *tx, const void *rx, int64_t frame_stride, const double *scal,
-                           int64_t n_frames, cudaStream_t s);
 
 // measured ceilings (wifi_peaks.cu): which = 0 FP32 FMA, 1 FP64 FMA, 2 FP64 DMMA (TFLOP/s), 3 streaming copy (GB/s)
 cudaError_t measure_peak(int which, double *value, cudaStream_t s);

@@ -4,12 +4,11 @@
 //                       memory; the pivot arg-max is a warp-shuffle reduction.
 //   filter_form_kernel  W = R (R + diag d)^-1 in double-double, once per batch (main.c:183-201 intent).
 //   cinverse_reg_kernel batched inverse, orders 33..64: in-place Gauss-Jordan with implicit pivoting, the matrix in registers.
-//   cinverse_kernel     batched inverse, orders <= 32 (and WIFI_INV_SMEM=1): the shared-memory LU, one CTA per matrix.
+//   cinverse_kernel     batched inverse, orders <= 32: the shared-memory LU, one CTA per matrix.
 //   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
-#include <cstdlib>
 
 namespace wifi {
 
@@ -312,8 +311,8 @@ __device__ __forceinline__ double pivot_rcp(double d)
 __device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
 
-// TC = tile columns per thread: 8 (128 threads, 16 x 8: the FP32 default), 4 (256 threads, 16 x 16: the FP64 default) or 2 (512
-// threads, 16 x 32: half the registers, twice the warps -- measured 15 % slower in FP64, selectable with WIFI_INV_TC2=1).
+// TC = tile columns per thread: 8 (128 threads, 16 x 8: FP32) or 4 (256 threads, 16 x 16: FP64).  Measured and dropped: 2 (512
+// threads, half the registers, twice the warps): 15 % slower in FP64.
 template <typename T, int TC, int MINB>
 __global__ void __launch_bounds__(16 * (WIFI_MAX_ORDER / TC), MINB) cinverse_reg_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
 {
@@ -422,11 +421,9 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     g_last_launches = 1;
     const int ld = 2 * order + 1;
     cudaError_t e;
-    if (order > 32 && !getenv("WIFI_INV_SMEM")) {               // register-resident Gauss-Jordan (WIFI_INV_SMEM=1: the shared-memory LU)
-        // FP32: 4 x 8 tiles, 128 threads, 96 registers, 5 CTAs/SM (9.4 M matrices/s; 4 x 4 tiles with 256 threads, WIFI_INV_TC4=1: 9.0 M)
-        if (dt == WIFI_F32 && !getenv("WIFI_INV_TC4")) cinverse_reg_kernel<float, 8, 5><<<(unsigned)batch, 128, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
-        else if (dt == WIFI_F32) cinverse_reg_kernel<float, 4, 4><<<(unsigned)batch, 256, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
-        else if (getenv("WIFI_INV_TC2")) cinverse_reg_kernel<double, 2, 2><<<(unsigned)batch, 512, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
+    if (order > 32) {                                           // register-resident Gauss-Jordan
+        // FP32: 4 x 8 tiles, 128 threads, 96 registers, 5 CTAs/SM; FP64: 4 x 4 tiles, 256 threads (the 4 x 2 / 512-thread form was 15 % slower)
+        if (dt == WIFI_F32) cinverse_reg_kernel<float, 8, 5><<<(unsigned)batch, 128, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
         else cinverse_reg_kernel<double, 4, 2><<<(unsigned)batch, 256, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
         return cudaGetLastError();
     }
@@ -452,11 +449,14 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
 constexpr int PV_THREADS = 128;
 constexpr int PV_LD = NSC + 2;
 
-template <typename T>
-__global__ void __launch_bounds__(PV_THREADS) mmse_pivot_kernel(const cx<T> *__restrict__ R, const cx<T> *__restrict__ tx,
-                                                                const cx<T> *__restrict__ rx, int64_t frame_stride,
-                                                                const T *__restrict__ sigma2, const cx<T> *__restrict__ hls,
-                                                                cx<T> *__restrict__ H, int *info)
+// TIO = storage type of R/tx/rx/sigma2/hls/H, T = arithmetic type.  <float, double> is the WIFI_F32 default: sigma2/|tx|^2
+// (1e-10 .. 1e-7) is below the FP32 resolution of R, so the FP32-arithmetic elimination (<float, float>, WIFI_SOLVE_FAST32)
+// is only accurate to ~1e-1 at the 60 dB end.
+template <typename TIO, typename T>
+__global__ void __launch_bounds__(PV_THREADS) mmse_pivot_kernel(const cx<TIO> *__restrict__ R, const cx<TIO> *__restrict__ tx,
+                                                                const cx<TIO> *__restrict__ rx, int64_t frame_stride,
+                                                                const TIO *__restrict__ sigma2, const cx<TIO> *__restrict__ hls,
+                                                                cx<TIO> *__restrict__ H, int *info)
 {
     extern __shared__ __align__(16) unsigned char pv_smem[];
     cx<T> *a = (cx<T> *)pv_smem;          // [53][55]: A | y
@@ -464,19 +464,20 @@ __global__ void __launch_bounds__(PV_THREADS) mmse_pivot_kernel(const cx<T> *__r
     cx<T> *hv = lcol + NSC;               // [53] H_ls of this frame (rank-1 mode)
     __shared__ int ctl[2];
     const int64_t f = blockIdx.x;
-    const cx<T> *txf = tx + f * frame_stride, *rxf = rx + f * frame_stride;
-    const T s2 = sigma2[f];
+    const cx<TIO> *txf = tx + f * frame_stride, *rxf = rx + f * frame_stride;
+    auto wd = [](cx<TIO> v) { return mk<T>((T)v.x, (T)v.y); };
+    const T s2 = (T)sigma2[f];
     if (hls) {
-        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) hv[i] = hls[f * NSC + i];
+        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) hv[i] = wd(hls[f * NSC + i]);
         __syncthreads();
     }
     for (int e = threadIdx.x; e < NSC * NSC; e += PV_THREADS) {
         int i = e / NSC, j = e - i * NSC;
-        cx<T> r = hls ? cmul(hv[i], cconj(hv[j])) : R[e];
-        if (i == j) r.x += s2 / cabs2(txf[i]);
+        cx<T> r = hls ? cmul(hv[i], cconj(hv[j])) : wd(R[e]);
+        if (i == j) r.x += s2 / cabs2(wd(txf[i]));
         a[i * PV_LD + j] = r;
     }
-    for (int i = threadIdx.x; i < NSC; i += PV_THREADS) a[i * PV_LD + NSC] = cdiv(rxf[i], txf[i]);
+    for (int i = threadIdx.x; i < NSC; i += PV_THREADS) a[i * PV_LD + NSC] = cdiv(wd(rxf[i]), wd(txf[i]));
     __syncthreads();
     int sing = gj_solve<T>(a, NSC, PV_LD, NSC + 1, lcol, ctl);
     // z is column 53; H = R z
@@ -493,40 +494,39 @@ __global__ void __launch_bounds__(PV_THREADS) mmse_pivot_kernel(const cx<T> *__r
             if (threadIdx.x == 0) lcol[0] = acc;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) H[f * NSC + i] = cmul(hv[i], lcol[0]);
+        for (int i = threadIdx.x; i < NSC; i += PV_THREADS) { const cx<T> h = cmul(hv[i], lcol[0]); H[f * NSC + i] = mk<TIO>((TIO)h.x, (TIO)h.y); }
     } else {
         for (int i = threadIdx.x; i < NSC; i += PV_THREADS) {
             cx<T> acc = mk<T>(0, 0);
-            for (int j = 0; j < NSC; ++j) cfma(acc, R[i * NSC + j], a[j * PV_LD + NSC]);
-            H[f * NSC + i] = acc;
+            for (int j = 0; j < NSC; ++j) cfma(acc, wd(R[i * NSC + j]), a[j * PV_LD + NSC]);
+            H[f * NSC + i] = mk<TIO>((TIO)acc.x, (TIO)acc.y);
         }
     }
     if (threadIdx.x == 0 && info && sing) atomicExch(info, 1);
 }
 
+template <typename TIO, typename T>
+static cudaError_t launch_pivot(const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, const void *hls,
+                                void *H, int64_t n_frames, int *info, cudaStream_t s)
+{
+    const size_t smem = sizeof(cx<T>) * (NSC * PV_LD + 2 * NSC);
+    cudaError_t e = cudaFuncSetAttribute(mmse_pivot_kernel<TIO, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mmse_pivot_kernel<TIO, T><<<(unsigned)n_frames, PV_THREADS, smem, s>>>((const cx<TIO> *)R, (const cx<TIO> *)tx, (const cx<TIO> *)rx, frame_stride,
+                                                                          (const TIO *)sigma2, (const cx<TIO> *)hls, (cx<TIO> *)H, info);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info,
+                                       const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info, int fast32,
                                        cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    if (dt == WIFI_F32) {
-        size_t smem = sizeof(float2) * (NSC * PV_LD + 2 * NSC);
-        mmse_pivot_kernel<float><<<(unsigned)n_frames, PV_THREADS, smem, s>>>((const float2 *)R, (const float2 *)tx,
-                                                                             (const float2 *)rx, frame_stride,
-                                                                             (const float *)sigma2, (const float2 *)Hls_for_R,
-                                                                             (float2 *)H, info);
-    } else {
-        size_t smem = sizeof(double2) * (NSC * PV_LD + 2 * NSC);
-        cudaError_t e = cudaFuncSetAttribute(mmse_pivot_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mmse_pivot_kernel<double><<<(unsigned)n_frames, PV_THREADS, smem, s>>>((const double2 *)R, (const double2 *)tx,
-                                                                               (const double2 *)rx, frame_stride,
-                                                                               (const double *)sigma2, (const double2 *)Hls_for_R,
-                                                                               (double2 *)H, info);
-    }
-    return cudaGetLastError();
+    if (dt == WIFI_F32 && fast32) return launch_pivot<float, float>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
+    if (dt == WIFI_F32) return launch_pivot<float, double>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
+    return launch_pivot<double, double>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
 }
 
 }  // namespace wifi

@@ -26,15 +26,14 @@
 // registers.  tx/rx of the group's next frame are prefetched during the elimination (registers in FP32, L2 in FP64).
 //
 // TIO is the storage type of R/tx/rx/sigma2/H and T the arithmetic type: <float,float>, <double,double>, and
-// <double,float> = WIFI_SOLVE_WIDE (FP32 I/O, FP64 arithmetic: d_f is below the FP32 resolution of R).
+// <double,float> = FP32 I/O with FP64 arithmetic (the default for WIFI_F32: d_f is below the FP32 resolution of R).
 //
 // Two kernels: mmse_hpd_kernel (the layout above; the default for FP32 arithmetic) and mmse_hpd_dmma_kernel further down
 // (FP64 arithmetic: the same elimination blocked by two columns with the trailing updates on the FP64 tensor path, DESIGN.md
-// 4.2a; WIFI_HPD_CFG=10 selects mmse_hpd_kernel<double, ...> instead for A/B timing).  Both share the back-substitution stage.
+// 4.2a).  Both share the back-substitution stage.
 //
 // Replaces the two inverse() calls of main.c:186,201 (utils.c:141-170, O(n^5)) for the intended formula.
 #include <algorithm>
-#include <cstdlib>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -693,45 +692,19 @@ static cudaError_t launch_hpd(const void *R, const void *tx, const void *rx, int
     return cudaGetLastError();
 }
 
-// tuning variants (WIFI_HPD_CFG=<n> selects one at run time for the probes; the defaults were measured on B200)
-static int hpd_cfg()
-{
-    static int v = -2;
-    if (v == -2) { const char *e = getenv("WIFI_HPD_CFG"); v = e ? atoi(e) : -1; }
-    return v;
-}
-
+// Kernel choice (measured on B200, 256 Ki frames; the alternatives that lost are gone from the build):
+//   FP64 arithmetic (WIFI_F64, and WIFI_F32 by default: FP32 storage, FP64 arithmetic -- the FP32-I/O mode that meets the 1e-4
+//   bound): mmse_hpd_dmma_kernel, 6 frames per CTA (5: 31.7 M frames/s, 4: 31.9, 2: 22.6; the CUDA-core layout <8,6>: 34.5).
+//   FP32 arithmetic (WIFI_SOLVE_FAST32, documented accuracy 4e-3): mmse_hpd_kernel<float, float, 4, 12> (<8,8> 60.2, <4,8> 68.9).
 cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
-                                     const void *sigma2, void *H, int64_t n_frames, int wide, cudaStream_t s)
+                                     const void *sigma2, void *H, int64_t n_frames, int fast32, cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const int cfg = hpd_cfg();
-#define HPD_ARGS R, tx, rx, frame_stride, sigma2, H, n_frames, s
-    // measured on B200, 256 Ki frames: f32 <4,12> 80.9 M frames/s (<8,8> 60.2, <4,8> 68.9); FP64 arithmetic: DMMA kernel
-    // 38.5 M (5 frames per CTA 31.7, 4: 31.9, 2: 22.6), CUDA-core <8,6> 34.5 M (<8,4> 31.7)
-    if (dt == WIFI_F32 && wide) {
-        switch (cfg) {
-        case 1: return launch_hpd<double, float, 8, 4, 1>(HPD_ARGS);
-        case 10: return launch_hpd<double, float, 8, 6, 1>(HPD_ARGS);
-        default: return launch_hpd_dmma<float, 6>(HPD_ARGS);
-        }
-    }
-    if (dt == WIFI_F32) {
-        switch (cfg) {
-        case 1: return launch_hpd<float, float, 4, 8, 1>(HPD_ARGS);
-        case 2: return launch_hpd<float, float, 8, 8, 1>(HPD_ARGS);
-        case 10: return launch_hpd<float, float, 4, 12, 1, 0>(HPD_ARGS);
-        default: return launch_hpd<float, float, 4, 12, 1>(HPD_ARGS);
-        }
-    }
-    switch (cfg) {
-    case 1: return launch_hpd<double, double, 8, 4, 1>(HPD_ARGS);
-    case 10: return launch_hpd<double, double, 8, 6, 1>(HPD_ARGS);
-    default: return launch_hpd_dmma<double, 6>(HPD_ARGS);
-    }
-#undef HPD_ARGS
+    if (dt == WIFI_F32 && fast32) return launch_hpd<float, float, 4, 12, 1>(R, tx, rx, frame_stride, sigma2, H, n_frames, s);
+    if (dt == WIFI_F32) return launch_hpd_dmma<float, 6>(R, tx, rx, frame_stride, sigma2, H, n_frames, s);
+    return launch_hpd_dmma<double, 6>(R, tx, rx, frame_stride, sigma2, H, n_frames, s);
 }
 
 }  // namespace wifi

@@ -65,14 +65,18 @@ typedef enum {
  * blocks 1..4 of a whole frame (frame_stride >= 212) and Cubic uses the true divided-difference spans 14/28/42 */
 #define WIFI_PS_MATLAB 8
 
-/* flags of wifi_mmse_perframe_batch */
+/* flags of wifi_mmse_perframe_batch.  Every default mode meets the accuracy bound of its storage type (1e-10 for WIFI_F64,
+ * 1e-4 for WIFI_F32, relative per sub-carrier): with WIFI_F32 the arrays are FP32 and the solve runs in FP64 arithmetic --
+ * sigma2/|x|^2 (1e-10..1e-7) lies below the FP32 resolution of R (1e-4), so an FP32 elimination of R + D cannot. */
 #define WIFI_SOLVE_PIVOT 0      /* LU with partial pivoting + back-substitution, H = R z (any non-singular R + D) */
-#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: register-resident un-pivoted L D L^H, H = y - D z (growth factor 1); FP64
-                                 * arithmetic runs the trailing updates on the FP64 tensor path (DMMA) */
-#define WIFI_SOLVE_WIDE 2       /* with WIFI_SOLVE_HPD and WIFI_F32: FP32 storage, FP64 arithmetic inside the solve (sigma2/|x|^2
-                                 * is below the FP32 resolution of R: the plain FP32 HPD solve is accurate to ~4e-3, the pivoted
-                                 * one to ~1e-1; WIDE to 1e-7).  For frames that share |tx_k|^2 see wifi_mmse_eig_*. */
+#define WIFI_SOLVE_HPD 1        /* R Hermitian PSD: un-pivoted blocked L D L^H with the trailing updates on the FP64 tensor path
+                                 * (DMMA), H = y - D z (growth factor 1) */
+#define WIFI_SOLVE_WIDE 2       /* accepted and ignored: FP32 storage + FP64 arithmetic is what WIFI_F32 does by default */
 #define WIFI_SOLVE_REFINE WIFI_SOLVE_WIDE   /* former name */
+#define WIFI_SOLVE_FAST32 4     /* explicit opt-in, WIFI_F32 only: FP32 ARITHMETIC inside the solve (register-resident L D L^H on the
+                                 * FP32 cores, 2x the throughput).  Documented accuracy: ~4e-3 with WIFI_SOLVE_HPD, ~1e-1 with
+                                 * WIFI_SOLVE_PIVOT at sigma2 = 1e-8 -- it does NOT meet the 1e-4 bound.  For frames that share
+                                 * |tx_k|^2 prefer wifi_mmse_eig_* (FP32 arithmetic, 1e-5, 20x faster). */
 
 /* wifi_chermitian_batch / wifi_cadd_batch semantics */
 #define WIFI_AS_WRITTEN 0       /* bit-compatible with utils.c:3-7 (Re-Im, real-valued) / utils.c:111-121 (M1+M1) */
@@ -125,6 +129,11 @@ int wifi_mmse_shared_apply_batch(wifi_ctx *ctx, wifi_dtype dt, const void *H_ls,
 /* fused: per-block LS divide rx/tx (main.c:83 arithmetic on all 53 bins) + the GEMM */
 int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                            int64_t frame_stride, void *H, int64_t n_frames);
+/* Shared, known tx block vector (training symbols; 53 double2, device): fold the LS divide into the installed filter once,
+ * W' = W diag(1/tx), then H[n][53] = rx[n][53] W'^T reads only rx -- 848 instead of 1 272 bytes per frame in FP32.  The
+ * filter of wifi_mmse_filter_form/_set stays installed for the per-frame-tx calls. */
+int wifi_mmse_filter_fold_tx(wifi_ctx *ctx, const void *tx_block_f64);
+int wifi_mmse_shared_rx_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx_symbols, int64_t frame_stride, void *H, int64_t n_frames);
 /* Per-frame case: A_f = R + diag(sigma2[f]/|tx_k|^2); solve A_f z = rx/tx; H = R z (= rx/tx - D_f z).
  * R in the storage dtype (53x53), sigma2 real [n] in the storage dtype; flags: WIFI_SOLVE_*. */
 int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols,
@@ -192,6 +201,8 @@ int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const v
 int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);
 int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                           int64_t frame_stride, void *H, int64_t n_frames);
+int wifi_mmse_filter_fold_tx_host(wifi_ctx *ctx, const void *tx_block_f64);
+int wifi_mmse_shared_rx_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx_symbols, int64_t frame_stride, void *H, int64_t n_frames);
 int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx_symbols, const void *rx_symbols,
                             int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames, int flags);
 int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
@@ -206,6 +217,11 @@ int wifi_cadd_host(wifi_ctx *ctx, wifi_dtype dt, int mode, const void *M1, int r
 int wifi_couter_host(wifi_ctx *ctx, wifi_dtype dt, const void *M1, int r1, int c1, const void *M2, int r2, int c2, void *res, int64_t batch);
 int wifi_cidentity_host(wifi_ctx *ctx, wifi_dtype dt, void *Id, int size, double scalar, int64_t batch);
 int wifi_cinverse_host(wifi_ctx *ctx, wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info_host);
+/* per-array staging target of one chunk of the `_host` pipeline (default 48 MiB; two chunks are in flight) */
+int wifi_set_host_chunk_bytes(wifi_ctx *ctx, size_t bytes);
+/* PCIe ceiling under the conditions of the `_host` pipeline: ONE pinned H2D copy of h2d_bytes and ONE D2H copy of d2h_bytes
+ * issued together on the pipeline's two streams; *ms = wall time until both are done (either size may be 0) */
+int wifi_pcie_probe(wifi_ctx *ctx, const void *h_src, void *h_dst, size_t h2d_bytes, size_t d2h_bytes, double *ms);
 /* pinned host memory for the `_host` calls (cudaHostAlloc / cudaFreeHost) */
 int wifi_host_alloc(void **p, size_t bytes);
 int wifi_host_free(void *p);

@@ -25,7 +25,8 @@ def build(force=False):
     so = os.path.join(HERE, "libwifi_oracle.so")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(HERE, "wifi_oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, "all"])
-    elif os.path.exists("/root/reference/main.c") and not os.path.exists(os.path.join(HERE, "_ref", "libwifi_ref.so")):
+    elif os.path.exists("/root/reference/main.c") and not all(
+            os.path.exists(os.path.join(HERE, "_ref", n)) for n in ("libwifi_ref.so", "libwifi_ref_O0.so", "libwifi_ref_omp.so")):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
@@ -213,20 +214,23 @@ class Oracle:
 
 
 class Reference:
-    """The reference's own compiled sequential code (oracle/_ref/libwifi_ref.so)."""
+    """The reference's own compiled sequential code (oracle/_ref/libwifi_ref.so, -O2; opt="O0": the same sources at -O0, which
+    is what the reference's build helper compile.c:25-30 produces)."""
 
     path = os.path.join(HERE, "_ref", "libwifi_ref.so")
+    path_O0 = os.path.join(HERE, "_ref", "libwifi_ref_O0.so")
 
     @classmethod
-    def available(cls):
-        if not os.path.exists(cls.path) and os.path.exists("/root/reference/main.c"):
+    def available(cls, opt="O2"):
+        p = cls.path if opt == "O2" else cls.path_O0
+        if not os.path.exists(p) and os.path.exists("/root/reference/main.c"):
             build()
-        return os.path.exists(cls.path)
+        return os.path.exists(p)
 
-    def __init__(self):
-        if not self.available():
-            raise RuntimeError("oracle/_ref/libwifi_ref.so not built (needs /root/reference)")
-        self.lib = C.CDLL(self.path)
+    def __init__(self, opt="O2"):
+        if not self.available(opt):
+            raise RuntimeError("oracle/_ref/libwifi_ref%s.so not built (needs /root/reference)" % ("" if opt == "O2" else "_O0"))
+        self.lib = C.CDLL(self.path if opt == "O2" else self.path_O0)
         self.lib.ref_ow2.restype = C.c_double
         self.lib.ref_sinc.restype = C.c_double
 
@@ -297,3 +301,32 @@ class Reference:
         ts = np.empty(NSC * NBLK, np.complex128); rs = np.empty(NSC * NBLK, np.complex128)
         self.lib.ref_inputs(*(a.ctypes.data_as(_dp) for a in (tp, rp, ts, rs)))
         return dict(ow2=self.lib.ref_ow2(), tx_preamble_fft=tp, rx_preamble_fft=rp, tx_symb=ts, rx_symb=rs)
+
+
+class ReferenceOpenMP:
+    """The reference's OpenMP build as it is (main_openmp.c:70-176 + the _omp twins of utils.c; oracle/_ref/libwifi_ref_omp.so):
+    every estimator call spawns its own 53-thread intra-frame team.  Timed by bench.py on a small N'."""
+
+    path = os.path.join(HERE, "_ref", "libwifi_ref_omp.so")
+
+    @classmethod
+    def available(cls):
+        if not os.path.exists(cls.path) and os.path.exists("/root/reference/main.c"):
+            build()
+        return os.path.exists(cls.path)
+
+    def __init__(self):
+        if not self.available():
+            raise RuntimeError("oracle/_ref/libwifi_ref_omp.so not built (needs /root/reference)")
+        self.lib = C.CDLL(self.path)
+
+    def set_threads(self, n):
+        self.lib.refomp_set_threads(C.c_int(int(n)))
+
+    def estimate(self, which, a, b):
+        code = {"lt_ls": 0, "ps_linear": 1, "ps_cubic": 2, "ps_sinc": 3}[which]
+        x, px = _c(a); y, py = _c(b)
+        n = x.size // NSC
+        H = np.empty((n, NSC), np.complex128)
+        self.lib.refomp_estimate(C.c_int(code), px, py, H.ctypes.data_as(_dp), C.c_long(n))
+        return H.reshape(x.shape)

@@ -70,3 +70,49 @@ def test_dropin_symbols(wifi):
                  "WiFi_channel_estimation_PS_Sinc", "WiFi_channel_estimation_PS_MMSE", "hermitian", "multiply",
                  "multiplyVxVeqM", "identity", "addition", "inverse"):
         assert re.search(r"\bT %s\b" % name, out), name
+
+
+def test_dropin_cxx_mangled_symbols(wifi):
+    """The C++-linkage shim carries the names an UNMODIFIED reference object file asks for: the reference is C++ compiled by
+    g++ / mpiCC (compile.c:25-30), so main.c / main_openmp.c reference the mangled utils.h:38-60 and main.c:4-8 names."""
+    so = os.path.join(PKG, "libwifi_dropin_cxx.so")
+    if not os.path.exists(so):
+        pytest.skip("C++ drop-in shim not built")
+    mangled = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    for name in ("_Z7inversePPCeiS1_", "_Z8multiplyPPCeiiS1_iiS1_", "_Z9hermitianPPCeiiS1_"):          # SURVEY 8(b), nm of the rebuilt utils.o
+        assert re.search(r"\bT %s\b" % name, mangled), name
+    demangled = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True).stdout
+    ldc = r"long double _Complex"
+    for proto in (r"hermitian\(%s\*\*, int, int, %s\*\*\)" % (ldc, ldc),
+                  r"multiply\(%s\*\*, int, int, %s\*\*, int, int, %s\*\*\)" % (ldc, ldc, ldc),
+                  r"multiplyVxVeqM\(%s\*\*, int, int, %s\*\*, int, int, %s\*\*\)" % (ldc, ldc, ldc),
+                  r"identity\(%s\*\*, int, double\)" % ldc,
+                  r"addition\(%s\*\*, int, int, %s\*\*, int, int, %s\*\*\)" % (ldc, ldc, ldc),
+                  r"inverse\(%s\*\*, int, %s\*\*\)" % (ldc, ldc),
+                  r"WiFi_channel_estimation_LT_LS\(%s\*, %s\*, %s\*\)" % (ldc, ldc, ldc),
+                  r"WiFi_channel_estimation_PS_Linear\(%s\*, %s\*, %s\*\)" % (ldc, ldc, ldc),
+                  r"WiFi_channel_estimation_PS_Cubic\(%s\*, %s\*, %s\*\)" % (ldc, ldc, ldc),
+                  r"WiFi_channel_estimation_PS_Sinc\(%s\*, %s\*, %s\*\)" % (ldc, ldc, ldc),
+                  r"WiFi_channel_estimation_PS_MMSE\(%s\*, %s\*, %s\*\*, double, %s\*, %s\*\)" % (ldc, ldc, ldc, ldc, ldc)):
+        assert re.search(r"\bT " + proto, demangled), proto
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "main.c")), reason="the reference is not mounted on this box")
+def test_unmodified_reference_main_links_against_the_cxx_dropin(wifi, tmp_path):
+    """the reference's own main.c, compiled as it is (g++ -std=gnu++98, stub mpi.h because utils.h:1
+    includes it), links against libwifi_dropin_cxx.so with NO utils.o -- every estimator and utils symbol it needs comes from
+    the drop-in.  (Running it needs a GPU; tests/test_gpu_host_driver.py does that on the B200 box.)"""
+    so = os.path.join(PKG, "libwifi_dropin_cxx.so")
+    if not os.path.exists(so):
+        pytest.skip("C++ drop-in shim not built")
+    obj, exe = str(tmp_path / "main.o"), str(tmp_path / "main")
+    subprocess.check_call(["g++", "-std=gnu++98", "-w", "-I" + os.path.join(ROOT, "oracle", "stub"), "-I" + REF, "-c", os.path.join(REF, "main.c"), "-o", obj])
+    r = subprocess.run(["g++", "-o", exe, obj, "-L" + PKG, "-lwifi_dropin_cxx", "-lwifi_dropin", "-lwifi_b200", "-Wl,-rpath," + PKG, "-lm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    dyn = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for name in ("_Z8multiplyPPCeiiS1_iiS1_", "_Z7inversePPCeiS1_", "_Z9hermitianPPCeiiS1_"):       # main.c:183-205 calls them
+        assert name in dyn, name

@@ -81,7 +81,8 @@ def test_mmse_shared_1mi_frames(ctx, oracle, prec):
     if prec == "f64":
         assert rel_err(got, ref) < 1e-10
     else:
-        assert rel_err(got, ref, 1e-2) < 1e-4
+        print("mmse_shared f32, %d sampled frames of %d: rel_err %.3g at floor 1e-3" % (len(pick), n, rel_err(got, ref, 1e-3)))
+        assert rel_err(got, ref, 1e-3) < 1e-4
     # dense copy of block 0 == in-place read, bit for bit; scale by 2 == exact; halves == whole
     tx0d = fr["tx_symb"][:, 0, :].contiguous(); rx0d = fr["rx_symb"][:, 0, :].contiguous()
     Hd = ctx.mmse_shared(tx0d, rx0d)

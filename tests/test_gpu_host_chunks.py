@@ -1,6 +1,6 @@
-"""The *_host entry points with MANY chunks in flight (WIFI_B200_HOST_CHUNK_MB=1: two pipeline streams alternate, chunks of ~2 400
-frames): every result must equal the device-pointer call bit for bit -- this is what catches per-context scratch shared by the
-two streams.  Runs in a subprocess because the chunk size is read once per process."""
+"""The *_host entry points with MANY chunks in flight (wifi_set_host_chunk_bytes(1 MiB): two pipeline streams alternate, chunks
+of ~2 400 frames): every result must equal the device-pointer call bit for bit -- this is what catches per-context scratch
+shared by the two streams.  Runs in a subprocess so that a device fault cannot take the pytest process with it."""
 import os
 import subprocess
 import sys
@@ -16,6 +16,7 @@ sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
 import numpy as np, torch, synth
 wifi = importlib.import_module("80211parallelestimation_b200")
 ctx = wifi.WifiContext(0)
+ctx.set_host_chunk_bytes(1 << 20)
 n = 20011
 for prec, cdt in (("f32", np.complex64), ("f64", np.complex128)):
     fr = ctx.synth_frames(n, prec, per_frame_sigma=True)
@@ -51,7 +52,6 @@ print("host chunks ok")
 
 
 def test_host_entry_points_with_many_chunks():
-    env = dict(os.environ, WIFI_B200_HOST_CHUNK_MB="1")
-    out = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, ROOT)], capture_output=True, text=True, timeout=600)
     print(out.stdout[-2000:], out.stderr[-3000:])
     assert out.returncode == 0 and "host chunks ok" in out.stdout

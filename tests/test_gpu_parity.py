@@ -6,13 +6,13 @@ Tolerances (north star): FP64 mode <= 1e-10, FP32 mode <= 1e-4, relative per sub
 |d| / max(|ref_k|, floor * max_k|ref|)  (synth.rel_err) with floor = 1e-3 (FP64) -- the survey's floor for outputs that
 pass through ~0.  FP32 inputs are rounded to FP32 BEFORE the oracle sees them, so both sides work on the same numbers.
 Stated exceptions (DESIGN.md "Accuracy"):
-  * FP32 shared-filter MMSE (3xTF32 tensor-core GEMM): floor = 1e-2, i.e. bins more than 40 dB below the frame's peak
-    are compared absolutely; additionally |d| <= 5e-6 of the frame's peak everywhere.  An FP32 dot product of 106 terms
-    cannot do better than ~7e-5 at the 1e-3 floor, whatever the hardware.
+  * none for the FP32 shared-filter MMSE (3xTF32 tensor-core GEMM): it is asserted at the survey's floor 1e-3 like everything
+    else (round 1 used floor 1e-2), and additionally |d| <= 5e-6 of the frame's peak everywhere.
   * FP64 per-frame solve: <= 1e-10 for sigma2 >= 1e-7 (per-bin SNR <= 51 dB); 5e-10 down to sigma2 = 1e-8, where
     cond(R + D) ~ 6e7 sets the floor of ANY FP64 solve of this formulation (eps * cond * |noise|/|H|).
-  * FP32 per-frame solve without refinement: the sigma2/|x|^2 diagonal (1e-10..1e-7) is lost against R (1e-4) in FP32;
-    stated bound 0.3, tested; use FP64 or WIFI_SOLVE_REFINE.
+  * FP32 per-frame solve: complex64 arrays are solved in FP64 arithmetic by default (1e-4 asserted, ~6e-8 measured).  The
+    WIFI_SOLVE_FAST32 opt-in (FP32 arithmetic) loses the sigma2/|x|^2 diagonal (1e-10..1e-7) against R (1e-4): documented
+    bounds 3e-2 (HPD) / 0.3 (PIVOT), tested as such -- it is not a parity mode.
 """
 import importlib
 
@@ -176,7 +176,7 @@ def test_f32_views_at_odd_frames(ctx, oracle, n):
     W = host(ctx.mmse_filter_form(dev(R), dev(dd)))
     got = host(ctx.mmse_shared(v["tx_symb"].reshape(-1), v["rx_symb"].reshape(-1), frame_stride=15 * NSC, n_frames=n))
     ref = oracle.mmse_apply(W, h["rx_symb"][:, 0, :].astype(complex) / h["tx_symb"][:, 0, :].astype(complex))
-    assert rel_err(got, ref, 1e-2) < TOL["f32"]
+    assert rel_err(got, ref, 1e-3) < TOL["f32"]
 
 
 # ------------------------------------------------------------------ receiver front-end
@@ -269,7 +269,8 @@ def test_mmse_shared(ctx, oracle, prec, n):
     hls = (r32(rx, prec) / r32(tx, prec))
     ref = oracle.mmse_apply(W, hls)
     got = host(ctx.mmse_shared(dev(tx), dev(rx)))
-    floor = 1e-3 if prec == "f64" else 1e-2
+    floor = 1e-3                      # the survey's floor, for FP32 (3xTF32) too: measured 2.8e-5 .. 7e-5
+    print("mmse_shared %s n=%d: rel_err %.3g at floor 1e-3" % (prec, n, rel_err(got, ref, floor)))
     assert rel_err(got, ref, floor) < TOL[prec]
     got2 = host(ctx.mmse_shared_apply(dev(hls.astype(CDT[prec]))))
     ref2 = oracle.mmse_apply(W, r32(hls.astype(CDT[prec]), prec))
@@ -304,40 +305,6 @@ def test_mmse_perframe_f64(ctx, wifi, oracle, flags, n):
             assert rel_err(got[lo], ref[lo]) < 5e-10
 
 
-_CUDA_CORE_SOLVE = r"""
-import importlib, sys
-import numpy as np, torch
-sys.path[:0] = [%r, %r]
-import synth
-from oracle.pyoracle import Oracle
-wifi = importlib.import_module("80211parallelestimation_b200")
-ctx, o = wifi.WifiContext(0), Oracle()
-fr = synth.make_frames(61, seed=71, sigma2="perframe")
-tx, rx, s2 = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy(), fr["sigma2"]
-dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
-for R in (synth.channel_covariance(), synth.random_hpd(np.random.default_rng(5))):
-    ref = o.mmse_perframe(R, tx, rx, s2)
-    got = ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2), flags=wifi.SOLVE_HPD).cpu().numpy()
-    assert synth.rel_err(got, ref) < 5e-10, synth.rel_err(got, ref)
-    t32, r32, s32, R32 = tx.astype(np.complex64), rx.astype(np.complex64), s2.astype(np.float32), R.astype(np.complex64)
-    ref32 = o.mmse_perframe(R32.astype(complex), t32.astype(complex), r32.astype(complex), s32.astype(np.float64))
-    got32 = ctx.mmse_perframe(dev(R32), dev(t32), dev(r32), dev(s32), flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE).cpu().numpy()
-    assert synth.rel_err(got32, ref32) < 1e-6, synth.rel_err(got32, ref32)
-print("ok")
-"""
-
-
-def test_mmse_perframe_cuda_core_variant():
-    """WIFI_HPD_CFG=10 selects the CUDA-core L D L^H kernel that the DMMA kernel replaced for FP64 arithmetic (kept for A/B
-    timing); the variant is chosen once per process, hence the subprocess."""
-    import os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, WIFI_HPD_CFG="10")
-    r = subprocess.run([sys.executable, "-c", _CUDA_CORE_SOLVE % (root, os.path.join(root, "tests"))], env=env,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:]
-
-
 def test_mmse_perframe_kat(ctx, wifi, gold):
     k = gold["mmse_kat"]
     for fl in (wifi.SOLVE_PIVOT, wifi.SOLVE_HPD):
@@ -353,21 +320,27 @@ def test_mmse_cconv_inputs_h(ctx, gold):
     assert got[0][26] == 0
 
 
-@pytest.mark.parametrize("flags,bound", [("pivot", 0.3), ("hpd", 3e-2), ("hpd_wide", 1e-6)])
+@pytest.mark.parametrize("flags,bound", [("pivot", 1e-4), ("hpd", 1e-4), ("hpd_wide", 1e-4), ("pivot_fast32", 0.3), ("hpd_fast32", 3e-2)])
 def test_mmse_perframe_f32_stated_accuracy(ctx, wifi, oracle, flags, bound):
     """FP32 storage.  sigma2/|x|^2 (1e-10..1e-7) is below the FP32 resolution of R (1e-4), so an FP32 elimination of R + D
-    perturbs the small eigenvalues by O(1) at the 60 dB end:
-      * pivoted LU, H = R z:            stated bound 0.3   (measured 1e-2 .. 1.3e-1)
-      * HPD solve, H = y - D z:         stated bound 3e-2  (measured 3.7e-3: the error enters as D dz, not R dz)
-      * HPD | WIDE (FP64 arithmetic):   stated bound 1e-6  (measured 5.8e-8) -- the mode that meets the 1e-4 north-star bound."""
+    perturbs the small eigenvalues by O(1) at the 60 dB end.  Every DEFAULT mode therefore runs the solve in
+    FP64 arithmetic on the FP32 arrays and must meet the north-star FP32 bound of 1e-4 (measured 5.8e-8 for HPD); FP32
+    arithmetic is the explicit WIFI_SOLVE_FAST32 opt-in with a documented, weaker accuracy:
+      * FAST32 | PIVOT, H = R z:       stated bound 0.3   (measured 1e-2 .. 1.3e-1)
+      * FAST32 | HPD,   H = y - D z:   stated bound 3e-2  (measured 3.7e-3: the error enters as D dz, not R dz)."""
     fr = synth.make_frames(96, seed=77, sigma2="perframe", dtype=np.complex64)
     tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
     s2 = fr["sigma2"].astype(np.float32)
     R = synth.channel_covariance().astype(np.complex64)
     ref = oracle.mmse_perframe(R.astype(np.complex128), tx.astype(np.complex128), rx.astype(np.complex128), s2.astype(np.float64))
-    fl = {"pivot": wifi.SOLVE_PIVOT, "hpd": wifi.SOLVE_HPD, "hpd_wide": wifi.SOLVE_HPD | wifi.SOLVE_WIDE}[flags]
+    fl = {"pivot": wifi.SOLVE_PIVOT, "hpd": wifi.SOLVE_HPD, "hpd_wide": wifi.SOLVE_HPD | wifi.SOLVE_WIDE,
+          "pivot_fast32": wifi.SOLVE_PIVOT | wifi.SOLVE_FAST32, "hpd_fast32": wifi.SOLVE_HPD | wifi.SOLVE_FAST32}[flags]
     got = host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2), flags=fl))
-    assert rel_err(got, ref) < bound
+    err = rel_err(got, ref)
+    print("mmse_perframe f32 %s: rel_err %.3g (bound %.0e)" % (flags, err, bound))
+    assert err < bound
+    if "fast32" not in flags:
+        assert err < 1e-5        # FP64 arithmetic on FP32 inputs: the output rounding is all that is left
 
 
 @pytest.mark.parametrize("prec,flags", [("f64", "hpd"), ("f32", "hpd_wide")])
@@ -564,7 +537,7 @@ def test_host_entry_points(ctx, wifi, oracle, prec):
     W = ctx.mmse_filter_form(R, d)
     assert rel_err(W, oracle.mmse_filter(R, d), floor=1e-3) < 1e-6
     H = ctx.mmse_shared(txs[:, 0, :].copy(), rxs[:, 0, :].copy())
-    assert rel_err(H, oracle.mmse_apply(W, r32(rxs[:, 0, :], prec) / r32(txs[:, 0, :], prec)), 1e-3 if prec == "f64" else 1e-2) < TOL[prec]
+    assert rel_err(H, oracle.mmse_apply(W, r32(rxs[:, 0, :], prec) / r32(txs[:, 0, :], prec)), 1e-3) < TOL[prec]
     if prec == "f64":
         Hp = ctx.mmse_perframe(R, txs[:, 0, :].copy(), rxs[:, 0, :].copy(), fr["sigma2"])
         assert rel_err(Hp, oracle.mmse_perframe(R, txs[:, 0, :], rxs[:, 0, :], fr["sigma2"])) < 5e-10
