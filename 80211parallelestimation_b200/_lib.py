@@ -29,6 +29,7 @@ SIGNATURES = {
     "wifi_lt_ls_batch": [_vp, _i, _vp, _vp, _vp, _i64],
     "wifi_ps_batch": [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i64],
     "wifi_equalize_batch": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
+    "wifi_estimate_all_batch": [_vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_frontend_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_filter_form": [_vp, _vp, _vp, _vp],
     "wifi_mmse_filter_set": [_vp, _vp],
@@ -54,6 +55,7 @@ SIGNATURES = {
     "wifi_lt_ls_host": [_vp, _i, _vp, _vp, _vp, _i64],
     "wifi_ps_host": [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp, _i64],
     "wifi_equalize_host": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
+    "wifi_estimate_all_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_frontend_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_filter_form_host": [_vp, _vp, _vp, _vp],
     "wifi_mmse_shared_host": [_vp, _i, _vp, _vp, _i64, _vp, _i64],

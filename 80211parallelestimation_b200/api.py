@@ -173,6 +173,33 @@ class WifiContext:
     def ps_sinc(self, tx, rx, **kw):
         return self.ps(tx, rx, ("sinc",), **kw)["sinc"]
 
+    def estimate_all(self, tx_pre, rx_pre, tx_symbols, rx_symbols, frame_stride=None, n_frames=None, equalize=True, out=None):
+        """All five estimators (LT_LS, PS_Linear, PS_Cubic, PS_Sinc, shared-filter PS_MMSE) and, for whole frames, the equalizer
+        (WiFi_RX.m:47-60) in one call.  Returns a dict with keys lt_ls, linear, cubic, sinc, mmse (+ eq)."""
+        tp, rp, tx, rx = _Arg(tx_pre), _Arg(rx_pre), _Arg(tx_symbols), _Arg(rx_symbols)
+        dev, dt = _same(tp, rp, tx, rx)
+        if frame_stride is None:
+            frame_stride = FRAME if (len(tx.shape) == 3 and tx.shape[-2:] == (NBLK, NSC)) else NSC
+        if n_frames is None:
+            n_frames = tp.size // NSC
+        do_eq = bool(equalize) and frame_stride == FRAME
+        o = dict(out) if out else {}
+        for k in ("lt_ls", "linear", "cubic", "sinc", "mmse"):
+            if k not in o:
+                o[k] = tp.empty_like((n_frames, NSC))
+        if do_eq and "eq" not in o:
+            o["eq"] = tp.empty_like((n_frames, NBLK, NSC))
+        self._sync_stream(dev)
+        if dev:
+            self._ck(self.lib.wifi_estimate_all_batch(self.h, dt, tp.ptr, rp.ptr, tx.ptr, rx.ptr, frame_stride, _ptr(o["lt_ls"]), _ptr(o["linear"]),
+                                                      _ptr(o["cubic"]), _ptr(o["sinc"]), _ptr(o["mmse"]), _ptr(o["eq"]) if do_eq else None, n_frames))
+        else:
+            if frame_stride != FRAME:
+                raise TypeError("host arrays: pass whole frames [n][15][53]")
+            self._ck(self.lib.wifi_estimate_all_host(self.h, dt, tp.ptr, rp.ptr, tx.ptr, rx.ptr, _ptr(o["lt_ls"]), _ptr(o["linear"]), _ptr(o["cubic"]),
+                                                     _ptr(o["sinc"]), _ptr(o["mmse"]), _ptr(o["eq"]) if do_eq else None, n_frames))
+        return o
+
     def frontend(self, packet, lptot, want_ow2=True, out=None):
         """Receiver front-end (WiFi_blocks_extraction.m, WiFi_RX.m:19-31) for one side of n frames: packet [n][1200],
         lptot [n][160] -> (symb [n][15][53], pre_fft [n][53], ow2 [n] or None)."""

@@ -287,6 +287,11 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
 {
     if (!ctx->eig_valid) return fail(ctx, WIFI_ERR_STATE, "no eigen-domain operands installed: call wifi_mmse_eig_prepare first");
     if (n == 0) return WIFI_OK;
+    // Two launches, u = (rx/tx) G^T through a scratch array.  Measured and rejected (round 2): ONE tcgen05 kernel that keeps u in
+    // tensor memory and reads the same filter images transposed for the second product (G2 = M G^H, MN-major operand descriptor):
+    // kind::tf32 with an MN-major, un-swizzled B operand returned zeros on this hardware, a second image pair does not fit next to
+    // the staging buffers (308 KB), and with the A region of TMEM shared by both products the tiles serialise: 0.516 ms per 1 Mi
+    // frames (2.0 G frames/s) against 0.65 ms for the two launches -- not worth a cta_group::2 rewrite.
     const size_t need = (size_t)n * WIFI_NSC * esize(dt);
     if (ctx->eig_u_bytes[slot] < need) {
         CK(cudaStreamSynchronize(s));
@@ -297,7 +302,7 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
     void *U = ctx->eig_u[slot];
     int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, U, n, s);            // u = (rx/tx) G^T
     if (rc) return rc;
-    // one kernel: v = s (.) (u - p z_d) in the converter / producer stage, c = v G2^T on the tensor cores, H = rx/tx - c in the epilogue
+    // v = s (.) (u - p z_d) in the converter / producer stage, c = v G2^T on the tensor cores, H = rx/tx - c in the epilogue
     Timed t(ctx, s);
     if (dt == WIFI_F32)
         CK(launch_mmse_shared_tc_resid(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p,
@@ -353,6 +358,38 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
 
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                          const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check);
+
+// BASELINE configs[4]: all five estimators (+ the equalizer) of n frames behind one call: LT_LS, the fused pilot-LS + three
+// interpolators, the shared-filter PS_MMSE GEMM (reading block 0 of tx / rx in place) and the equalizer -- four launches, each
+// at >= 100 % of the measured HBM copy rate on its own bytes.  Two fusions were built, measured on B200 and rejected (round 2,
+// 1 Mi frames, FP32; the four launches take 2.93 ms):
+//   * LT_LS and the interpolators emitted by the GEMM kernel's converter warps from the block LS values they stage (one launch
+//     for the five estimates): those 8 warps are latency-bound, the launch took 1.00 ms against 0.83 ms for the three kernels;
+//   * a "frame finish" pass (LT_LS + interpolators + equalizer, no estimate re-read: 1 912 instead of 2 022 complex values per
+//     frame), as a shared-memory tile kernel with flat 16-byte vectors (3.8 ms) and as one thread per (frame, sub-carrier) with
+//     the estimates in registers (2.73 ms at 6.0 TB/s of DRAM traffic; 8-byte accesses, 27 warps per SM): 3.05 ms with the GEMM.
+static int estimate_all(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx, const void *rx, int64_t frame_stride,
+                        void *H_lt, void *H_lin, void *H_cub, void *H_sinc, void *H_mmse, void *eq, int64_t n, cudaStream_t s)
+{
+    if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
+    if (n == 0) return WIFI_OK;
+    { Timed t(ctx, s); CK(launch_lt_ls(dt, tx_pre, rx_pre, H_lt, n, s)); }
+    { Timed t(ctx, s); CK(launch_ps(dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx, rx, frame_stride, H_lin, H_cub, H_sinc, n, ctx->tab, s)); }
+    int rc = gemm_with(ctx, ctx->img, dt, tx, rx, frame_stride, H_mmse, n, s);
+    if (rc) return rc;
+    if (eq) { Timed t(ctx, s); CK(launch_equalize(dt, rx, H_lt, H_lin, eq, n, s)); }      // WiFi_RX.m:60: H_EST_LT_LS and H_EST_PS_Linear
+    return WIFI_OK;
+}
+
+int wifi_estimate_all_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx_symbols, const void *rx_symbols,
+                            int64_t frame_stride, void *H_lt, void *H_linear, void *H_cubic, void *H_sinc, void *H_mmse, void *eq, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    NEED(n == 0 || (tx_pre && rx_pre && tx_symbols && rx_symbols && H_lt && H_linear && H_cubic && H_sinc && H_mmse));
+    NEED(!eq || frame_stride == WIFI_FRAME);                  // the equalizer works on whole frames [n][15][53]
+    return estimate_all(ctx, dt, tx_pre, rx_pre, tx_symbols, rx_symbols, frame_stride, H_lt, H_linear, H_cubic, H_sinc, H_mmse, eq, n, ctx->stream);
+}
 
 // R_f = H_ls H_ls^H: closed form (wifi_ls.cu mmse_rank1_kernel)
 static int mmse_cconv(wifi_ctx *ctx, wifi_dtype dt, int matlab, const void *tx, const void *rx, int64_t frame_stride, const void *ow2,
@@ -725,6 +762,34 @@ int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const vo
                          [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
                              return mmse_shared(ctx, dt, d[0], d[1], WIFI_NSC, d[2], nc, s);
                          });
+}
+
+int wifi_estimate_all_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx_frames, const void *rx_frames,
+                           void *H_lt, void *H_linear, void *H_cubic, void *H_sinc, void *H_mmse, void *eq, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (dt == WIFI_F32 || dt == WIFI_F64));
+    NEED(n == 0 || (tx_pre && rx_pre && tx_frames && rx_frames && H_lt && H_linear && H_cubic && H_sinc && H_mmse));
+    if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
+    CK(cudaStreamSynchronize(ctx->stream));   // the filter images were built on the ctx stream
+    // whole frames [n][15][53] on the host; only block 0 of tx crosses the bus, rx crosses whole when the equalizer is asked for
+    const size_t row = WIFI_NSC * esize(dt), frow = WIFI_FRAME * esize(dt);
+    std::vector<Arr> arrs = {in_arr(tx_pre, row, row), in_arr(rx_pre, row, row), in_arr(tx_frames, row, frow), in_arr(rx_frames, eq ? frow : row, frow),
+                             out_arr(H_lt, row), out_arr(H_linear, row), out_arr(H_cubic, row), out_arr(H_sinc, row), out_arr(H_mmse, row)};
+    if (eq) arrs.push_back(out_arr(eq, frow));
+    return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+        // tx is staged as block vectors (stride 53); rx too without the equalizer, as whole frames (stride 795) with it
+        if (!eq) return estimate_all(ctx, dt, d[0], d[1], d[2], d[3], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s);
+        // with the equalizer the estimators want tx and rx at ONE stride: block 0 of rx is gathered on the device into the eq
+        // staging buffer, which is free until the equalizer (the last kernel of the chunk) overwrites it
+        cudaError_t e = cudaMemcpy2DAsync(d[9], row, d[3], frow, row, (size_t)nc, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
+        int rc = estimate_all(ctx, dt, d[0], d[1], d[2], d[9], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s);
+        if (rc) return rc;
+        Timed t(ctx, s);
+        CK(launch_equalize(dt, d[3], d[4], d[5], d[9], nc, s));
+        return (int)WIFI_OK;
+    });
 }
 
 int wifi_mmse_filter_fold_tx_host(wifi_ctx *ctx, const void *tx_block_f64)

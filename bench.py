@@ -311,16 +311,13 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
         X.rate("equalize_" + prec, lambda: ctx.equalize(fr["rx_symb"], H, outs["linear"], out=eq), n, 1696 * cbytes, config="configs[4]")
         # BASELINE configs[4] per GPU: all five estimators + the equalizer on whole frames, in place (block 0 at stride 795)
         Hm5 = torch.empty_like(H)
-        txf, rxf = fr["tx_symb"].reshape(-1), fr["rx_symb"].reshape(-1)
-
-        def all5():
-            ctx.lt_ls(fr["tx_pre"], fr["rx_pre"], out=H)
-            ctx.ps(fr["tx_symb"], fr["rx_symb"], out=outs)
-            ctx.mmse_shared(txf, rxf, frame_stride=NBLK * NSC, n_frames=n, out=Hm5)
-            ctx.equalize(fr["rx_symb"], H, outs["linear"], out=eq)
-        X.rate("all5_plus_equalizer_" + prec, all5, n, (159 + 167 + 159 + 1696) * cbytes, config="configs[4]",
-               note="LT_LS + PS_Linear/Cubic/Sinc + shared-filter PS_MMSE + equalizer on whole frames, 4 launches per pass")
-        del eq, Hm5, txf, rxf
+        o5 = {"lt_ls": H, "linear": outs["linear"], "cubic": outs["cubic"], "sinc": outs["sinc"], "mmse": Hm5, "eq": eq}
+        X.rate("all5_plus_equalizer_" + prec, lambda: ctx.estimate_all(fr["tx_pre"], fr["rx_pre"], fr["tx_symb"], fr["rx_symb"], out=o5), n,
+               2014 * cbytes, config="configs[4]",
+               note="LT_LS + PS_Linear/Cubic/Sinc + shared-filter PS_MMSE + equalizer on whole frames through wifi_estimate_all_batch (4 launches); "
+                    "hbm_frac is on the algorithmic bytes of a single fused pass (read tx_pre, rx_pre, block 0 of tx, rx_symb = 954 c, write five estimates "
+                    "+ eq = 1 060 c); the four kernels move 2 181 c (the equalizer re-reads H_lt, H_linear; block 0 of rx is read three times)")
+        del eq, Hm5, o5
         tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
         del fr
         Hm = torch.empty_like(tx0)

@@ -8,17 +8,21 @@
  *           [N g/G, N (g+1)/G) of the global synthetic sequence, no exchange on the estimation path; the per-shard error
  *           statistics (4 doubles per device) are summed on the host.
  *
- *   part 3  (--file in out) frame-file pipeline: a WIFI_FILE_FREQ or WIFI_FILE_TIME file (include/wifi_frame_file.h) is
- *           read in chunks into pinned buffers, copied to the device, run through the front-end (TIME files), all five
- *           estimators (PS_MMSE in main.c:148's calling convention, R_f = H_lt H_lt^H) and the equalizer with the
- *           intermediates staying in HBM, and the results are written as a WIFI_FILE_EST file.
+ *   part 3  (--file in out [gpus]) streaming frame-file pipeline: a WIFI_FILE_FREQ or WIFI_FILE_TIME file
+ *           (include/wifi_frame_file.h) is sharded by contiguous frame ranges over the GPUs; per GPU a reader thread, a
+ *           dispatcher and a writer thread share a ring of pinned slots, so file reads, H2D, the front-end (TIME files), all
+ *           five estimators (PS_MMSE in main.c:148's calling convention, R_f = H_lt H_lt^H), the equalizer, D2H and file
+ *           writes of different chunks overlap; the results are written as a WIFI_FILE_EST file.
  *
  *   usage: wifi_host_main [frames_total=4194304] [fixture=tests/golden/inputs_h_frame.f64]
- *          wifi_host_main --file frames.bin estimates.bin
+ *          wifi_host_main --file frames.bin estimates.bin [max_gpus]
  */
 #include <complex.h>
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <pthread.h>
+#include <semaphore.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -108,95 +112,234 @@ static void *shard_main(void *arg)
     return NULL;
 }
 
-/* ---- part 3: frame-file pipeline ------------------------------------------------------------------------ */
-#define FCK(x) do { int rc_ = (x); if (rc_) { fprintf(stderr, "%s:%d: %s -> %d (%s)\n", __FILE__, __LINE__, #x, rc_, ctx ? wifi_last_error(ctx) : ""); return 1; } } while (0)
-#define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d: %s -> %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return 1; } } while (0)
+/* ---- part 3: frame-file pipeline: streaming, one shard of the file per GPU ----------------------------------------
+ * Every GPU g of G takes the contiguous frame range [n g/G, n (g+1)/G) of the file.  Per GPU three threads share a ring of
+ * FP_SLOTS slots (pinned input planes, pinned output planes, device buffers, one CUDA stream each):
+ *     reader      pread()s the four input planes of the next chunk into a free slot's pinned buffers
+ *     dispatcher  enqueues H2D copies, the kernels and the D2H copies of that slot on the slot's stream (never blocks on the GPU)
+ *     writer      waits for the slot's event and pwrite()s the seven output planes, then frees the slot
+ * so file reads, PCIe traffic in both directions, kernels and file writes of different chunks overlap.  Planes are whole
+ * arrays in the file, so a chunk is four preads at four offsets and seven pwrites. */
+#define FCK(x) do { int rc_ = (x); if (rc_) { fprintf(stderr, "%s:%d: %s -> %d (%s)\n", __FILE__, __LINE__, #x, rc_, ctx ? wifi_last_error(ctx) : ""); w->rc = 1; goto done; } } while (0)
+#define CCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d: %s -> %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); w->rc = 1; goto done; } } while (0)
+#define FP_SLOTS 3
+#define FP_CHUNK 16384L
 
-static int file_pipeline(const char *in_path, const char *out_path)
+typedef struct {
+    void *hin[4], *hout[7];
+    void *din[4], *dsymb[2], *dpre[2], *dow2, *dH[5], *deq, *dblk;
+    cudaStream_t st;
+    cudaEvent_t done;
+    long f0, nc;
+} fp_slot;
+
+typedef struct fp_worker {
+    int dev, ndev, fd_in, fd_out, rc;
+    wifi_dtype dt; int kind; size_t es; long n, lo, hi, nchunks;
+    size_t in_w[4], in_off[4], out_w[7], out_off[7];       /* plane widths in values per frame (ow2: real) and file offsets */
+    fp_slot slot[FP_SLOTS];
+    sem_t s_free, s_free1, s_filled, s_submitted;
+    double t_read, t_write, pcie_ms, t_start, t_end; size_t pcie_h2d, pcie_d2h;
+} fp_worker;
+typedef struct { fp_worker *w; int part; } fp_reader_arg;
+
+static size_t out_bytes(const fp_worker *w, int i) { return i == 6 ? w->es / 2 : w->out_w[i] * w->es; }     /* per frame */
+
+/* two readers per GPU: reader `part` fills planes part and part + 2 of every chunk (tx side / rx side) */
+static void *fp_reader(void *arg)
 {
-    wifi_ctx *ctx = NULL;
-    FILE *fi = fopen(in_path, "rb");
-    if (!fi) { fprintf(stderr, "cannot open %s\n", in_path); return 1; }
-    wifi_file_header h;
-    if (fread(&h, sizeof h, 1, fi) != 1 || memcmp(h.magic, WIFI_FILE_MAGIC, 8) || h.dtype > 1 || h.kind > WIFI_FILE_TIME) {
-        fprintf(stderr, "%s: not a FREQ/TIME frame file\n", in_path); fclose(fi); return 1;
+    fp_worker *w = ((fp_reader_arg *)arg)->w;
+    const int part = ((fp_reader_arg *)arg)->part;
+    for (long c = 0; c < w->nchunks; ++c) {
+        sem_wait(part ? &w->s_free1 : &w->s_free);
+        fp_slot *s = &w->slot[c % FP_SLOTS];
+        const long f0 = w->lo + c * FP_CHUNK, nc_ = w->hi - f0 < FP_CHUNK ? w->hi - f0 : FP_CHUNK;
+        if (!part) { s->f0 = f0; s->nc = nc_; }
+        double t0 = now_s();
+        for (int i = part; i < 4; i += 2) {
+            size_t bytes = (size_t)nc_ * w->in_w[i] * w->es, got = 0;
+            while (got < bytes) {
+                ssize_t r = pread(w->fd_in, (char *)s->hin[i] + got, bytes - got, (off_t)(w->in_off[i] + (size_t)f0 * w->in_w[i] * w->es + got));
+                if (r <= 0) { fprintf(stderr, "short read\n"); w->rc = 1; break; }
+                got += (size_t)r;
+            }
+        }
+        if (!part) w->t_read += now_s() - t0;
+        sem_post(&w->s_filled);
     }
-    const wifi_dtype dt = (wifi_dtype)h.dtype;
-    const size_t es = dt == WIFI_F32 ? 8 : 16;                       /* bytes per complex value */
+    return NULL;
+}
+
+static void *fp_writer(void *arg)
+{
+    fp_worker *w = (fp_worker *)arg;
+    cudaSetDevice(w->dev);
+    for (long c = 0; c < w->nchunks; ++c) {
+        sem_wait(&w->s_submitted);
+        fp_slot *s = &w->slot[c % FP_SLOTS];
+        if (cudaEventSynchronize(s->done) != cudaSuccess) w->rc = 1;
+        double t0 = now_s();
+        for (int i = 0; i < 7; ++i) {
+            size_t bytes = (size_t)s->nc * out_bytes(w, i), put = 0;
+            while (put < bytes) {
+                ssize_t r = pwrite(w->fd_out, (char *)s->hout[i] + put, bytes - put, (off_t)(w->out_off[i] + (size_t)s->f0 * out_bytes(w, i) + put));
+                if (r <= 0) { fprintf(stderr, "short write\n"); w->rc = 1; break; }
+                put += (size_t)r;
+            }
+        }
+        w->t_write += now_s() - t0;
+        sem_post(&w->s_free); sem_post(&w->s_free1);
+    }
+    return NULL;
+}
+
+static void *fp_worker_main(void *arg)
+{
+    fp_worker *w = (fp_worker *)arg;
+    wifi_ctx *ctx = NULL;
+    const wifi_dtype dt = w->dt; const size_t es = w->es;
+    pthread_t rd[2], wr; int started = 0;
+    fp_reader_arg ra[2] = {{w, 0}, {w, 1}};
+    w->lo = w->n * w->dev / w->ndev; w->hi = w->n * (w->dev + 1) / w->ndev;
+    w->nchunks = (w->hi - w->lo + FP_CHUNK - 1) / FP_CHUNK;
+    if (w->nchunks == 0) return NULL;
+    FCK(wifi_create(w->dev, &ctx));
+    CCK(cudaSetDevice(w->dev));
+    for (int k = 0; k < FP_SLOTS; ++k) {
+        fp_slot *s = &w->slot[k];
+        for (int i = 0; i < 4; ++i) { FCK(wifi_host_alloc(&s->hin[i], FP_CHUNK * w->in_w[i] * es)); CCK(cudaMalloc(&s->din[i], FP_CHUNK * w->in_w[i] * es)); }
+        for (int i = 0; i < 7; ++i) FCK(wifi_host_alloc(&s->hout[i], FP_CHUNK * out_bytes(w, i)));
+        for (int i = 0; i < 2; ++i) { CCK(cudaMalloc(&s->dsymb[i], FP_CHUNK * WIFI_FRAME * es)); CCK(cudaMalloc(&s->dpre[i], FP_CHUNK * NSC * es)); }
+        for (int i = 0; i < 5; ++i) CCK(cudaMalloc(&s->dH[i], FP_CHUNK * NSC * es));
+        CCK(cudaMalloc(&s->deq, FP_CHUNK * WIFI_FRAME * es)); CCK(cudaMalloc(&s->dow2, FP_CHUNK * es / 2)); CCK(cudaMalloc(&s->dblk, 2 * FP_CHUNK * NSC * es));
+        CCK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)); CCK(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+    }
+    {   /* the PCIe ceiling of one chunk's volumes on this GPU, for the report */
+        size_t h2d = 0, d2h = 0;
+        for (int i = 0; i < 4; ++i) h2d += FP_CHUNK * w->in_w[i] * es;
+        for (int i = 0; i < 7; ++i) d2h += FP_CHUNK * out_bytes(w, i);
+        w->pcie_h2d = h2d; w->pcie_d2h = d2h;
+        void *a = NULL, *b = NULL;
+        if (!wifi_host_alloc(&a, h2d) && !wifi_host_alloc(&b, d2h)) { wifi_pcie_probe(ctx, a, b, h2d, d2h, &w->pcie_ms); wifi_pcie_probe(ctx, a, b, h2d, d2h, &w->pcie_ms); }
+        if (a) wifi_host_free(a);
+        if (b) wifi_host_free(b);
+    }
+    sem_init(&w->s_free, 0, FP_SLOTS); sem_init(&w->s_free1, 0, FP_SLOTS); sem_init(&w->s_filled, 0, 0); sem_init(&w->s_submitted, 0, 0);
+    w->t_start = now_s();                                    /* set-up (context, 1 GB of pinned slots) is reported separately */
+    pthread_create(&rd[0], NULL, fp_reader, &ra[0]); pthread_create(&rd[1], NULL, fp_reader, &ra[1]); pthread_create(&wr, NULL, fp_writer, w); started = 1;
+    for (long c = 0; c < w->nchunks; ++c) {
+        sem_wait(&w->s_filled); sem_wait(&w->s_filled);       /* both readers have filled their planes of this slot */
+        fp_slot *s = &w->slot[c % FP_SLOTS];
+        const long nc = s->nc;
+        FCK(wifi_set_stream(ctx, s->st));
+        for (int i = 0; i < 4; ++i) CCK(cudaMemcpyAsync(s->din[i], s->hin[i], (size_t)nc * w->in_w[i] * es, cudaMemcpyHostToDevice, s->st));
+        const void *tx_pre, *rx_pre, *tx_symb, *rx_symb;
+        if (w->kind == WIFI_FILE_TIME) {                              /* time samples -> symbols, preamble spectra, noise estimate */
+            FCK(wifi_frontend_batch(ctx, dt, s->din[0], s->din[2], s->dsymb[0], s->dpre[0], NULL, nc));
+            FCK(wifi_frontend_batch(ctx, dt, s->din[1], s->din[3], s->dsymb[1], s->dpre[1], s->dow2, nc));
+            tx_pre = s->dpre[0]; rx_pre = s->dpre[1]; tx_symb = s->dsymb[0]; rx_symb = s->dsymb[1];
+        } else {
+            tx_pre = s->din[0]; rx_pre = s->din[1]; tx_symb = s->din[2]; rx_symb = s->din[3];
+            /* inputs.h carries ow2 as a constant (inputs.h:18); FREQ files use it for every frame */
+            if (dt == WIFI_F32) { float *v = (float *)s->hout[6]; for (long i = 0; i < nc; ++i) v[i] = 9.6172e-08f; }
+            else { double *v = (double *)s->hout[6]; for (long i = 0; i < nc; ++i) v[i] = 9.6172e-08; }
+            CCK(cudaMemcpyAsync(s->dow2, s->hout[6], (size_t)nc * es / 2, cudaMemcpyHostToDevice, s->st));
+        }
+        FCK(wifi_lt_ls_batch(ctx, dt, tx_pre, rx_pre, s->dH[0], nc));
+        FCK(wifi_ps_batch(ctx, dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx_symb, rx_symb, WIFI_FRAME, s->dH[1], s->dH[2], s->dH[3], nc));
+        /* main.c:148 calling convention on block 0 (main.c:30-33): frame_stride is fixed at 53 there, so gather block 0 */
+        void *tx0 = s->dblk, *rx0 = (char *)s->dblk + (size_t)nc * NSC * es;
+        CCK(cudaMemcpy2DAsync(tx0, NSC * es, tx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
+        CCK(cudaMemcpy2DAsync(rx0, NSC * es, rx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
+        FCK(wifi_mmse_cconv_batch(ctx, dt, tx0, rx0, s->dow2, s->dH[0], s->dH[4], nc));
+        FCK(wifi_equalize_batch(ctx, dt, rx_symb, s->dH[0], s->dH[1], s->deq, nc));
+        for (int i = 0; i < 5; ++i) CCK(cudaMemcpyAsync(s->hout[i], s->dH[i], (size_t)nc * NSC * es, cudaMemcpyDeviceToHost, s->st));
+        CCK(cudaMemcpyAsync(s->hout[5], s->deq, (size_t)nc * WIFI_FRAME * es, cudaMemcpyDeviceToHost, s->st));
+        CCK(cudaMemcpyAsync(s->hout[6], s->dow2, (size_t)nc * es / 2, cudaMemcpyDeviceToHost, s->st));
+        CCK(cudaEventRecord(s->done, s->st));
+        sem_post(&w->s_submitted);
+    }
+done:
+    if (started) {
+        if (w->rc) { for (int k = 0; k < 4 * FP_SLOTS + 4; ++k) { sem_post(&w->s_free); sem_post(&w->s_free1); sem_post(&w->s_filled); sem_post(&w->s_submitted); } }   /* unblock on error */
+        pthread_join(rd[0], NULL); pthread_join(rd[1], NULL); pthread_join(wr, NULL);
+        w->t_end = now_s();
+    }
+    cudaDeviceSynchronize();
+    for (int k = 0; k < FP_SLOTS; ++k) {
+        fp_slot *s = &w->slot[k];
+        for (int i = 0; i < 4; ++i) { if (s->hin[i]) wifi_host_free(s->hin[i]); cudaFree(s->din[i]); }
+        for (int i = 0; i < 7; ++i) if (s->hout[i]) wifi_host_free(s->hout[i]);
+        for (int i = 0; i < 2; ++i) { cudaFree(s->dsymb[i]); cudaFree(s->dpre[i]); }
+        for (int i = 0; i < 5; ++i) cudaFree(s->dH[i]);
+        cudaFree(s->deq); cudaFree(s->dow2); cudaFree(s->dblk);
+        if (s->st) cudaStreamDestroy(s->st);
+        if (s->done) cudaEventDestroy(s->done);
+    }
+    if (ctx) wifi_destroy(ctx);
+    return NULL;
+}
+
+static int file_pipeline(const char *in_path, const char *out_path, int max_dev)
+{
+    int fd = open(in_path, O_RDONLY);
+    if (fd < 0) { fprintf(stderr, "cannot open %s\n", in_path); return 1; }
+    wifi_file_header h;
+    if (pread(fd, &h, sizeof h, 0) != (ssize_t)sizeof h || memcmp(h.magic, WIFI_FILE_MAGIC, 8) || h.dtype > 1 || h.kind > WIFI_FILE_TIME) {
+        fprintf(stderr, "%s: not a FREQ/TIME frame file\n", in_path); close(fd); return 1;
+    }
+    const size_t es = h.dtype == WIFI_F32 ? 8 : 16;                  /* bytes per complex value */
     const long n = (long)h.n_frames;
-    /* input planes (values per frame) and where each starts in the file */
+    int fo = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (fo < 0) { fprintf(stderr, "cannot create %s\n", out_path); close(fd); return 1; }
+    wifi_file_header ho = h; ho.kind = WIFI_FILE_EST;
+    if (pwrite(fo, &ho, sizeof ho, 0) != (ssize_t)sizeof ho) { fprintf(stderr, "cannot write %s\n", out_path); return 1; }
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    if (ndev > 8) ndev = 8;
+    if (max_dev > 0 && ndev > max_dev) ndev = max_dev;
+    if (ndev < 1) { fprintf(stderr, "no CUDA device: there is no CPU path\n"); return 1; }
+    fp_worker *ws = (fp_worker *)calloc((size_t)ndev, sizeof(fp_worker));
+    pthread_t th[8];
+    /* input planes (values per frame) and where each starts in the file -- FREQ: tx_pre rx_pre tx_symb rx_symb;  TIME: tx_packet rx_packet tx_lptot rx_lptot */
     const size_t in_w[4] = {h.kind == WIFI_FILE_FREQ ? NSC : WIFI_PACKET, h.kind == WIFI_FILE_FREQ ? NSC : WIFI_PACKET,
                             h.kind == WIFI_FILE_FREQ ? WIFI_FRAME : WIFI_LPTOT, h.kind == WIFI_FILE_FREQ ? WIFI_FRAME : WIFI_LPTOT};
-    /* FREQ: tx_pre rx_pre tx_symb rx_symb;  TIME: tx_packet rx_packet tx_lptot rx_lptot */
-    size_t in_off[4], o = sizeof h;
-    for (int i = 0; i < 4; ++i) { in_off[i] = o; o += (size_t)n * in_w[i] * es; }
-    /* output planes */
-    const size_t out_w[6] = {NSC, NSC, NSC, NSC, NSC, WIFI_FRAME};
-    size_t out_off[7]; o = sizeof h;
-    for (int i = 0; i < 6; ++i) { out_off[i] = o; o += (size_t)n * out_w[i] * es; }
-    out_off[6] = o;                                                 /* ow2 [n] real */
-    FILE *fo = fopen(out_path, "wb");
-    if (!fo) { fprintf(stderr, "cannot create %s\n", out_path); fclose(fi); return 1; }
-    wifi_file_header ho = h; ho.kind = WIFI_FILE_EST;
-    fwrite(&ho, sizeof ho, 1, fo);
-
-    FCK(wifi_create(0, &ctx));
-    const long chunk = n < 32768 ? (n > 0 ? n : 1) : 32768;
-    void *hin[4], *hout[7], *din[4], *dsymb[2], *dpre[2], *dow2, *dH[5], *deq;
-    for (int i = 0; i < 4; ++i) { FCK(wifi_host_alloc(&hin[i], chunk * in_w[i] * es)); CCK(cudaMalloc(&din[i], chunk * in_w[i] * es)); }
-    for (int i = 0; i < 6; ++i) FCK(wifi_host_alloc(&hout[i], chunk * out_w[i] * es));
-    FCK(wifi_host_alloc(&hout[6], chunk * es / 2));
-    for (int i = 0; i < 2; ++i) { CCK(cudaMalloc(&dsymb[i], chunk * WIFI_FRAME * es)); CCK(cudaMalloc(&dpre[i], chunk * NSC * es)); }
-    for (int i = 0; i < 5; ++i) CCK(cudaMalloc(&dH[i], chunk * NSC * es));
-    CCK(cudaMalloc(&deq, chunk * WIFI_FRAME * es)); CCK(cudaMalloc(&dow2, chunk * es / 2));
+    const size_t out_w[7] = {NSC, NSC, NSC, NSC, NSC, WIFI_FRAME, 1};
     double t0 = now_s();
-    for (long f0 = 0; f0 < n; f0 += chunk) {
-        const long nc = n - f0 < chunk ? n - f0 : chunk;
-        for (int i = 0; i < 4; ++i) {
-            fseek(fi, (long)(in_off[i] + (size_t)f0 * in_w[i] * es), SEEK_SET);
-            if (fread(hin[i], in_w[i] * es, nc, fi) != (size_t)nc) { fprintf(stderr, "short read\n"); return 1; }
-            CCK(cudaMemcpyAsync(din[i], hin[i], nc * in_w[i] * es, cudaMemcpyHostToDevice, 0));
-        }
-        const void *tx_pre, *rx_pre, *tx_symb, *rx_symb;
-        if (h.kind == WIFI_FILE_TIME) {                              /* time samples -> symbols, preamble spectra, noise estimate */
-            FCK(wifi_frontend_batch(ctx, dt, din[0], din[2], dsymb[0], dpre[0], NULL, nc));
-            FCK(wifi_frontend_batch(ctx, dt, din[1], din[3], dsymb[1], dpre[1], dow2, nc));
-            tx_pre = dpre[0]; rx_pre = dpre[1]; tx_symb = dsymb[0]; rx_symb = dsymb[1];
-        } else {
-            tx_pre = din[0]; rx_pre = din[1]; tx_symb = din[2]; rx_symb = din[3];
-            /* inputs.h carries ow2 as a constant (inputs.h:18); FREQ files use it for every frame */
-            if (dt == WIFI_F32) { float *w = (float *)hout[6]; for (long i = 0; i < nc; ++i) w[i] = 9.6172e-08f; }
-            else { double *w = (double *)hout[6]; for (long i = 0; i < nc; ++i) w[i] = 9.6172e-08; }
-            CCK(cudaMemcpyAsync(dow2, hout[6], nc * es / 2, cudaMemcpyHostToDevice, 0));
-        }
-        FCK(wifi_lt_ls_batch(ctx, dt, tx_pre, rx_pre, dH[0], nc));
-        FCK(wifi_ps_batch(ctx, dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx_symb, rx_symb, WIFI_FRAME, dH[1], dH[2], dH[3], nc));
-        /* main.c:148 calling convention on block 0 (main.c:30-33): frame_stride is fixed at 53 there, so gather block 0 */
-        CCK(cudaMemcpy2DAsync(dsymb[0] == tx_symb ? deq : dsymb[0], NSC * es, tx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, 0));
-        void *tx0 = dsymb[0] == tx_symb ? deq : dsymb[0];
-        void *rx0 = (char *)tx0 + (size_t)nc * NSC * es;
-        CCK(cudaMemcpy2DAsync(rx0, NSC * es, rx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, 0));
-        FCK(wifi_mmse_cconv_batch(ctx, dt, tx0, rx0, dow2, dH[0], dH[4], nc));
-        FCK(wifi_synchronize(ctx));
-        FCK(wifi_equalize_batch(ctx, dt, rx_symb, dH[0], dH[1], deq, nc));
-        for (int i = 0; i < 5; ++i) CCK(cudaMemcpyAsync(hout[i], dH[i], nc * NSC * es, cudaMemcpyDeviceToHost, 0));
-        CCK(cudaMemcpyAsync(hout[5], deq, nc * WIFI_FRAME * es, cudaMemcpyDeviceToHost, 0));
-        CCK(cudaMemcpyAsync(hout[6], dow2, nc * es / 2, cudaMemcpyDeviceToHost, 0));
-        CCK(cudaDeviceSynchronize());
-        for (int i = 0; i < 6; ++i) { fseek(fo, (long)(out_off[i] + (size_t)f0 * out_w[i] * es), SEEK_SET); fwrite(hout[i], out_w[i] * es, nc, fo); }
-        fseek(fo, (long)(out_off[6] + (size_t)f0 * es / 2), SEEK_SET); fwrite(hout[6], es / 2, nc, fo);
+    for (int g = 0; g < ndev; ++g) {
+        fp_worker *w = &ws[g];
+        w->dev = g; w->ndev = ndev; w->fd_in = fd; w->fd_out = fo; w->dt = (wifi_dtype)h.dtype; w->kind = (int)h.kind; w->es = es; w->n = n;
+        size_t o = sizeof h;
+        for (int i = 0; i < 4; ++i) { w->in_w[i] = in_w[i]; w->in_off[i] = o; o += (size_t)n * in_w[i] * es; }
+        o = sizeof h;
+        for (int i = 0; i < 7; ++i) { w->out_w[i] = out_w[i]; w->out_off[i] = o; o += (size_t)n * out_bytes(w, i); }
+        pthread_create(&th[g], NULL, fp_worker_main, w);
     }
-    double dt_s = now_s() - t0;
-    fclose(fi); fclose(fo);
-    printf("frame file %s (%s, %s, %ld frames) -> %s: %.3f s = %.3e frames/s incl. file I/O\n", in_path, h.kind == WIFI_FILE_TIME ? "time samples" : "frequency domain",
-           dt == WIFI_F32 ? "complex64" : "complex128", n, out_path, dt_s, n / dt_s);
-    wifi_destroy(ctx);
-    return 0;
+    int bad = 0;
+    double t_read = 0, t_write = 0, ceil_fps = 0, t_first = 1e300, t_last = 0;
+    for (int g = 0; g < ndev; ++g) {
+        pthread_join(th[g], NULL);
+        bad |= ws[g].rc; t_read += ws[g].t_read; t_write += ws[g].t_write;
+        if (ws[g].t_start > 0 && ws[g].t_start < t_first) t_first = ws[g].t_start;
+        if (ws[g].t_end > t_last) t_last = ws[g].t_end;
+        if (ws[g].pcie_ms > 0) ceil_fps += FP_CHUNK / (1e-3 * ws[g].pcie_ms);
+    }
+    const double total_s = now_s() - t0, dt_s = t_last > t_first ? t_last - t_first : total_s;
+    close(fd); close(fo);
+    const double per_frame_in = (double)(ws[0].pcie_h2d) / FP_CHUNK, per_frame_out = (double)(ws[0].pcie_d2h) / FP_CHUNK;
+    printf("frame file %s (%s, %s, %ld frames) -> %s on %d GPU(s): %.3f s = %.3e frames/s incl. file I/O (%.2f GB/s read + %.2f GB/s written; "
+           "tx-side reader threads busy %.2f s, writer threads %.2f s in total; %.2f s of set-up -- contexts, pinned slots -- not included)\n", in_path, h.kind == WIFI_FILE_TIME ? "time samples" : "frequency domain",
+           h.dtype == WIFI_F32 ? "complex64" : "complex128", n, out_path, ndev, dt_s, n / dt_s, n * per_frame_in / dt_s / 1e9, n * per_frame_out / dt_s / 1e9, t_read, t_write, total_s - dt_s);
+    if (ceil_fps > 0)
+        printf("PCIe ceiling for these volumes (%.0f B in + %.0f B out per frame, pinned copies of one chunk issued together, measured per GPU): %.3e frames/s -> "
+               "the pipeline ran at %.1f %% of it\n", per_frame_in, per_frame_out, ceil_fps, 100.0 * (n / dt_s) / ceil_fps);
+    free(ws);
+    return bad;
 }
 
 int main(int argc, char **argv)
 {
-    if (argc == 4 && !strcmp(argv[1], "--file")) return file_pipeline(argv[2], argv[3]);
+    if (argc >= 4 && !strcmp(argv[1], "--file")) return file_pipeline(argv[2], argv[3], argc > 4 ? atoi(argv[4]) : 0);
     long n_total = argc > 1 ? atol(argv[1]) : 4194304L;
     const char *fixture = argc > 2 ? argv[2] : "tests/golden/inputs_h_frame.f64";
     printf("%s\n", wifi_version());

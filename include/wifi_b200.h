@@ -108,6 +108,14 @@ int wifi_ps_batch(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbol
 int wifi_equalize_batch(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
                         void *eq, int64_t n_frames);
 
+/* BASELINE configs[4] in one call: all five estimators of main.c:4-8 (+ the equalizer when eq != NULL) for n frames.
+ * tx_pre/rx_pre [n][53]; tx_symbols/rx_symbols: block 0 at frame_stride (53: block vectors, 795: whole frames in place);
+ * PS_MMSE is the shared-filter form (wifi_mmse_filter_form/_set first); eq [n][15][53] needs whole frames (frame_stride 795)
+ * and blends H_lt with H_linear like WiFi_RX.m:60.  Four launches (LT_LS, pilot-LS + interpolators, PS_MMSE GEMM, equalizer). */
+int wifi_estimate_all_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx_symbols,
+                            const void *rx_symbols, int64_t frame_stride, void *H_lt, void *H_linear, void *H_cubic, void *H_sinc,
+                            void *H_mmse, void *eq, int64_t n_frames);
+
 /* ---- receiver front-end: time samples -> the estimators' inputs ------------------------------------
  * WiFi_blocks_extraction.m:5-10 and WiFi_RX.m:19-31, for one side (tx or rx) of n frames:
  *   packet [n][1200] = 15 OFDM blocks of 16 cyclic-prefix + 64 samples;  lptot [n][160] = long-training field
@@ -196,6 +204,9 @@ int wifi_ps_host(wifi_ctx *ctx, wifi_dtype dt, int which, const void *tx_symbols
                  int64_t frame_stride, void *H_linear, void *H_cubic, void *H_sinc, int64_t n_frames);
 int wifi_equalize_host(wifi_ctx *ctx, wifi_dtype dt, const void *rx_frames, const void *H_lt, const void *H_ps,
                        void *eq, int64_t n_frames);
+/* whole frames [n][15][53] on the host; eq may be NULL (then only block 0 of rx crosses the bus) */
+int wifi_estimate_all_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx_frames, const void *rx_frames,
+                           void *H_lt, void *H_linear, void *H_cubic, void *H_sinc, void *H_mmse, void *eq, int64_t n_frames);
 int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft,
                        void *ow2, int64_t n_frames);
 int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);

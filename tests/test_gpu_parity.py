@@ -577,3 +577,60 @@ def test_synth_and_stats(ctx):
     assert np.array_equal(host(fr2["rx_pre"]), host(fr["rx_pre"])[1000:1100])
     st = host(ctx.error_stats(fr["H_true"], fr["H_true"] * 1.001))
     assert abs(st[0] / st[1] - 1e-6 / 1.001 ** 2) < 1e-9 and st[2] == 4096 * 53
+
+
+# ------------------------------------------------------------------ all five estimators + equalizer in one call (configs[4])
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("n,whole", [(1, True), (31, True), (32, False), (33, True), (128, True), (1000, False), (4133, True)])
+def test_estimate_all(ctx, oracle, prec, n, whole):
+    """wifi_estimate_all_batch (all five estimators + the equalizer behind one call, BASELINE configs[4]) against the oracle
+    estimator by estimator: LT_LS main.c:66-75, PS_* main.c:77-146, shared-filter PS_MMSE, WiFi_Equalization.m; whole
+    frames read in place (stride 795) and dense block vectors (stride 53); ragged tails (n not a multiple of the 32-frame chunk)."""
+    fr = synth.make_frames(n, seed=900 + n)
+    c = lambda x: np.ascontiguousarray(x.astype(CDT[prec]))
+    tp, rp, txs, rxs = c(fr["tx_pre"]), c(fr["rx_pre"]), c(fr["tx_symb"]), c(fr["rx_symb"])
+    if n >= 3:
+        tp[2, 7] = 3.0 + 3.0j                                # Re(tx) == Im(tx): LT_LS is NaN there, like the reference (main.c:69-72)
+    R = synth.channel_covariance()
+    d = synth.OW2 / np.abs(fr["tx_symb"][0, 0, :]) ** 2
+    W = host(ctx.mmse_filter_form(dev(R), dev(d)))
+    if whole:
+        out = ctx.estimate_all(dev(tp), dev(rp), dev(txs), dev(rxs))
+    else:
+        out = ctx.estimate_all(dev(tp), dev(rp), dev(c(txs[:, 0, :])), dev(c(rxs[:, 0, :])))
+        assert "eq" not in out
+    g = {k: host(v) for k, v in out.items()}
+    w = lambda x: r32(x, prec)
+    tol = TOL[prec]
+    ref_lt = oracle.lt_ls(w(tp), w(rp))
+    if n >= 3:
+        assert np.isnan(g["lt_ls"][2, 7]) and np.isnan(ref_lt[2, 7])
+    assert rel_err(g["lt_ls"], ref_lt) < tol
+    assert (g["lt_ls"][:, 26] == 0).all()
+    tx0, rx0 = w(txs[:, 0, :]), w(rxs[:, 0, :])
+    for name in ("linear", "cubic", "sinc"):
+        assert rel_err(g[name], getattr(oracle, "ps_" + name)(tx0, rx0)) < tol, name
+    assert rel_err(g["mmse"], oracle.mmse_apply(W, rx0 / tx0)) < tol
+    if whole:
+        lt_in, lin_in = g["lt_ls"].astype(np.complex128), g["linear"].astype(np.complex128)
+        ref_eq = oracle.equalize(w(rxs), lt_in, lin_in)
+        assert rel_err(g["eq"], ref_eq, floor=1e-6) < tol
+    # the combined call agrees with the stand-alone entry point
+    assert rel_err(g["mmse"], host(ctx.mmse_shared(dev(c(txs[:, 0, :])), dev(c(rxs[:, 0, :])))), 1e-6) < 1e-6
+
+
+def test_estimate_all_host_arrays(ctx, oracle):
+    n = 2500
+    fr = synth.make_frames(n, seed=17, dtype=np.complex64)
+    R = synth.channel_covariance()
+    ctx.mmse_filter_form(R, synth.OW2 / np.abs(fr["tx_symb"][0, 0, :].astype(np.complex128)) ** 2)
+    ctx.set_host_chunk_bytes(1 << 20)                      # several chunks in flight
+    try:
+        for eq in (True, False):
+            a = ctx.estimate_all(fr["tx_pre"], fr["rx_pre"], fr["tx_symb"], fr["rx_symb"], equalize=eq)
+            b = ctx.estimate_all(dev(fr["tx_pre"]), dev(fr["rx_pre"]), dev(fr["tx_symb"]), dev(fr["rx_symb"]), equalize=eq)
+            assert set(a) == set(b) and ("eq" in a) == eq
+            for k in a:
+                assert np.array_equal(a[k], host(b[k]), equal_nan=True), k
+    finally:
+        ctx.set_host_chunk_bytes(48 << 20)
