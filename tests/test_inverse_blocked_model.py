@@ -1,0 +1,48 @@
+"""CPU model of the blocked in-place Gauss-Jordan inverse of csrc/wifi_solve.cu (cinverse_blk_kernel): NB scalar steps with
+implicit partial pivoting composed into one rank-NB update  A <- A - C' R~  (C' = the multiplier vectors + e_(r_s), R~ = the
+pivot rows after a unit-lower-triangular transform), panel columns replaced by the factored panel, result un-permuted at the
+end.  Checks the algebra the kernel relies on against numpy.linalg.inv (replaces inverse(), utils.c:141-170)."""
+import numpy as np
+import pytest
+
+
+def blocked_gj_inverse(A, NB=4):
+    n0 = A.shape[0]
+    N = -(-n0 // NB) * NB
+    a = np.zeros((N, N), complex); a[:n0, :n0] = A
+    for i in range(n0, N):
+        a[i, i] = 1.0                                   # padding rows / columns pivot on themselves
+    used = np.zeros(N, bool); rowof = np.zeros(N, int); kof = np.zeros(N, int)
+    for K in range(0, N, NB):
+        P = a[:, K:K + NB].copy()                       # the panel, factored alone (warp 0 of the kernel)
+        Cp = np.zeros((N, NB), complex); rs = []
+        for s in range(NB):
+            cand = np.where(~used)[0]
+            r = cand[np.argmax(np.abs(P[cand, s]))]
+            inv = 1.0 / P[r, s]
+            c = P[:, s] * inv; c[r] = -inv
+            Cp[:, s] = c; Cp[r, s] += 1.0               # C' = c + e_(r_s)
+            rho = P[r, :].copy(); rho[s] = 1.0
+            P[r, :] = 0; P[:, s] = 0
+            P -= np.outer(c, rho)
+            used[r] = True; rowof[K + s] = r; kof[r] = K + s; rs.append(r)
+        rho = np.zeros((NB, N), complex)
+        for s in range(NB):                             # rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t); c^(t)[r_s] = C'[r_s][t] for t < s
+            rho[s] = a[rs[s], :] - sum(Cp[rs[s], t] * rho[t] for t in range(s))
+        a -= Cp @ rho
+        a[:, K:K + NB] = P
+    Y = np.zeros((N, N), complex)
+    Y[np.ix_(kof, rowof)] = a
+    return Y[:n0, :n0]
+
+
+@pytest.mark.parametrize("n", [33, 47, 53, 56, 64])
+@pytest.mark.parametrize("NB", [2, 4])
+def test_blocked_gauss_jordan_model(n, NB):
+    rng = np.random.default_rng(n * 10 + NB)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Y = blocked_gj_inverse(A, NB)
+    ref = np.linalg.inv(A)
+    assert np.abs(Y - ref).max() / np.abs(ref).max() < 1e-12
+    B = A.copy(); B[0, 0] = 0                          # a zero leading element: un-pivoted elimination (the reference's determinant) fails here
+    assert np.abs(blocked_gj_inverse(B, NB) @ B - np.eye(n)).max() < 1e-11
