@@ -26,8 +26,8 @@ struct wifi_ctx {
     FilterImages img_rx;     // W diag(1/tx) for a shared, known tx block vector (wifi_mmse_filter_fold_tx): applied to rx directly
     FilterImages eig[2];     // eigen-domain per-frame MMSE: G = V^H M^-1/2 and G2 = M^1/2 V as shared-filter operands
     double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc; double eig_Rdd, eig_md;
-    void *eig_u[2]; size_t eig_u_bytes[2];   // [n][53] scratch between the two products, one per pipeline stream (the two
-                                             // chunks of a *_host call are in flight at the same time)
+    void *eig_u[2]; size_t eig_u_bytes[2];   // scratch, one per pipeline stream (the two chunks of a *_host call are in flight at the
+                                             // same time): [n][53] between the two eigen-domain products, [n][4] pilot records of estimate_all
     int *d_info;             // device scratch: singularity flags
     int *h_info;             // pinned mirror
     char err[512];
@@ -272,12 +272,12 @@ int wifi_mmse_filter_set(wifi_ctx *ctx, const void *W)
 }
 
 static int gemm_with(wifi_ctx *ctx, const FilterImages &im, wifi_dtype dt, const void *a, const void *rx, int64_t frame_stride, void *H,
-                     int64_t n, cudaStream_t s)
+                     int64_t n, cudaStream_t s, void *hp_out = nullptr)
 {
     Timed t(ctx, s);
     // FP32: 3xTF32 on the tcgen05 tensor cores; FP64: DMMA (tcgen05 has no FP64 kind)
-    if (dt == WIFI_F32) CK(launch_mmse_shared_tc(im, a, rx, frame_stride, H, n, s));
-    else CK(launch_mmse_shared_dmma(im, a, rx, frame_stride, H, n, s));
+    if (dt == WIFI_F32) CK(launch_mmse_shared_tc(im, a, rx, frame_stride, H, n, s, hp_out));
+    else CK(launch_mmse_shared_dmma(im, a, rx, frame_stride, H, n, s, hp_out));
     return WIFI_OK;
 }
 
@@ -359,24 +359,33 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                          const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check);
 
-// BASELINE configs[4]: all five estimators (+ the equalizer) of n frames behind one call: LT_LS, the fused pilot-LS + three
-// interpolators, the shared-filter PS_MMSE GEMM (reading block 0 of tx / rx in place) and the equalizer -- four launches, each
-// at >= 100 % of the measured HBM copy rate on its own bytes.  Two fusions were built, measured on B200 and rejected (round 2,
-// 1 Mi frames, FP32; the four launches take 2.93 ms):
+// BASELINE configs[4]: all five estimators (+ the equalizer) of n frames behind one call, four launches: LT_LS; the shared-filter
+// PS_MMSE GEMM (reading block 0 of tx / rx in place), whose LS-divide stage also hands the four pilot LS values of every frame
+// to the interpolators as a 32-byte record; the three interpolators from those records (no pilot gather: 8 isolated values per
+// frame cost 512 B of DRAM traffic, the records 32 B); the equalizer.  Two deeper fusions were built, measured on B200 and
+// rejected (round 2, 1 Mi frames, FP32; four stand-alone launches take 2.93 ms):
 //   * LT_LS and the interpolators emitted by the GEMM kernel's converter warps from the block LS values they stage (one launch
 //     for the five estimates): those 8 warps are latency-bound, the launch took 1.00 ms against 0.83 ms for the three kernels;
 //   * a "frame finish" pass (LT_LS + interpolators + equalizer, no estimate re-read: 1 912 instead of 2 022 complex values per
 //     frame), as a shared-memory tile kernel with flat 16-byte vectors (3.8 ms) and as one thread per (frame, sub-carrier) with
 //     the estimates in registers (2.73 ms at 6.0 TB/s of DRAM traffic; 8-byte accesses, 27 warps per SM): 3.05 ms with the GEMM.
 static int estimate_all(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, const void *rx_pre, const void *tx, const void *rx, int64_t frame_stride,
-                        void *H_lt, void *H_lin, void *H_cub, void *H_sinc, void *H_mmse, void *eq, int64_t n, cudaStream_t s)
+                        void *H_lt, void *H_lin, void *H_cub, void *H_sinc, void *H_mmse, void *eq, int64_t n, cudaStream_t s, int slot = 0)
 {
     if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
     if (n == 0) return WIFI_OK;
+    const size_t need = (size_t)n * 4 * esize(dt);                    // pilot records [n][4]; the scratch is shared with the eigen-domain path
+    if (ctx->eig_u_bytes[slot] < need) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->eig_u[slot]); ctx->eig_u[slot] = nullptr; ctx->eig_u_bytes[slot] = 0;
+        if (cudaMalloc(&ctx->eig_u[slot], need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "pilot scratch cudaMalloc(%zu) failed", need);
+        ctx->eig_u_bytes[slot] = need;
+    }
+    void *hp = ctx->eig_u[slot];
     { Timed t(ctx, s); CK(launch_lt_ls(dt, tx_pre, rx_pre, H_lt, n, s)); }
-    { Timed t(ctx, s); CK(launch_ps(dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx, rx, frame_stride, H_lin, H_cub, H_sinc, n, ctx->tab, s)); }
-    int rc = gemm_with(ctx, ctx->img, dt, tx, rx, frame_stride, H_mmse, n, s);
+    int rc = gemm_with(ctx, ctx->img, dt, tx, rx, frame_stride, H_mmse, n, s, hp);
     if (rc) return rc;
+    { Timed t(ctx, s); CK(launch_ps(dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx, rx, frame_stride, H_lin, H_cub, H_sinc, n, ctx->tab, s, hp)); }
     if (eq) { Timed t(ctx, s); CK(launch_equalize(dt, rx, H_lt, H_lin, eq, n, s)); }      // WiFi_RX.m:60: H_EST_LT_LS and H_EST_PS_Linear
     return WIFI_OK;
 }
@@ -779,12 +788,13 @@ int wifi_estimate_all_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, con
     if (eq) arrs.push_back(out_arr(eq, frow));
     return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
         // tx is staged as block vectors (stride 53); rx too without the equalizer, as whole frames (stride 795) with it
-        if (!eq) return estimate_all(ctx, dt, d[0], d[1], d[2], d[3], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s);
+        const int slot = s == ctx->hstream[1] ? 1 : 0;
+        if (!eq) return estimate_all(ctx, dt, d[0], d[1], d[2], d[3], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s, slot);
         // with the equalizer the estimators want tx and rx at ONE stride: block 0 of rx is gathered on the device into the eq
         // staging buffer, which is free until the equalizer (the last kernel of the chunk) overwrites it
         cudaError_t e = cudaMemcpy2DAsync(d[9], row, d[3], frow, row, (size_t)nc, cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
-        int rc = estimate_all(ctx, dt, d[0], d[1], d[2], d[9], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s);
+        int rc = estimate_all(ctx, dt, d[0], d[1], d[2], d[9], WIFI_NSC, d[4], d[5], d[6], d[7], d[8], nullptr, nc, s, slot);
         if (rc) return rc;
         Timed t(ctx, s);
         CK(launch_equalize(dt, d[3], d[4], d[5], d[9], nc, s));

@@ -117,7 +117,7 @@ struct DmEig {
 template <bool FUSED, bool EIG>
 __global__ void __launch_bounds__(DW_THREADS, 1)
     mmse_shared_dmma_ws_kernel(const double *__restrict__ Bt_g, const double2 *__restrict__ a_in, const double2 *__restrict__ rx,
-                               int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames, DmEig eg)
+                               int64_t frame_stride, double2 *__restrict__ H, int64_t n_frames, DmEig eg, double2 *__restrict__ hp_out)
 {
     extern __shared__ __align__(16) unsigned char dm_smem[];
     double *Bt = (double *)dm_smem;                                   // [112][116]
@@ -202,6 +202,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
                             const double2 t = tv[batch & 1][u], r = rv[batch & 1][u];
                             const double inv = dm_rcp(t.x * t.x + t.y * t.y);
                             y = make_double2((r.x * t.x + r.y * t.y) * inv, (r.y * t.x - r.x * t.y) * inv);
+                            // on request the four pilot LS values of a frame (main.c:82-84) go out as hp_out[f][4] for the interpolators
+                            if (hp_out != nullptr && f < nf && (kk == WIFI_P0 || kk == WIFI_P1 || kk == WIFI_P2 || kk == WIFI_P3))
+                                hp_out[(f0 + f) * 4 + (kk - WIFI_P0) / (WIFI_P1 - WIFI_P0)] = y;
                         }
                         *reinterpret_cast<double2 *>(Ab + f * DM_AS + 2 * kk) = y;
                     }
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
 
 template <bool FUSED, bool EIG>
 static cudaError_t launch_ws(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
-                             const DmEig &eg, cudaStream_t s)
+                             const DmEig &eg, cudaStream_t s, void *hp_out = nullptr)
 {
     const size_t smem = sizeof(double) * (DM_N * DM_BS + DW_PAIRS * 2 * DW_ROWS * DM_AS) + sizeof(uint64_t) * DW_PAIRS * 4 +
                         sizeof(double) * 56 + sizeof(double2) * (56 + DW_PAIRS * 2 * 8);
@@ -325,7 +328,7 @@ static cudaError_t launch_ws(const FilterImages &img, const void *a, const void 
     cudaError_t e = cudaFuncSetAttribute(mmse_shared_dmma_ws_kernel<FUSED, EIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mmse_shared_dmma_ws_kernel<FUSED, EIG><<<grid, DW_THREADS, smem, s>>>(img.B64, (const double2 *)a, (const double2 *)rx, frame_stride,
-                                                                         (double2 *)H, n_frames, eg);
+                                                                         (double2 *)H, n_frames, eg, (double2 *)hp_out);
     return cudaGetLastError();
 }
 
@@ -342,13 +345,13 @@ cudaError_t launch_mmse_shared_dmma_eig(const FilterImages &img, const void *u, 
 }
 
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
-                                    int64_t n_frames, cudaStream_t s)
+                                    int64_t n_frames, cudaStream_t s, void *hp_out)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
     const DmEig none = {nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0.0, 0.0, -1};
-    return rx ? launch_ws<true, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+    return rx ? launch_ws<true, false>(img, a, rx, frame_stride, H, n_frames, none, s, hp_out)
               : launch_ws<false, false>(img, a, nullptr, frame_stride, H, n_frames, none, s);
 }
 

@@ -216,7 +216,7 @@ template <bool FUSED, bool RESID, bool MID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
                           const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16,
-                          TcResid res)
+                          TcResid res, float2 *__restrict__ hp_out)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     TcSmem &sm = *reinterpret_cast<TcSmem *>(tc_smem_raw);
@@ -484,6 +484,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
             }
             __syncwarp();
+            // FUSED, on request: the four pilot LS values of my frame (H_ls[5, 19, 33, 47], main.c:82-84) go out as one 32-byte
+            // record, hp_out[f][4] -- the interpolating estimators then need no pilot gather of their own (8 isolated values per
+            // frame cost a 64-byte DRAM atom each: 512 B against these 32)
+            if (FUSED && hp_out != nullptr && lane < valid) {
+                const float2 *rowp = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
+                const float2 p0 = rowp[WIFI_P0], p1 = rowp[WIFI_P1], p2 = rowp[WIFI_P2], p3 = rowp[WIFI_P3];
+                float4 *o = reinterpret_cast<float4 *>(hp_out + (f0 + lane) * 4);
+                st_stream(o, make_float4(p0.x, p0.y, p1.x, p1.y));
+                st_stream(o + 1, make_float4(p2.x, p2.y, p3.x, p3.y));
+            }
             // ---- b. my frame -> hi/lo -> TMEM (A operand), after the previous tile's MMAs have released it ----
             if (it > 0) { mbar_wait(&sm.bar_mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
             const float2 *row = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF);
@@ -547,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
 template <bool FUSED, bool RESID, bool MID>
 static cudaError_t launch_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
-                             const TcResid &res, cudaStream_t s)
+                             const TcResid &res, cudaStream_t s, void *hp_out = nullptr)
 {
     const size_t smem = sizeof(TcSmem);
     const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
@@ -556,18 +566,18 @@ static cudaError_t launch_tc(const FilterImages &img, const void *a, const void 
     cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, RESID, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mmse_shared_tc_kernel<FUSED, RESID, MID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
-                                                                       (float2 *)H, n_frames, aligned16, res);
+                                                                       (float2 *)H, n_frames, aligned16, res, (float2 *)hp_out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H,
-                                  int64_t n_frames, cudaStream_t s)
+                                  int64_t n_frames, cudaStream_t s, void *hp_out)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
     const TcResid none = {nullptr, nullptr, 0, nullptr, -1, nullptr, nullptr, nullptr, 0.f, 0.f};
-    return rx ? launch_tc<true, false, false>(img, a, rx, frame_stride, H, n_frames, none, s)
+    return rx ? launch_tc<true, false, false>(img, a, rx, frame_stride, H, n_frames, none, s, hp_out)
               : launch_tc<false, false, false>(img, a, nullptr, frame_stride, H, n_frames, none, s);
 }
 

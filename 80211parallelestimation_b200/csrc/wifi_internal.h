@@ -24,8 +24,9 @@ struct FilterImages {
 };
 
 cudaError_t launch_lt_ls(wifi_dtype dt, const void *tx, const void *rx, void *H, int64_t n_frames, cudaStream_t s);
+// hp_in != NULL: the four pilot LS values of every frame, [n][4], as written by the PS_MMSE GEMM kernels (hp_out) -- tx / rx are not read
 cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl, void *Hc,
-                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s);
+                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s, const void *hp_in = nullptr);
 cudaError_t launch_equalize(wifi_dtype dt, const void *rx, const void *Hlt, const void *Hps, void *eq, int64_t n_frames,
                             cudaStream_t s);
 
@@ -50,13 +51,13 @@ cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *t
 cudaError_t launch_filter_fold(const void *W64, const void *tx64, void *Wout64, cudaStream_t s);   // W diag(1/tx)
 cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // W64 -> Bhi/Blo (UMMA canonical layout)
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
-                                  int64_t n_frames, cudaStream_t s);             // FP32 I/O, 3xTF32 on tcgen05
+                                  int64_t n_frames, cudaStream_t s, void *hp_out = nullptr);   // FP32 I/O, 3xTF32 on tcgen05; hp_out [n][4]: pilot LS
 cudaError_t launch_mmse_shared_tc_resid(const FilterImages &img, const void *v, const void *tx, const void *rx, int64_t frame_stride,
                                         int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
                                         int64_t n_frames, cudaStream_t s);   // H = rx/tx - v W^T (eigen-domain MMSE; sigma2: fused mid pass)
 cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s);   // W64 -> B64
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
-                                    int64_t n_frames, cudaStream_t s);           // FP64 I/O, DMMA m8n8k4
+                                    int64_t n_frames, cudaStream_t s, void *hp_out = nullptr);   // FP64 I/O, DMMA m8n8k4; hp_out [n][4]: pilot LS
 cudaError_t launch_mmse_shared_dmma_eig(const FilterImages &img, const void *u, const void *tx, const void *rx, int64_t frame_stride,
                                         int dc, const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
                                         int64_t n_frames, cudaStream_t s);   // FP64: H = rx/tx - v G2^T, v formed from u in the kernel

@@ -133,7 +133,7 @@ template <typename T>
 __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx,
                                                                int64_t frame_stride, cx<T> *__restrict__ Hl,
                                                                cx<T> *__restrict__ Hc, cx<T> *__restrict__ Hs, int which,
-                                                               int64_t n_frames, const T *__restrict__ wtab)
+                                                               int64_t n_frames, const T *__restrict__ wtab, const cx<T> *__restrict__ hp_in)
 {
     __shared__ cx<T> hp[PS_TILE][4];
     const int64_t f0 = (int64_t)blockIdx.x * PS_TILE;
@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__re
     const int navg = (which & WIFI_PS_MATLAB) ? 4 : 1;
     for (int idx = threadIdx.x; idx < nf * 4; idx += PS_THREADS) {
         int f = idx >> 2, p = idx & 3;
+        if (hp_in != nullptr) {                 // pilot LS values handed over by the PS_MMSE GEMM kernel of the same call: hp_in[f][4]
+            hp[f][p] = ld_stream(hp_in + (f0 + f) * 4 + p);
+            continue;
+        }
         int64_t off = (f0 + f) * frame_stride + (WIFI_P0 + (WIFI_P1 - WIFI_P0) * p);
         cx<T> h = cdiv(ld_gather(rx + off), ld_gather(tx + off));
         if (navg == 4) {
@@ -192,18 +196,18 @@ __global__ void __launch_bounds__(PS_THREADS) ps_interp_kernel(const cx<T> *__re
 }
 
 cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, int64_t frame_stride, void *Hl, void *Hc,
-                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s)
+                      void *Hs, int64_t n_frames, const InterpTables &tab, cudaStream_t s, const void *hp_in)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     unsigned grid = (unsigned)((n_frames + PS_TILE - 1) / PS_TILE);
     if (dt == WIFI_F32)
         ps_interp_kernel<float><<<grid, PS_THREADS, 0, s>>>((const float2 *)tx, (const float2 *)rx, frame_stride, (float2 *)Hl,
-                                                            (float2 *)Hc, (float2 *)Hs, which, n_frames, tab.w32);
+                                                            (float2 *)Hc, (float2 *)Hs, which, n_frames, tab.w32, (const float2 *)hp_in);
     else
         ps_interp_kernel<double><<<grid, PS_THREADS, 0, s>>>((const double2 *)tx, (const double2 *)rx, frame_stride,
                                                              (double2 *)Hl, (double2 *)Hc, (double2 *)Hs, which, n_frames,
-                                                             tab.w64);
+                                                             tab.w64, (const double2 *)hp_in);
     g_last_launches = 1;
     return cudaGetLastError();
 }

@@ -314,9 +314,10 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
         o5 = {"lt_ls": H, "linear": outs["linear"], "cubic": outs["cubic"], "sinc": outs["sinc"], "mmse": Hm5, "eq": eq}
         X.rate("all5_plus_equalizer_" + prec, lambda: ctx.estimate_all(fr["tx_pre"], fr["rx_pre"], fr["tx_symb"], fr["rx_symb"], out=o5), n,
                2014 * cbytes, config="configs[4]",
-               note="LT_LS + PS_Linear/Cubic/Sinc + shared-filter PS_MMSE + equalizer on whole frames through wifi_estimate_all_batch (4 launches); "
-                    "hbm_frac is on the algorithmic bytes of a single fused pass (read tx_pre, rx_pre, block 0 of tx, rx_symb = 954 c, write five estimates "
-                    "+ eq = 1 060 c); the four kernels move 2 181 c (the equalizer re-reads H_lt, H_linear; block 0 of rx is read three times)")
+               note="LT_LS + PS_Linear/Cubic/Sinc + shared-filter PS_MMSE + equalizer on whole frames through wifi_estimate_all_batch: 4 launches, the "
+                    "GEMM kernel hands the four pilot LS values of every frame to the interpolators (no pilot gather). hbm_frac is on the algorithmic "
+                    "bytes of a single fused pass (read tx_pre, rx_pre, block 0 of tx, rx_symb = 954 c, write five estimates + eq = 1 060 c); the four "
+                    "kernels move 2 181 c (the equalizer re-reads H_lt, H_linear; block 0 of rx is read twice)")
         del eq, Hm5, o5
         tx0 = fr["tx_symb"][:, 0, :].contiguous(); rx0 = fr["rx_symb"][:, 0, :].contiguous()
         del fr

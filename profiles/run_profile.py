@@ -28,8 +28,9 @@ def main():
             if want("equalize"): ctx.equalize(fr["rx_symb"][: n // 8], H[: n // 8], outs["linear"][: n // 8], out=eq)
             if want("mmse_shared"): ctx.mmse_shared(tx0, rx0, out=H)
             if want("mmse_hpd"): ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD, out=H[: 1 << 16])
-            if want("mmse_hpd") and prec == "f32":
-                ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD | wifi.SOLVE_WIDE, out=H[: 1 << 16])
+            if want("mmse_hpd") and prec == "f32":      # the FP32-arithmetic opt-in (not a parity mode)
+                ctx.mmse_perframe(Rp, tx0[: 1 << 16], rx0[: 1 << 16], fr["sigma2"][: 1 << 16], flags=wifi.SOLVE_HPD | wifi.SOLVE_FAST32, out=H[: 1 << 16])
+            if want("mmse_pivot"): ctx.mmse_perframe(Rp, tx0[: 1 << 13], rx0[: 1 << 13], fr["sigma2"][: 1 << 13], flags=wifi.SOLVE_PIVOT, out=H[: 1 << 13])
             if want("eig") and rep == 0:
                 ctx.mmse_eig_prepare(R, (tx0[0].abs().to(torch.float64)) ** 2)
             if want("eig"): ctx.mmse_perframe_eig(tx0, rx0, fr["sigma2"], out=H)
