@@ -15,6 +15,11 @@ AS_WRITTEN, INTENDED = 0, 1
 
 _vp, _i, _i64, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint64
 
+class RxChainOut(C.Structure):
+    """wifi_rx_chain_out (include/wifi_b200.h): the optional output planes of the fused receiver chain."""
+    _fields_ = [(k, _vp) for k in ("H_lt", "H_linear", "H_cubic", "H_sinc", "H_mmse_cconv", "H_ls0", "H_mmse_shared", "eq", "rx_symb", "ow2")]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/wifi_b200.h line by line
 SIGNATURES = {
     "wifi_create": [_i, C.POINTER(_vp)],
@@ -31,6 +36,7 @@ SIGNATURES = {
     "wifi_equalize_batch": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
     "wifi_estimate_all_batch": [_vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_frontend_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
+    "wifi_rx_chain_batch": [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(RxChainOut), _i64],
     "wifi_mmse_filter_form": [_vp, _vp, _vp, _vp],
     "wifi_mmse_filter_set": [_vp, _vp],
     "wifi_mmse_shared_apply_batch": [_vp, _i, _vp, _vp, _i64],
@@ -57,6 +63,7 @@ SIGNATURES = {
     "wifi_equalize_host": [_vp, _i, _vp, _vp, _vp, _vp, _i64],
     "wifi_estimate_all_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_frontend_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
+    "wifi_rx_chain_host": [_vp, _i, _vp, _vp, _vp, _vp, C.POINTER(RxChainOut), _i64],
     "wifi_mmse_filter_form_host": [_vp, _vp, _vp, _vp],
     "wifi_mmse_shared_host": [_vp, _i, _vp, _vp, _i64, _vp, _i64],
     "wifi_mmse_filter_fold_tx_host": [_vp, _vp],

@@ -218,6 +218,28 @@ class WifiContext:
         self._ck(fn(self.h, dt, pk.ptr, lp.ptr, _ptr(symb), _ptr(pre), _ptr(ow2), n))
         return symb, pre, ow2
 
+    RX_CHAIN_PLANES = {"lt_ls": "H_lt", "linear": "H_linear", "cubic": "H_cubic", "sinc": "H_sinc", "mmse_cconv": "H_mmse_cconv",
+                       "ls0": "H_ls0", "mmse": "H_mmse_shared", "eq": "eq", "rx_symb": "rx_symb", "ow2": "ow2"}
+
+    def rx_chain(self, tx_packet, tx_lptot, rx_packet, rx_lptot, want=("lt_ls", "linear", "cubic", "sinc", "mmse_cconv", "eq", "ow2"), out=None):
+        """Fused receiver chain (WiFi_RX.m:17-60 with the C estimators of main.c:66-146): time samples of n frames -> the planes
+        named in `want`, one launch (two with "mmse", the shared-filter PS_MMSE).  Packets [n][1200], lptot [n][160]."""
+        tp, tl, rp, rl = _Arg(tx_packet), _Arg(tx_lptot), _Arg(rx_packet), _Arg(rx_lptot)
+        dev, dt = _same(tp, tl, rp, rl)
+        n = rp.size // 1200
+        if tp.size != n * 1200 or tl.size != n * 160 or rl.size != n * 160:
+            raise ValueError("packets are [n][1200] and lptot [n][160] for the same n")
+        o = dict(out) if out is not None else {}
+        st = _lib.RxChainOut()
+        for name in want:
+            if name not in o:
+                o[name] = rp.empty_like((n,), real=True) if name == "ow2" else rp.empty_like((n, NBLK, NSC) if name in ("eq", "rx_symb") else (n, NSC))
+            setattr(st, self.RX_CHAIN_PLANES[name], _ptr(o[name]))
+        self._sync_stream(dev)
+        fn = self.lib.wifi_rx_chain_batch if dev else self.lib.wifi_rx_chain_host
+        self._ck(fn(self.h, dt, tp.ptr, tl.ptr, rp.ptr, rl.ptr, C.byref(st), n))
+        return o
+
     def equalize(self, rx_frames, H_lt, H_ps, out=None):
         """WiFi_Equalization.m: rx [n][15][53], H_lt / H_ps [n][53] -> [n][15][53]."""
         rx, a, b = _Arg(rx_frames), _Arg(H_lt), _Arg(H_ps)

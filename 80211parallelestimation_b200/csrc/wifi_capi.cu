@@ -363,6 +363,44 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                          const void *sigma2, const void *hls, void *H, int64_t n, int flags, cudaStream_t s, bool check);
 
+// fused receiver chain on device pointers (wifi_frontend.cu rx_chain_kernel); the shared-filter PS_MMSE, when asked for, is the
+// tcgen05 / DMMA GEMM on the H_ls0 plane the chain kernel wrote (scratch if the caller does not want it)
+static int rx_chain(wifi_ctx *ctx, wifi_dtype dt, const void *tx_packet, int64_t tx_pkt_stride, const void *tx_lptot, const void *rx_packet,
+                    const void *rx_lptot, const wifi_rx_chain_out &o, int64_t n, cudaStream_t s, int slot = 0)
+{
+    if (n == 0) return WIFI_OK;
+    void *hls0 = o.H_ls0;
+    if (o.H_mmse_shared) {
+        if (!ctx->img.valid) return fail(ctx, WIFI_ERR_STATE, "no shared filter installed: call wifi_mmse_filter_form/_set first");
+        if (!hls0) {
+            const size_t need = (size_t)n * WIFI_NSC * esize(dt);
+            if (ctx->eig_u_bytes[slot] < need) {
+                CK(cudaStreamSynchronize(s));
+                cudaFree(ctx->eig_u[slot]); ctx->eig_u[slot] = nullptr; ctx->eig_u_bytes[slot] = 0;
+                if (cudaMalloc(&ctx->eig_u[slot], need) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "H_ls scratch cudaMalloc(%zu) failed", need);
+                ctx->eig_u_bytes[slot] = need;
+            }
+            hls0 = ctx->eig_u[slot];
+        }
+    }
+    {
+        Timed t(ctx, s);
+        CK(launch_rx_chain(dt, tx_packet, tx_pkt_stride, tx_lptot, rx_packet, rx_lptot, o.H_lt, o.H_linear, o.H_cubic, o.H_sinc, o.H_mmse_cconv,
+                           hls0, o.eq, o.rx_symb, o.ow2, n, ctx->tab, s));
+    }
+    if (o.H_mmse_shared) return gemm_with(ctx, ctx->img, dt, hls0, nullptr, WIFI_NSC, o.H_mmse_shared, n, s);
+    return WIFI_OK;
+}
+
+int wifi_rx_chain_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_packet, const void *tx_lptot, const void *rx_packet, const void *rx_lptot,
+                        const wifi_rx_chain_out *out, int64_t n)
+{
+    ENTER();
+    NEED(out && n >= 0 && (n == 0 || (tx_packet && tx_lptot && rx_packet && rx_lptot)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    NEED(((((uintptr_t)tx_packet) | ((uintptr_t)tx_lptot) | ((uintptr_t)rx_packet) | ((uintptr_t)rx_lptot)) & 15) == 0);   // 16-byte vector loads
+    return rx_chain(ctx, dt, tx_packet, WIFI_PACKET, tx_lptot, rx_packet, rx_lptot, *out, n, ctx->stream);
+}
+
 // BASELINE configs[4]: all five estimators (+ the equalizer) of n frames behind one call, four launches: LT_LS; the shared-filter
 // PS_MMSE GEMM (reading block 0 of tx / rx in place), whose LS-divide stage also hands the four pilot LS values of every frame
 // to the interpolators as a 32-byte record; the three interpolators from those records (no pilot gather: 8 isolated values per
@@ -739,6 +777,28 @@ int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const v
         Timed t(ctx, s);
         CK(launch_frontend(dt, d[0], d[1], d[2], d[3], ow2 ? d[4] : nullptr, nc, s));
         return (int)WIFI_OK;
+    });
+}
+
+int wifi_rx_chain_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_packet, const void *tx_lptot, const void *rx_packet, const void *rx_lptot,
+                       const wifi_rx_chain_out *out, int64_t n)
+{
+    ENTER();
+    NEED(out && n >= 0 && (n == 0 || (tx_packet && tx_lptot && rx_packet && rx_lptot)) && (dt == WIFI_F32 || dt == WIFI_F64));
+    const size_t es = esize(dt), row = WIFI_NSC * es, frow = WIFI_FRAME * es;
+    // of tx_packet only OFDM block 0 with its cyclic prefix (80 samples) is staged; the kernel then reads it at a stride of 80
+    std::vector<Arr> arrs = {in_arr(tx_packet, 80 * es, WIFI_PACKET * es), in_arr(tx_lptot, WIFI_LPTOT * es, WIFI_LPTOT * es),
+                             in_arr(rx_packet, WIFI_PACKET * es, WIFI_PACKET * es), in_arr(rx_lptot, WIFI_LPTOT * es, WIFI_LPTOT * es)};
+    void *const outs[10] = {out->H_lt, out->H_linear, out->H_cubic, out->H_sinc, out->H_mmse_cconv, out->H_ls0, out->H_mmse_shared, out->eq,
+                            out->rx_symb, out->ow2};
+    const size_t rows[10] = {row, row, row, row, row, row, row, frow, frow, es / 2};
+    int at[10];
+    for (int i = 0; i < 10; ++i) { at[i] = -1; if (outs[i]) { at[i] = (int)arrs.size(); arrs.push_back(out_arr(outs[i], rows[i])); } }
+    return host_pipeline(ctx, n, arrs, [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+        wifi_rx_chain_out o;
+        void **po[10] = {&o.H_lt, &o.H_linear, &o.H_cubic, &o.H_sinc, &o.H_mmse_cconv, &o.H_ls0, &o.H_mmse_shared, &o.eq, &o.rx_symb, &o.ow2};
+        for (int i = 0; i < 10; ++i) *po[i] = at[i] >= 0 ? d[at[i]] : nullptr;
+        return rx_chain(ctx, dt, d[0], 80, d[1], d[2], d[3], o, nc, s, s == ctx->hstream[1] ? 1 : 0);
     });
 }
 

@@ -64,6 +64,36 @@ template <typename T> __device__ __forceinline__ void sincospi_t(T x, T *s, T *c
 template <> __device__ __forceinline__ void sincospi_t<float>(float x, float *s, float *c) { sincospif(x, s, c); }
 template <> __device__ __forceinline__ void sincospi_t<double>(double x, double *s, double *c) { sincospi(x, s, c); }
 
+// Steps B-D for the 4 transforms a warp holds in its tile (natural-order samples at tile[t * FE_TS + n]); on return the 4 x 53
+// kept bins are packed back to back, tile[t * 53 + i] = X_t[(i - 26) mod 64], and visible to the whole warp.
+template <typename T> __device__ __forceinline__ void fft4_rows(cx<T> *tile, const int t, const int j, const cx<T> (&tw)[8])
+{
+    // ---- B. first radix-8 pass over m, twiddle ----
+    cx<T> v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = tile[t * FE_TS + j + 8 * m];
+    dft8<T>(v);
+#pragma unroll
+    for (int p = 1; p < 8; ++p) v[p] = cmul(v[p], tw[p]);
+    __syncwarp();
+    // ---- C. transpose: tile[t][p][j] with rows of 9 (a lane then reads 8 consecutive values at a 72-byte lane
+    //         stride: conflict-free; rows of 8 would be a 4-way conflict), second pass over j on lane (t, p = j) ----
+#pragma unroll
+    for (int p = 0; p < 8; ++p) tile[t * FE_TS + p * 9 + j] = v[p];
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) v[jj] = tile[t * FE_TS + j * 9 + jj];      // this lane's p is its j
+    dft8<T>(v);                                                                // v[c] = X[p + 8 c]
+    __syncwarp();
+    // ---- D. circshift 26, keep 53: X[k] -> y[(k + 26) mod 64]; rows of 53 packed back to back in the tile ----
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int i = (j + 8 * c + 26) & 63;
+        if (i < NSC) tile[t * NSC + i] = v[c];
+    }
+    __syncwarp();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__restrict__ packet, const cx<T> *__restrict__ lptot,
                                                               cx<T> *__restrict__ symb, cx<T> *__restrict__ pre_fft, T *__restrict__ ow2,
@@ -126,30 +156,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__res
             if (lane == 0) ow2[f] = nv * (T)(1.0 / 128.0);
         }
         __syncwarp();
-        // ---- B. first radix-8 pass over m, twiddle ----
-        cx<T> v[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = tile[t * FE_TS + j + 8 * m];
-        dft8<T>(v);
-#pragma unroll
-        for (int p = 1; p < 8; ++p) v[p] = cmul(v[p], tw[p]);
-        __syncwarp();
-        // ---- C. transpose: tile[t][p][j] with rows of 9 (a lane then reads 8 consecutive values at a 72-byte lane
-        //         stride: conflict-free; rows of 8 would be a 4-way conflict), second pass over j on lane (t, p = j) ----
-#pragma unroll
-        for (int p = 0; p < 8; ++p) tile[t * FE_TS + p * 9 + j] = v[p];
-        __syncwarp();
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) v[jj] = tile[t * FE_TS + j * 9 + jj];      // this lane's p is its j
-        dft8<T>(v);                                                                // v[c] = X[p + 8 c]
-        __syncwarp();
-        // ---- D. circshift 26, keep 53: X[k] -> y[(k + 26) mod 64]; rows of 53 packed back to back in the tile ----
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int i = (j + 8 * c + 26) & 63;
-            if (i < NSC) tile[t * NSC + i] = v[c];
-        }
-        __syncwarp();
+        fft4_rows<T>(tile, t, j, tw);                             // steps B-D
         const int n_data = q < 3 ? 4 : 3;                        // data rows in this group (group 3 ends with the preamble)
         cx<T> *dst = symb + (f * NBLK + 4 * q) * NSC;
 #pragma unroll
@@ -176,6 +183,213 @@ cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot
     else
         frontend_kernel<double><<<grid, FE_THREADS, 0, s>>>((const double2 *)packet, (const double2 *)lptot, (double2 *)symb,
                                                             (double2 *)pre_fft, (double *)ow2, n_frames);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused receiver chain: time samples -> all estimates (+ equalized symbols) in ONE pass (WiFi_RX.m:17-60 with
+// the C estimators of main.c:66-146).  The symbols the front-end produces never touch HBM unless the caller asks for them:
+//     in   rx_packet (15 x 64 samples, cyclic prefixes skipped), rx_lptot, tx_lptot, OFDM block 0 of tx_packet   1 280 c
+//     out  H_lt, H_linear, H_cubic, H_sinc (53 each) [+ H_mmse (main.c:148 convention) + H_ls of block 0 + eq (795) + ow2]
+// against front-end x 2 (3 872 c) + estimators + equalizer (2 014 c) through HBM.  One warp per frame, five groups of four
+// transforms:   group 0 = { tx preamble, rx preamble (+ noise estimate), tx block 0, rx block 0 }  ->  LT_LS, the four pilot LS
+// values, the three interpolators, the closed-form rank-one PS_MMSE and the equalized block 0;   groups 1-4 = rx blocks 1-14
+// -> equalized with the blend of the LT_LS and PS_Linear estimates the warp keeps in shared memory (WiFi_Equalization.m:1-9).
+// ------------------------------------------------------------------------------------------
+template <typename T> struct ChainOut {
+    cx<T> *H_lt, *H_lin, *H_cub, *H_sinc, *H_cconv, *H_ls0, *eq, *rx_symb;
+    T *ow2;
+};
+
+constexpr int RC_WT = 3 * NSC * 4;           // interpolation weights staged per CTA: [est][k][4]
+constexpr int RC_WARP_C = 4 * FE_TS + 2 * 56;   // complex values of shared memory per warp: tile + H_lt + H_linear
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(FE_THREADS, MINB) rx_chain_kernel(const cx<T> *__restrict__ tx_packet, const cx<T> *__restrict__ tx_lptot,
+                                                              const cx<T> *__restrict__ rx_packet, const cx<T> *__restrict__ rx_lptot,
+                                                              int64_t tx_pkt_stride, ChainOut<T> out, const T *__restrict__ wtab, int64_t n_frames)
+{
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    T *wt = reinterpret_cast<T *>(rc_smem);                                           // [3][53][4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cx<T> *tile = reinterpret_cast<cx<T> *>(rc_smem + ((RC_WT * sizeof(T) + 15) & ~(size_t)15)) + warp * RC_WARP_C;
+    cx<T> *s_hl = tile + 4 * FE_TS, *s_hp = s_hl + 56;
+    for (int i = threadIdx.x; i < RC_WT; i += FE_THREADS) wt[i] = wtab[i];
+    __syncthreads();
+    const int t = lane >> 3, j = lane & 7;
+    cx<T> tw[8];
+#pragma unroll
+    for (int p = 1; p < 8; ++p) {
+        T s, c;
+        sincospi_t<T>((T)(j * p) * (T)(-1.0 / 32.0), &s, &c);
+        tw[p] = mk<T>(c, s);
+    }
+    const int n2 = 2 * lane;                                      // this lane's two consecutive samples of every transform
+    const int64_t wstride = (int64_t)gridDim.x * FE_WARPS;
+    for (int64_t f = (int64_t)blockIdx.x * FE_WARPS + warp; f < n_frames; f += wstride) {
+        // HBM -> L2 for this warp's NEXT frame: 15 rx blocks (cyclic prefixes skipped), the two long-training symbols of both
+        // sides, tx block 0
+        {
+            const int64_t fn = f + wstride;
+            if (fn < n_frames && lane < 18) {
+                const cx<T> *src; uint32_t cnt = 64;
+                if (lane < NBLK) src = rx_packet + fn * FE_PKT + lane * FE_BLK + FE_CP;
+                else if (lane == 15) { src = rx_lptot + fn * FE_LP + 32; cnt = 128; }
+                else if (lane == 16) { src = tx_lptot + fn * FE_LP + 32; cnt = 128; }
+                else src = tx_packet + fn * tx_pkt_stride + FE_CP;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(cnt * sizeof(cx<T>))) : "memory");
+            }
+        }
+        // ---- group 0: tx preamble, rx preamble (averaged on the fly, WiFi_RX.m:19-29), tx block 0, rx block 0 ----
+        T nv;
+        {
+            cx<T> a0, a1, b0, b1, c0, c1, d0, d1, x0, x1, y0, y1;
+            ld_pair(tx_lptot + f * FE_LP + 96 + n2, a0, a1);
+            ld_pair(tx_lptot + f * FE_LP + 32 + n2, b0, b1);
+            ld_pair(rx_lptot + f * FE_LP + 96 + n2, c0, c1);
+            ld_pair(rx_lptot + f * FE_LP + 32 + n2, d0, d1);
+            ld_pair(tx_packet + f * tx_pkt_stride + FE_CP + n2, x0, x1);
+            ld_pair(rx_packet + f * FE_PKT + FE_CP + n2, y0, y1);
+            tile[0 * FE_TS + n2] = mk<T>((a0.x + b0.x) * (T)0.5, (a0.y + b0.y) * (T)0.5);
+            tile[0 * FE_TS + n2 + 1] = mk<T>((a1.x + b1.x) * (T)0.5, (a1.y + b1.y) * (T)0.5);
+            tile[1 * FE_TS + n2] = mk<T>((c0.x + d0.x) * (T)0.5, (c0.y + d0.y) * (T)0.5);
+            tile[1 * FE_TS + n2 + 1] = mk<T>((c1.x + d1.x) * (T)0.5, (c1.y + d1.y) * (T)0.5);
+            tile[2 * FE_TS + n2] = x0; tile[2 * FE_TS + n2 + 1] = x1;
+            tile[3 * FE_TS + n2] = y0; tile[3 * FE_TS + n2 + 1] = y1;
+            const T e0x = d0.x - c0.x, e0y = d0.y - c0.y, e1x = d1.x - c1.x, e1y = d1.y - c1.y;     // WiFi_RX.m:31
+            nv = warp_sum<T>(e0x * e0x + e0y * e0y + e1x * e1x + e1y * e1y) * (T)(1.0 / 128.0);
+        }
+        if (out.ow2 && lane == 0) out.ow2[f] = nv;
+        __syncwarp();
+        fft4_rows<T>(tile, t, j, tw);
+        // rows: 0 = tx_pre, 1 = rx_pre, 2 = tx block 0, 3 = rx block 0
+        {
+            // pilot LS (main.c:82-84): lane i & 3 divides pilot i, lanes 0..3 broadcast
+            const int pk = WIFI_P0 + (WIFI_P1 - WIFI_P0) * (lane & 3);
+            const cx<T> mine = cdiv(tile[3 * NSC + pk], tile[2 * NSC + pk]);
+            cx<T> hp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hp[i] = mk<T>(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i));
+            cx<T> hl[2], v[2], r0[2];
+            T a3x = 0, a3y = 0, vv = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                hl[h] = v[h] = r0[h] = mk<T>(0, 0);
+                if (k < NSC) {
+                    const cx<T> x0 = tile[2 * NSC + k];
+                    r0[h] = tile[3 * NSC + k];
+                    hl[h] = k == DCBIN ? mk<T>(0, 0) : lt_ls_one<T>(tile[k], tile[NSC + k]);          // main.c:66-75
+                    if (out.H_lt) st_stream(out.H_lt + f * NSC + k, hl[h]);
+                    if (out.H_ls0) st_stream(out.H_ls0 + f * NSC + k, cdiv(r0[h], x0));
+                    const T *w = wt + k * 4;
+                    const cx<T> lin = mk<T>(w[0] * hp[0].x + w[1] * hp[1].x + w[2] * hp[2].x + w[3] * hp[3].x,
+                                            w[0] * hp[0].y + w[1] * hp[1].y + w[2] * hp[2].y + w[3] * hp[3].y);
+                    if (out.H_lin) st_stream(out.H_lin + f * NSC + k, lin);
+                    if (out.H_cub) {
+                        const T *wc = wt + (NSC + k) * 4;
+                        st_stream(out.H_cub + f * NSC + k, mk<T>(wc[0] * hp[0].x + wc[1] * hp[1].x + wc[2] * hp[2].x + wc[3] * hp[3].x,
+                                                                  wc[0] * hp[0].y + wc[1] * hp[1].y + wc[2] * hp[2].y + wc[3] * hp[3].y));
+                    }
+                    if (out.H_sinc) {
+                        const T *ws = wt + (2 * NSC + k) * 4;
+                        st_stream(out.H_sinc + f * NSC + k, mk<T>(ws[0] * hp[0].x + ws[1] * hp[1].x + ws[2] * hp[2].x + ws[3] * hp[3].x,
+                                                                   ws[0] * hp[0].y + ws[1] * hp[1].y + ws[2] * hp[2].y + ws[3] * hp[3].y));
+                    }
+                    s_hl[k] = hl[h]; s_hp[k] = lin;
+                    // rank-one PS_MMSE (main.c:148 convention, mmse_rank1_kernel): v = tx (.) H_lt, a3 = v^H rx, vv = v^H v
+                    v[h] = cmul(x0, hl[h]);
+                    a3x += v[h].x * r0[h].x + v[h].y * r0[h].y;
+                    a3y += v[h].x * r0[h].y - v[h].y * r0[h].x;
+                    vv += v[h].x * v[h].x + v[h].y * v[h].y;
+                    if (out.rx_symb) st_stream(out.rx_symb + f * FRAME + k, r0[h]);
+                    if (out.eq) {                                                                       // block 0: i = 1
+                        const T wp = (T)(1.0 / NBLK), wl = (T)1 - wp;
+                        st_stream(out.eq + f * FRAME + k,
+                                  k == DCBIN ? mk<T>(0, 0) : eq_div(r0[h], mk<T>(wl * hl[h].x + wp * lin.x, wl * hl[h].y + wp * lin.y)));
+                    }
+                }
+            }
+            if (out.H_cconv) {                                     // warp-uniform
+                a3x = warp_sum<T>(a3x); a3y = warp_sum<T>(a3y); vv = warp_sum<T>(vv);
+                const T den = nv + vv;
+                const cx<T> c = mk<T>(a3x / den, a3y / den);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (lane + 32 * h < NSC) st_stream(out.H_cconv + f * NSC + lane + 32 * h, cmul(hl[h], c));
+            }
+        }
+        __syncwarp();
+        if (!out.eq && !out.rx_symb) continue;                     // warp-uniform: the estimates alone need block 0 only
+        // ---- groups 1-4: rx blocks 1..14 -> equalized symbols (and the symbols themselves on request); the samples of the next
+        //      group are requested before the transforms of the current one ----
+        cx<T> nx[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ld_pair(rx_packet + f * FE_PKT + (1 + i) * FE_BLK + FE_CP + n2, nx[i][0], nx[i][1]);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            const int b0 = 1 + 4 * g;
+            const int rows = g < 3 ? 4 : 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { tile[i * FE_TS + n2] = nx[i][0]; tile[i * FE_TS + n2 + 1] = nx[i][1]; }
+            __syncwarp();
+            if (g < 3) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    nx[i][0] = nx[i][1] = mk<T>(0, 0);
+                    if (b0 + 4 + i < NBLK) ld_pair(rx_packet + f * FE_PKT + (b0 + 4 + i) * FE_BLK + FE_CP + n2, nx[i][0], nx[i][1]);
+                }
+            }
+            fft4_rows<T>(tile, t, j, tw);
+            const int64_t base = f * FRAME + b0 * NSC;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int o = i * 32 + lane;
+                if (o < rows * NSC) {
+                    const cx<T> r = tile[o];
+                    if (out.rx_symb) st_stream(out.rx_symb + base + o, r);
+                    if (out.eq) {
+                        const int tt = o / NSC, k = o - tt * NSC;
+                        const T wp = (T)(b0 + tt + 1) * (T)(1.0 / NBLK), wl = (T)1 - wp;               // WiFi_Equalization.m:4-5, i = b + 1
+                        const cx<T> hl = s_hl[k], hq = s_hp[k];
+                        st_stream(out.eq + base + o, k == DCBIN ? mk<T>(0, 0) : eq_div(r, mk<T>(wl * hl.x + wp * hq.x, wl * hl.y + wp * hq.y)));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+cudaError_t launch_rx_chain(wifi_dtype dt, const void *tx_packet, int64_t tx_pkt_stride, const void *tx_lptot, const void *rx_packet, const void *rx_lptot,
+                            void *H_lt, void *H_lin, void *H_cub, void *H_sinc, void *H_cconv, void *H_ls0, void *eq, void *rx_symb, void *ow2,
+                            int64_t n_frames, const InterpTables &tab, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    const int64_t need = (n_frames + FE_WARPS - 1) / FE_WARPS;
+    cudaError_t e;
+    // measured on B200, 256 Ki frames, all planes: FP32 1.035 / 0.976 / 1.191 ms at 2 / 3 / 4 CTAs per SM (116 / 80 / 64 registers);
+    // FP64 2.151 / 3.085 / 3.588 ms (128 registers, then spills)
+#define RC_LAUNCH(T, T2, MB, tabw)                                                                                                         \
+    do {                                                                                                                                   \
+        const size_t smem = ((RC_WT * sizeof(T) + 15) & ~(size_t)15) + (size_t)FE_WARPS * RC_WARP_C * sizeof(T2);                          \
+        if ((e = cudaFuncSetAttribute(rx_chain_kernel<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+        const ChainOut<T> o = {(T2 *)H_lt, (T2 *)H_lin, (T2 *)H_cub, (T2 *)H_sinc, (T2 *)H_cconv, (T2 *)H_ls0, (T2 *)eq, (T2 *)rx_symb, (T *)ow2}; \
+        rx_chain_kernel<T, MB><<<std::min<int64_t>(need, 148 * MB * 2), FE_THREADS, smem, s>>>((const T2 *)tx_packet, (const T2 *)tx_lptot, (const T2 *)rx_packet, \
+                                                                  (const T2 *)rx_lptot, tx_pkt_stride, o, tabw, n_frames);                 \
+    } while (0)
+    if (dt == WIFI_F32) RC_LAUNCH(float, float2, 3, tab.w32);
+    else RC_LAUNCH(double, double2, 2, tab.w64);
+#undef RC_LAUNCH
     return cudaGetLastError();
 }
 

@@ -38,6 +38,12 @@ cudaError_t launch_mmse_rank1(wifi_dtype dt, int matlab, const void *tx, const v
 cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft, void *ow2,
                             int64_t n_frames, cudaStream_t s);
 
+// fused receiver chain (wifi_frontend.cu): time samples -> estimates (+ equalized symbols) in one launch; every output may be NULL.
+// tx_packet is read at tx_pkt_stride complex values per frame (only its OFDM block 0 -- samples 16..79 -- is used)
+cudaError_t launch_rx_chain(wifi_dtype dt, const void *tx_packet, int64_t tx_pkt_stride, const void *tx_lptot, const void *rx_packet,
+                            const void *rx_lptot, void *H_lt, void *H_lin, void *H_cub, void *H_sinc, void *H_cconv, void *H_ls0, void *eq,
+                            void *rx_symb, void *ow2, int64_t n_frames, const InterpTables &tab, cudaStream_t s);
+
 // dense solves (wifi_solve.cu)
 cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s);
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);

@@ -21,14 +21,7 @@ thread_local int g_last_launches = 0;
 // ------------------------------------------------------------------------------------------
 // LT_LS
 // ------------------------------------------------------------------------------------------
-// main.c:69-72 as written: c = Re(tx) - Im(tx) (a real scalar), H = (c*rx)/(c*tx).  Re(tx) == Im(tx)
-// gives 0/0 = NaN exactly like the reference.
-template <typename T> __device__ __forceinline__ cx<T> lt_ls_one(cx<T> tx, cx<T> rx)
-{
-    T c = tx.x - tx.y;
-    return cdiv(mk<T>(c * rx.x, c * rx.y), mk<T>(c * tx.x, c * tx.y));
-}
-
+// lt_ls_one() -- main.c:69-72 as written -- lives in wifi_common.cuh (shared with the fused receiver chain)
 constexpr int LT_THREADS = 256;
 constexpr int LT_UNROLL = 4;
 
@@ -218,17 +211,7 @@ cudaError_t launch_ps(wifi_dtype dt, int which, const void *tx, const void *rx, 
 constexpr int EQ_THREADS = 256;
 constexpr int EQ_UNROLL = 4;
 
-// r / h for the FP32 equalizer with one reciprocal (MUFU.RCP + Newton step, relative error ~1e-7, branch-free); the IEEE
-// '/' of cdiv() is ~12 instructions and a slow-path branch per real divide.  0/0 still yields NaN.
-__device__ __forceinline__ float2 eq_div(float2 a, float2 b)
-{
-    const float den = fmaf(b.x, b.x, b.y * b.y);
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-    r = fmaf(r, fmaf(-den, r, 1.0f), r);
-    return make_float2(fmaf(a.x, b.x, a.y * b.y) * r, fmaf(a.y, b.x, -a.x * b.y) * r);
-}
-__device__ __forceinline__ double2 eq_div(double2 a, double2 b) { return cdiv(a, b); }
+// eq_div() -- r / h with one reciprocal in FP32 -- lives in wifi_common.cuh (shared with the fused receiver chain)
 
 // one equalized value: element 795 (fb + q) + rem' of the flat [n][15][53] array, given as frame base fb and a 32-bit
 // offset rem >= 0 from that frame's first element (64-bit divisions per element cost more than the memory traffic)

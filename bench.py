@@ -355,7 +355,17 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
             fe_out = (torch.empty(nfe, NBLK, NSC, dtype=cdt, device=tx0.device), torch.empty(nfe, NSC, dtype=cdt, device=tx0.device),
                       torch.empty(nfe, dtype=rdt, device=tx0.device))
             X.rate("frontend_" + prec, lambda: ctx.frontend(pk, lp, out=fe_out), nfe, (1088 + 848) * cbytes + cbytes // 2, config="8(f)1")
-            del pk, lp, fe_out
+            del fe_out
+            # fused receiver chain (wifi_rx_chain_batch): time samples of both sides -> 5 estimates + equalized symbols + ow2 in ONE
+            # launch; 1 280 c in (rx: 15 x 64 + 128, tx: block 0 + 128), 5 x 53 + 795 c out.  The unfused path moves 5 886 c.
+            pk2 = torch.randn(nfe, 1200, dtype=cdt, device=tx0.device); lp2 = torch.randn(nfe, 160, dtype=cdt, device=tx0.device)
+            want = ("lt_ls", "linear", "cubic", "sinc", "mmse_cconv", "eq", "ow2")
+            ch_out = ctx.rx_chain(pk, lp, pk2, lp2, want=want)
+            X.rate("rx_chain_" + prec, lambda: ctx.rx_chain(pk, lp, pk2, lp2, want=want, out=ch_out), nfe, (1280 + 5 * 53 + 795) * cbytes + cbytes // 2,
+                   config="8(f)1 fused: time samples -> LT_LS, PS_Linear/Cubic/Sinc, PS_MMSE (main.c:148 convention), equalizer, one launch",
+                   note="the front-end's OFDM symbols never round-trip through HBM; the same planes through wifi_frontend_batch x 2 + "
+                        "the stand-alone estimators and equalizer move 5 886 c per frame")
+            del pk, lp, pk2, lp2, ch_out
             # PS_MMSE in main.c:148's calling convention (R_f = H_ls H_ls^H), rank-one closed form: 212 c + ow2 per frame
             Hc = torch.empty_like(tx0)
             X.rate("mmse_cconv_" + prec, lambda: ctx.mmse_cconv(tx0, rx0, s2n, H, out=Hc), n, 212 * cbytes + cbytes // 2, config="main.c:148 convention")

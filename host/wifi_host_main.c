@@ -10,7 +10,8 @@
  *
  *   part 3  (--file in out [gpus]) streaming frame-file pipeline: a WIFI_FILE_FREQ or WIFI_FILE_TIME file
  *           (include/wifi_frame_file.h) is sharded by contiguous frame ranges over the GPUs; per GPU a reader thread, a
- *           dispatcher and a writer thread share a ring of pinned slots, so file reads, H2D, the front-end (TIME files), all
+ *           dispatcher and a writer thread share a ring of pinned slots, so file reads, H2D, the kernels (TIME files: the fused receiver
+ *           chain wifi_rx_chain_batch, one launch from time samples to estimates + equalized symbols; FREQ files: all
  *           five estimators (PS_MMSE in main.c:148's calling convention, R_f = H_lt H_lt^H), the equalizer, D2H and file
  *           writes of different chunks overlap; the results are written as a WIFI_FILE_EST file.
  *
@@ -127,7 +128,7 @@ static void *shard_main(void *arg)
 
 typedef struct {
     void *hin[4], *hout[7];
-    void *din[4], *dsymb[2], *dpre[2], *dow2, *dH[5], *deq, *dblk;
+    void *din[4], *dow2, *dH[5], *deq, *dblk;
     cudaStream_t st;
     cudaEvent_t done;
     long f0, nc;
@@ -209,7 +210,6 @@ static void *fp_worker_main(void *arg)
         fp_slot *s = &w->slot[k];
         for (int i = 0; i < 4; ++i) { FCK(wifi_host_alloc(&s->hin[i], FP_CHUNK * w->in_w[i] * es)); CCK(cudaMalloc(&s->din[i], FP_CHUNK * w->in_w[i] * es)); }
         for (int i = 0; i < 7; ++i) FCK(wifi_host_alloc(&s->hout[i], FP_CHUNK * out_bytes(w, i)));
-        for (int i = 0; i < 2; ++i) { CCK(cudaMalloc(&s->dsymb[i], FP_CHUNK * WIFI_FRAME * es)); CCK(cudaMalloc(&s->dpre[i], FP_CHUNK * NSC * es)); }
         for (int i = 0; i < 5; ++i) CCK(cudaMalloc(&s->dH[i], FP_CHUNK * NSC * es));
         CCK(cudaMalloc(&s->deq, FP_CHUNK * WIFI_FRAME * es)); CCK(cudaMalloc(&s->dow2, FP_CHUNK * es / 2)); CCK(cudaMalloc(&s->dblk, 2 * FP_CHUNK * NSC * es));
         CCK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)); CCK(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
@@ -233,26 +233,29 @@ static void *fp_worker_main(void *arg)
         const long nc = s->nc;
         FCK(wifi_set_stream(ctx, s->st));
         for (int i = 0; i < 4; ++i) CCK(cudaMemcpyAsync(s->din[i], s->hin[i], (size_t)nc * w->in_w[i] * es, cudaMemcpyHostToDevice, s->st));
-        const void *tx_pre, *rx_pre, *tx_symb, *rx_symb;
-        if (w->kind == WIFI_FILE_TIME) {                              /* time samples -> symbols, preamble spectra, noise estimate */
-            FCK(wifi_frontend_batch(ctx, dt, s->din[0], s->din[2], s->dsymb[0], s->dpre[0], NULL, nc));
-            FCK(wifi_frontend_batch(ctx, dt, s->din[1], s->din[3], s->dsymb[1], s->dpre[1], s->dow2, nc));
-            tx_pre = s->dpre[0]; rx_pre = s->dpre[1]; tx_symb = s->dsymb[0]; rx_symb = s->dsymb[1];
+        if (w->kind == WIFI_FILE_TIME) {
+            /* time samples -> every estimate, the equalized symbols and the noise estimate in ONE launch: the OFDM symbols the
+             * front-end produces never round-trip through HBM (wifi_rx_chain_batch; inputs tx_packet rx_packet tx_lptot rx_lptot) */
+            wifi_rx_chain_out o;
+            memset(&o, 0, sizeof o);
+            o.H_lt = s->dH[0]; o.H_linear = s->dH[1]; o.H_cubic = s->dH[2]; o.H_sinc = s->dH[3]; o.H_mmse_cconv = s->dH[4];
+            o.eq = s->deq; o.ow2 = s->dow2;
+            FCK(wifi_rx_chain_batch(ctx, dt, s->din[0], s->din[2], s->din[1], s->din[3], &o, nc));
         } else {
-            tx_pre = s->din[0]; rx_pre = s->din[1]; tx_symb = s->din[2]; rx_symb = s->din[3];
+            const void *tx_pre = s->din[0], *rx_pre = s->din[1], *tx_symb = s->din[2], *rx_symb = s->din[3];
             /* inputs.h carries ow2 as a constant (inputs.h:18); FREQ files use it for every frame */
             if (dt == WIFI_F32) { float *v = (float *)s->hout[6]; for (long i = 0; i < nc; ++i) v[i] = 9.6172e-08f; }
             else { double *v = (double *)s->hout[6]; for (long i = 0; i < nc; ++i) v[i] = 9.6172e-08; }
             CCK(cudaMemcpyAsync(s->dow2, s->hout[6], (size_t)nc * es / 2, cudaMemcpyHostToDevice, s->st));
+            FCK(wifi_lt_ls_batch(ctx, dt, tx_pre, rx_pre, s->dH[0], nc));
+            FCK(wifi_ps_batch(ctx, dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx_symb, rx_symb, WIFI_FRAME, s->dH[1], s->dH[2], s->dH[3], nc));
+            /* main.c:148 calling convention on block 0 (main.c:30-33): frame_stride is fixed at 53 there, so gather block 0 */
+            void *tx0 = s->dblk, *rx0 = (char *)s->dblk + (size_t)nc * NSC * es;
+            CCK(cudaMemcpy2DAsync(tx0, NSC * es, tx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
+            CCK(cudaMemcpy2DAsync(rx0, NSC * es, rx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
+            FCK(wifi_mmse_cconv_batch(ctx, dt, tx0, rx0, s->dow2, s->dH[0], s->dH[4], nc));
+            FCK(wifi_equalize_batch(ctx, dt, rx_symb, s->dH[0], s->dH[1], s->deq, nc));
         }
-        FCK(wifi_lt_ls_batch(ctx, dt, tx_pre, rx_pre, s->dH[0], nc));
-        FCK(wifi_ps_batch(ctx, dt, WIFI_PS_LINEAR | WIFI_PS_CUBIC | WIFI_PS_SINC, tx_symb, rx_symb, WIFI_FRAME, s->dH[1], s->dH[2], s->dH[3], nc));
-        /* main.c:148 calling convention on block 0 (main.c:30-33): frame_stride is fixed at 53 there, so gather block 0 */
-        void *tx0 = s->dblk, *rx0 = (char *)s->dblk + (size_t)nc * NSC * es;
-        CCK(cudaMemcpy2DAsync(tx0, NSC * es, tx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
-        CCK(cudaMemcpy2DAsync(rx0, NSC * es, rx_symb, WIFI_FRAME * es, NSC * es, nc, cudaMemcpyDeviceToDevice, s->st));
-        FCK(wifi_mmse_cconv_batch(ctx, dt, tx0, rx0, s->dow2, s->dH[0], s->dH[4], nc));
-        FCK(wifi_equalize_batch(ctx, dt, rx_symb, s->dH[0], s->dH[1], s->deq, nc));
         for (int i = 0; i < 5; ++i) CCK(cudaMemcpyAsync(s->hout[i], s->dH[i], (size_t)nc * NSC * es, cudaMemcpyDeviceToHost, s->st));
         CCK(cudaMemcpyAsync(s->hout[5], s->deq, (size_t)nc * WIFI_FRAME * es, cudaMemcpyDeviceToHost, s->st));
         CCK(cudaMemcpyAsync(s->hout[6], s->dow2, (size_t)nc * es / 2, cudaMemcpyDeviceToHost, s->st));
@@ -270,7 +273,6 @@ done:
         fp_slot *s = &w->slot[k];
         for (int i = 0; i < 4; ++i) { if (s->hin[i]) wifi_host_free(s->hin[i]); cudaFree(s->din[i]); }
         for (int i = 0; i < 7; ++i) if (s->hout[i]) wifi_host_free(s->hout[i]);
-        for (int i = 0; i < 2; ++i) { cudaFree(s->dsymb[i]); cudaFree(s->dpre[i]); }
         for (int i = 0; i < 5; ++i) cudaFree(s->dH[i]);
         cudaFree(s->deq); cudaFree(s->dow2); cudaFree(s->dblk);
         if (s->st) cudaStreamDestroy(s->st);

@@ -125,6 +125,22 @@ int wifi_estimate_all_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, co
 int wifi_frontend_batch(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft,
                         void *ow2, int64_t n_frames);
 
+/* ---- fused receiver chain: time samples -> every estimate (+ equalized symbols) in ONE launch ----
+ * WiFi_RX.m:17-60 with the C estimators of main.c:66-146 (OFDM block 0, C cubic): the front-end's symbols never round-trip
+ * through HBM.  tx_packet / rx_packet [n][1200], tx_lptot / rx_lptot [n][160], 16-byte aligned; of tx_packet only OFDM block 0
+ * (samples 16..79 of every frame) is read.  Every output may be NULL:
+ *   H_lt, H_linear, H_cubic, H_sinc [n][53]   LT_LS and the three pilot interpolators
+ *   H_mmse_cconv [n][53]   PS_MMSE in the main.c:148 calling convention (R_f = H_lt H_lt^H, ow2 = the frame's noise estimate)
+ *   H_ls0 [n][53]          rx/tx of OFDM block 0 (the LS input of the shared-filter / per-frame PS_MMSE)
+ *   H_mmse_shared [n][53]  the installed shared filter (wifi_mmse_filter_form/_set) applied to H_ls0 (a second launch)
+ *   eq [n][15][53]         WiFi_Equalization.m with H_lt and H_linear;  rx_symb [n][15][53] the rx symbols themselves
+ *   ow2 [n] real           WiFi_RX.m:31 */
+typedef struct {
+    void *H_lt, *H_linear, *H_cubic, *H_sinc, *H_mmse_cconv, *H_ls0, *H_mmse_shared, *eq, *rx_symb, *ow2;
+} wifi_rx_chain_out;
+int wifi_rx_chain_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_packet, const void *tx_lptot, const void *rx_packet,
+                        const void *rx_lptot, const wifi_rx_chain_out *out, int64_t n_frames);
+
 /* ---- PS_MMSE, intended formula  H = R (R + s2 (X X^H)^-1)^-1 (rx/tx) ------------- */
 /* Shared-filter case.  Form W = R (R + diag(d))^-1 once in FP64 on the device
  * (R: 53x53 double2 row-major, d: 53 doubles = s2/|x_k|^2, W_out: optional 53x53 double2)
@@ -209,6 +225,9 @@ int wifi_estimate_all_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_pre, con
                            void *H_lt, void *H_linear, void *H_cubic, void *H_sinc, void *H_mmse, void *eq, int64_t n_frames);
 int wifi_frontend_host(wifi_ctx *ctx, wifi_dtype dt, const void *packet, const void *lptot, void *symb, void *pre_fft,
                        void *ow2, int64_t n_frames);
+/* host arrays: of tx_packet only the 80 samples of OFDM block 0 cross the bus */
+int wifi_rx_chain_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_packet, const void *tx_lptot, const void *rx_packet,
+                       const void *rx_lptot, const wifi_rx_chain_out *out, int64_t n_frames);
 int wifi_mmse_filter_form_host(wifi_ctx *ctx, const void *R_f64, const double *d_f64, void *W_out_f64);
 int wifi_mmse_shared_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                           int64_t frame_stride, void *H, int64_t n_frames);

@@ -210,6 +210,86 @@ def test_frontend_ragged_and_host(ctx, oracle, prec, n):
     assert np.array_equal(hs, host(symb)) and np.array_equal(hp, host(pre)) and np.array_equal(ho, host(ow2))
 
 
+def _chain_oracle(oracle, td, prec):
+    """The oracle's receiver chain, stage by stage: front-end (both sides) -> LT_LS, PS_* on block 0, rank-one PS_MMSE, equalizer."""
+    c = lambda k: r32(td[k].astype(CDT[prec]), prec)
+    ts, tp, _ = oracle.frontend(c("tx_packet"), c("tx_lptot"))
+    rs, rp, ow2 = oracle.frontend(c("rx_packet"), c("rx_lptot"))
+    tx0, rx0 = ts[:, 0, :].copy(), rs[:, 0, :].copy()
+    ref = {"lt_ls": oracle.lt_ls(tp, rp), "linear": oracle.ps_linear(tx0, rx0), "cubic": oracle.ps_cubic(tx0, rx0),
+           "sinc": oracle.ps_sinc(tx0, rx0), "ls0": rx0 / tx0, "rx_symb": rs, "ow2": ow2}
+    ref["mmse_cconv"] = oracle.mmse_cconv_batch(tx0, rx0, ow2, ref["lt_ls"])
+    ref["eq"] = oracle.equalize(rs, ref["lt_ls"], ref["linear"])
+    return ref
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n", [0, 1, 3, 8, 301])
+def test_rx_chain_fused(ctx, oracle, prec, n):
+    """Time samples -> all estimates + equalized symbols in one launch (wifi_rx_chain_*): every plane against the oracle's
+    stage-by-stage chain, against the unfused device path, and through the host entry point."""
+    fr = synth.make_frames(max(n, 1), seed=4100 + n)
+    td = {k: v[:n] for k, v in synth.to_time_domain(fr).items()}
+    a = lambda k: td[k].astype(CDT[prec])
+    want = ("lt_ls", "linear", "cubic", "sinc", "mmse_cconv", "ls0", "eq", "rx_symb", "ow2")
+    got = ctx.rx_chain(dev(a("tx_packet")), dev(a("tx_lptot")), dev(a("rx_packet")), dev(a("rx_lptot")), want=want)
+    if n == 0:
+        assert all(host(got[k]).shape[0] == 0 for k in want)
+        return
+    ref = _chain_oracle(oracle, td, prec)
+    tol = TOL[prec]
+    for k in ("lt_ls", "linear", "cubic", "sinc", "rx_symb", "mmse_cconv"):
+        assert rel_err(host(got[k]), ref[k]) < tol, k
+    # H_ls of block 0: the DC bin divides by tx = -1e-4, which an FP32 64-point FFT of O(1) samples only knows to ~0.5 %
+    keep = np.arange(NSC) != 26
+    assert rel_err(host(got["ls0"])[:, keep], ref["ls0"][:, keep]) < tol
+    assert rel_err(host(got["ls0"])[:, 26:27], ref["ls0"][:, 26:27]) < (tol if prec == "f64" else 5e-2)
+    assert np.allclose(host(got["ow2"]), ref["ow2"], rtol=1e-12 if prec == "f64" else 1e-5)
+    assert rel_err(host(got["eq"]), ref["eq"], floor=1e-6) < (tol if prec == "f64" else 2e-4)
+    assert np.all(host(got["eq"])[:, :, 26] == 0) and np.all(host(got["lt_ls"])[:, 26] == 0)
+    # the unfused device path: front-end x 2, then the estimators on the symbols it wrote
+    ts, tp, _ = ctx.frontend(dev(a("tx_packet")), dev(a("tx_lptot")))
+    rs, rp, ow2 = ctx.frontend(dev(a("rx_packet")), dev(a("rx_lptot")))
+    assert rel_err(host(got["rx_symb"]), host(rs).astype(complex)) < (1e-13 if prec == "f64" else 1e-6)
+    assert np.allclose(host(ow2), host(got["ow2"]), rtol=1e-13 if prec == "f64" else 1e-6)
+    ps = ctx.ps(ts, rs)
+    for k in ("linear", "cubic", "sinc"):
+        assert rel_err(host(got[k]), host(ps[k]).astype(complex)) < (1e-13 if prec == "f64" else 1e-5), k
+    assert rel_err(host(got["lt_ls"]), host(ctx.lt_ls(tp, rp)).astype(complex)) < (1e-13 if prec == "f64" else 1e-5)
+    # estimates only (no equalizer, no symbols): the kernel stops after group 0
+    few = ctx.rx_chain(dev(a("tx_packet")), dev(a("tx_lptot")), dev(a("rx_packet")), dev(a("rx_lptot")), want=("linear", "mmse_cconv"))
+    assert np.array_equal(host(few["linear"]), host(got["linear"])) and np.array_equal(host(few["mmse_cconv"]), host(got["mmse_cconv"]))
+    # host pointers: H2D (tx block 0 only) + kernel + D2H
+    hg = ctx.rx_chain(a("tx_packet"), a("tx_lptot"), a("rx_packet"), a("rx_lptot"), want=want)
+    for k in want:
+        assert np.array_equal(hg[k], host(got[k])), k
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_rx_chain_shared_filter_and_matlab_workspace(ctx, oracle, gold, prec):
+    """The chain's shared-filter PS_MMSE (second launch on the H_ls plane) and the reference's own time samples (matlab.mat)."""
+    n = 130
+    fr = synth.make_frames(n, seed=4242)
+    td = synth.to_time_domain(fr)
+    a = lambda k: td[k].astype(CDT[prec])
+    R = synth.channel_covariance()
+    d = synth.OW2 / np.abs(fr["tx_symb"][0, 0, :]) ** 2
+    W = host(ctx.mmse_filter_form(dev(R), dev(d)))
+    got = ctx.rx_chain(dev(a("tx_packet")), dev(a("tx_lptot")), dev(a("rx_packet")), dev(a("rx_lptot")), want=("mmse", "lt_ls"))
+    ref = _chain_oracle(oracle, td, prec)
+    if prec == "f64":
+        assert rel_err(host(got["mmse"]), oracle.mmse_apply(W, ref["ls0"])) < 1e-10
+    else:
+        assert rel_err(host(got["mmse"]), oracle.mmse_apply(W, ref["ls0"]), 1e-2) < 2e-4      # FFT (1e-6 of the peak) + 3xTF32 GEMM
+    m = gold["matlab_mat"]
+    pk = lambda sd, nm, w: dev(m[sd + nm].reshape(1, w).astype(CDT[prec]))
+    g1 = ctx.rx_chain(pk("tx", "_packet", 1200), pk("tx", "_lptot", 160), pk("rx", "_packet", 1200), pk("rx", "_lptot", 160),
+                      want=("lt_ls", "rx_symb", "ow2"))
+    assert rel_err(host(g1["lt_ls"])[0], m["H_EST_LT_LS"].ravel()) < TOL[prec]
+    assert rel_err(host(g1["rx_symb"])[0], m["rx_symb"].T) < TOL[prec]
+    assert abs(host(g1["ow2"])[0] / float(gold["inputs_h"]["ow2"]) - 1) < 1e-4
+
+
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_wifi_rx_m_end_to_end(ctx, oracle, gold, prec):
     """WiFi_RX.m on the device: the reference's time samples -> front-end -> LT_LS -> PS_Linear/Cubic/Sinc in MATLAB mode
