@@ -47,6 +47,7 @@ cudaError_t launch_rx_chain(wifi_dtype dt, const void *tx_packet, int64_t tx_pkt
 // dense solves (wifi_solve.cu)
 cudaError_t launch_filter_form(const void *R64, const double *d64, void *W64, int *info, cudaStream_t s);
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);
+cudaError_t launch_cinverse_tc(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s);   // orders 33..64 (wifi_inverse_tc.cu)
 cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                                        const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info, int fast32,
                                        cudaStream_t s);

@@ -1,0 +1,394 @@
+// wifi_inverse_tc.cu -- batched inverse() (utils.c:141-170) for orders 33..64 with the trailing updates on the tensor cores.
+//
+// ONE WARP PER MATRIX, the matrix resident in shared memory, no CTA barrier anywhere: the blocked in-place Gauss-Jordan with
+// implicit partial pivoting of tests/test_inverse_blocked_model.py,
+//        A  <-  A - C' R~      per NB pivot columns (the panel columns then take the factored panel),
+// C' = the NB multiplier vectors (+ e_(r_s): stands in for zeroing the pivot rows), R~ = the NB pivot rows after a unit-lower-
+// triangular transform.  A complex rank-NB update is a real rank-2NB product: with the matrix stored as real planes -- per row
+// tile the real parts of TR complex rows followed by their imaginary parts --
+//        [Re A; Im A]  -=  [Re C', -Im C'; Im C', Re C'] [Re R~; Im R~]
+// has exactly the shape of one warp-level MMA per tile and block step, and a lane builds its whole A (B) fragment from ONE
+// complex element of C' (R~):
+//   FP32  mma.sync.m16n8k8.tf32, NB = 4, 3xTF32 (hi/lo split of both operands, FP32 accumulate: FP32-level accuracy); row tile =
+//         8 complex rows.  A fragment of lane (g, t): a0 = a3 = Re c, a1 = -a2 = Im c, c = C'[8 rt + g][t]; B: b0, b1 = Re, Im of
+//         R~[t][8 ct + g]; C: (c0, c1) = Re, (c2, c3) = Im of a[8 rt + g][8 ct + 2t, +1].
+//   FP64  mma.sync.m8n8k4.f64 (DMMA), NB = 2; row tile = 4 complex rows.  Lane (g, t): A = +-Re/Im of C'[4 rt + (g & 3)][t & 1],
+//         B = Re/Im of R~[t & 1][8 ct + g], C = a[4 rt + (g & 3)][8 ct + 2t, +1] (Re for g < 4, Im for g >= 4).
+// Per block step the warp (1) reads the panel columns (lane = rows lane, lane + 32), (2) factors the panel in registers -- per
+// column one redux.sync arg-max over the rows not used yet, the pivot row's NB values by shuffle, one reciprocal -- and publishes
+// -C', (3) reads the NB pivot rows and transforms them (lane = columns lane, lane + 32), (4) runs the NT x NT tile updates with
+// the accumulators streamed through shared memory (conflict-free row stride), (5) writes the factored panel back.
+// The register-resident CTA-per-matrix kernel this replaces (cinverse_blk_kernel, rounds 1-2) was bound by its two CTA barriers
+// and the one-warp panel per block step: 9.4 M (FP32) / 4.8 M (FP64) matrices/s = 15 % of the FMA peaks.
+#include <algorithm>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+template <typename T> struct IwT;
+template <> struct IwT<float> { static constexpr int NB = 4, TR = 8; };     // pivot columns per block step, complex rows per row tile
+template <> struct IwT<double> { static constexpr int NB = 2, TR = 4; };
+
+template <typename T, int NT> struct IwLayout {
+    static constexpr int NB = IwT<T>::NB, TR = IwT<T>::TR;
+    static constexpr int N8 = 8 * NT;                                     // padded order (column tiles of 8)
+    static constexpr int LD = N8 + ((N8 % 16 == 0) ? 8 : 0);              // row stride of the planes: LD mod 16 == 8 -> conflict-free accumulator tiles
+    static constexpr int ROWS = 2 * N8;
+    static constexpr int RLD = N8 + 4;                                    // row stride of R~ in complex values (RLD mod 8 == 4: conflict-free B fragments)
+    static constexpr size_t BYTES = sizeof(T) * ((size_t)ROWS * LD + 2 * N8 * NB + 2 * NB * RLD) + 2 * 64;     // + rowof, kof (bytes)
+};
+
+__device__ __forceinline__ float iw_rcp(float d)
+{
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(d));
+    return fmaf(x, fmaf(-d, x, 1.0f), x);
+}
+__device__ __forceinline__ double iw_rcp(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    x = fma(x, fma(-d, x, 1.0), x);
+    return fma(x, fma(-d, x, 1.0), x);
+}
+__device__ __forceinline__ unsigned iw_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned iw_bits(double v) { return (unsigned)__double2hiint(v); }
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_f64(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// Accumulator tiles go through ld/st.volatile.shared: ptxas keeps volatile accesses in program order, which pins the software
+// pipeline of iw_update (with plain accesses it re-serialises every tile into LDS -> MMA -> STS on two register sets).
+__device__ __forceinline__ float2 lds_acc(const float *p)
+{
+    float2 v;
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ void sts_acc(float *p, float x, float y)
+{
+    asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ double2 lds_acc(const double *p)
+{
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ void sts_acc(double *p, double x, double y)
+{
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "d"(x), "d"(y) : "memory");
+}
+
+// NB consecutive plane values (one panel row, real or imaginary parts) as one 16-byte access
+__device__ __forceinline__ void ld_panel(const float *p, float (&v)[4]) { const float4 q = *reinterpret_cast<const float4 *>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+__device__ __forceinline__ void ld_panel(const double *p, double (&v)[2]) { const double2 q = *reinterpret_cast<const double2 *>(p); v[0] = q.x; v[1] = q.y; }
+__device__ __forceinline__ void st_panel(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st_panel(double *p, const double (&v)[2]) { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
+// one row of -C' (NB complex values) as 16-byte stores
+__device__ __forceinline__ void st_crow(float2 *p, const float2 (&c)[4])
+{
+    reinterpret_cast<float4 *>(p)[0] = make_float4(c[0].x, c[0].y, c[1].x, c[1].y);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(c[2].x, c[2].y, c[3].x, c[3].y);
+}
+__device__ __forceinline__ void st_crow(double2 *p, const double2 (&c)[2]) { p[0] = c[0]; p[1] = c[1]; }
+
+// plane row of the real part of complex row i (the imaginary part sits TR rows below)
+template <int TR> __device__ __forceinline__ int erow(int i) { return (i / TR) * (2 * TR) + (i % TR); }
+
+// ---- step 4, FP32: all NT x NT tiles, 3xTF32 ----
+// Software-pipelined over the column tiles: the accumulators of column tile ct + 1 are loaded and their MMAs issued BEFORE the
+// results of ct are stored, so the store never waits for a tensor-core result (ncu, first version: a quarter of all stall samples
+// sat on the STS behind the HMMA chain).
+template <int NT> __device__ __forceinline__ void iw_update(float *M, const float2 *Cn, const float2 *Rho, int lane)
+{
+    using L = IwLayout<float, NT>;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t arh[NT], arl[NT], aih[NT], ail[NT], nih[NT], nil[NT];
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt) {
+        const float2 c = Cn[(8 * rt + g) * 4 + t];                         // -C'[8 rt + g][t]
+        split_tf32(c.x, arh[rt], arl[rt]);
+        split_tf32(c.y, aih[rt], ail[rt]);
+        nih[rt] = aih[rt] ^ 0x80000000u; nil[rt] = ail[rt] ^ 0x80000000u;
+    }
+    float *const p0 = M + (g * L::LD + 2 * t);
+    const float2 *const r0 = Rho + t * L::RLD + g;
+    float acc[2][NT][4];
+    auto issue = [&](int ct, float (&a)[NT][4]) {
+        const float2 b = r0[8 * ct];
+        uint32_t brh, brl, bih, bil;
+        split_tf32(b.x, brh, brl);
+        split_tf32(b.y, bih, bil);
+        const float *p = p0 + 8 * ct;
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt) {
+            const float2 re = lds_acc(p + rt * 16 * L::LD), im = lds_acc(p + (rt * 16 + 8) * L::LD);
+            a[rt][0] = re.x; a[rt][1] = re.y; a[rt][2] = im.x; a[rt][3] = im.y;
+        }
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arl[rt], ail[rt], nil[rt], arl[rt], brh, bih);       // A_lo B_hi
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arh[rt], aih[rt], nih[rt], arh[rt], brl, bil);       // A_hi B_lo
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arh[rt], aih[rt], nih[rt], arh[rt], brh, bih);       // A_hi B_hi
+    };
+    issue(0, acc[0]);
+#pragma unroll
+    for (int ct = 0; ct < NT; ++ct) {
+        if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
+        float *p = p0 + 8 * ct;
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt) {
+            sts_acc(p + rt * 16 * L::LD, acc[ct & 1][rt][0], acc[ct & 1][rt][1]);
+            sts_acc(p + (rt * 16 + 8) * L::LD, acc[ct & 1][rt][2], acc[ct & 1][rt][3]);
+        }
+    }
+}
+
+// ---- step 4, FP64: 2 NT x NT tiles of 8 x 8 doubles, one DMMA each; pipelined like the FP32 form ----
+template <int NT> __device__ __forceinline__ void iw_update(double *M, const double2 *Cn, const double2 *Rho, int lane)
+{
+    using L = IwLayout<double, NT>;
+    const int g = lane >> 2, t = lane & 3;
+    // A[g][k]: Re rows (g < 4): k < 2 -> Re c, k >= 2 -> -Im c;  Im rows: k < 2 -> Im c, k >= 2 -> Re c;  c = -C'[4 rt + (g & 3)][k & 1]
+    const int apart = (g >> 2) ^ (t >> 1);
+    const bool aneg = g < 4 && t >= 2;
+    double af[2 * NT];
+#pragma unroll
+    for (int rt = 0; rt < 2 * NT; ++rt) {
+        const double v = reinterpret_cast<const double *>(Cn + (4 * rt + (g & 3)) * 2 + (t & 1))[apart];
+        af[rt] = aneg ? -v : v;
+    }
+    double *const p0 = M + (g * L::LD + 2 * t);
+    const double *const r0 = reinterpret_cast<const double *>(Rho + (t & 1) * L::RLD + g) + (t >> 1);
+    double acc[2][2 * NT][2];
+    auto issue = [&](int ct, double (&a)[2 * NT][2]) {
+        const double bf = r0[16 * ct];                                       // R~[t & 1][8 ct + g], Re (t < 2) or Im
+        const double *p = p0 + 8 * ct;
+#pragma unroll
+        for (int rt = 0; rt < 2 * NT; ++rt) {
+            const double2 v = lds_acc(p + rt * 8 * L::LD);
+            a[rt][0] = v.x; a[rt][1] = v.y;
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2 * NT; ++rt) mma_f64(a[rt], af[rt], bf);
+    };
+    issue(0, acc[0]);
+#pragma unroll
+    for (int ct = 0; ct < NT; ++ct) {
+        if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
+        double *p = p0 + 8 * ct;
+#pragma unroll
+        for (int rt = 0; rt < 2 * NT; ++rt) sts_acc(p + rt * 8 * L::LD, acc[ct & 1][rt][0], acc[ct & 1][rt][1]);
+    }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(256) cinverse_warp_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info, int64_t batch)
+{
+    using L = IwLayout<T, NT>;
+    constexpr int NB = L::NB, TR = L::TR, N8 = L::N8, LD = L::LD;
+    extern __shared__ __align__(16) unsigned char iw_smem[];
+    const int64_t mat = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp = one matrix; warps never meet
+    if (mat >= batch) return;
+    T *M = reinterpret_cast<T *>(iw_smem + (threadIdx.x >> 5) * L::BYTES);                // [2 N8][LD] real planes
+    cx<T> *Cn = reinterpret_cast<cx<T> *>(M + (size_t)L::ROWS * LD);     // [N8][NB]: -C'
+    cx<T> *Rho = Cn + N8 * NB;                                           // [NB][RLD]: transformed pivot rows
+    unsigned char *rowof = reinterpret_cast<unsigned char *>(Rho + NB * L::RLD), *kof = rowof + 64;
+    const int lane = threadIdx.x & 31;
+    const cx<T> *Ab = A + mat * n * n;
+    cx<T> *Yb = Y + mat * n * n;
+    const cx<T> zero = mk<T>((T)0, (T)0), one = mk<T>((T)1, (T)0);
+
+    // ---- load: [A, 0; 0, I] into the planes (rows / columns n .. N8-1 carry a unit diagonal and pivot on themselves) ----
+    // (lane = columns lane, lane + 32; eight rows = sixteen loads in flight before the first store)
+    for (int i0 = 0; i0 < N8; i0 += 8) {
+        cx<T> v[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + q, j = lane + 32 * h;
+                v[q][h] = (i == j) ? one : zero;
+                if (i < n && j < n) v[q][h] = Ab[i * n + j];
+            }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = erow<TR>(i0 + q);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                if (j < N8) { M[r * LD + j] = v[q][h].x; M[(r + TR) * LD + j] = v[q][h].y; }
+            }
+        }
+    }
+    rowof[lane] = (unsigned char)lane; rowof[lane + 32] = (unsigned char)(lane + 32);
+    kof[lane] = (unsigned char)lane; kof[lane + 32] = (unsigned char)(lane + 32);
+    unsigned usedw = 0;                                                  // bit h: row lane + 32 h has been a pivot row (or lies beyond N8)
+    if (lane >= N8) usedw |= 1u;
+    if (lane + 32 >= N8) usedw |= 2u;
+    int bad = 0;
+    __syncwarp();
+
+#pragma unroll 1
+    for (int K = 0; K < N8; K += NB) {
+        // ---- 1. panel columns K .. K+NB-1 of rows lane, lane + 32 ----
+        cx<T> pc[2][NB];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) pc[h][u] = zero;
+            if (i < N8) {
+                const T *pr = M + erow<TR>(i) * LD + K;
+                T vr[NB], vi[NB];
+                ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
+#pragma unroll
+                for (int u = 0; u < NB; ++u) pc[h][u] = mk<T>(vr[u], vi[u]);
+            }
+        }
+        // ---- 2. NB scalar Gauss-Jordan steps on the panel, in registers ----
+        int rsel[NB];
+        cx<T> cn[2][NB];
+#pragma unroll
+        for (int s_ = 0; s_ < NB; ++s_) {
+            unsigned key = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
+                if (!((usedw >> h) & 1u) && kh > key) key = kh;
+            }
+            const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
+            const int hr = r >> 5, ol = r & 31;
+            rsel[s_] = r;
+            cx<T> rho[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const cx<T> v = hr ? pc[1][u] : pc[0][u];
+                rho[u].x = __shfl_sync(0xffffffffu, v.x, ol);
+                rho[u].y = __shfl_sync(0xffffffffu, v.y, ol);
+            }
+            const cx<T> piv = rho[s_];
+            const T den = cabs2(piv), rden = iw_rcp(den);
+            const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
+            bad |= !(den > (T)0);
+            // Column s of C' is c + e_(r_s) with c_i = a_is / p and c_(r_s) = -1 / p, i.e. C'_(r_s) = (p - 1) / p: with THAT multiplier the
+            // pivot row needs no zeroing -- rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is special
+            // (a_is <- -c_i, a_(r_s)s <- 1 / p).
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool mine = (lane + 32 * h) == r;
+                cx<T> tq = pc[h][s_];
+                if (mine) tq.x -= (T)1;
+                const cx<T> c = cmul(tq, inv);
+                cn[h][s_] = mk<T>(-c.x, -c.y);
+#pragma unroll
+                for (int u = 0; u < NB; ++u)
+                    if (u != s_) cfms(pc[h][u], c, rho[u]);
+                pc[h][s_] = mine ? inv : cn[h][s_];
+                if (mine) usedw |= 1u << h;
+            }
+            if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (lane + 32 * h < N8) st_crow(Cn + (lane + 32 * h) * NB, cn[h]);
+        __syncwarp();
+        // ---- 3. pivot rows (lane = columns lane, lane + 32): rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t), c^(t)[r_s] = -Cn[r_s][t] ----
+        {
+            cx<T> rho[NB][2];
+#pragma unroll
+            for (int s_ = 0; s_ < NB; ++s_) {
+                const T *pr = M + erow<TR>(rsel[s_]) * LD, *pi = pr + TR * LD;
+                cx<T> gm[NB];
+#pragma unroll
+                for (int tt = 0; tt < s_; ++tt) gm[tt] = Cn[rsel[s_] * NB + tt];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    cx<T> v = j < N8 ? mk<T>(pr[j], pi[j]) : zero;
+#pragma unroll
+                    for (int tt = 0; tt < s_; ++tt) cfma(v, gm[tt], rho[tt][h]);        // v -= c rho = v + Cn rho
+                    rho[s_][h] = v;
+                    if (j < N8) Rho[s_ * L::RLD + j] = v;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- 4. rank-NB update of the whole matrix on the tensor cores ----
+        iw_update<NT>(M, Cn, Rho, lane);
+        __syncwarp();
+        // ---- 5. the panel columns take the factored panel ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i < N8) {
+                T *pr = M + erow<TR>(i) * LD + K;
+                T vr[NB], vi[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) { vr[u] = pc[h][u].x; vi[u] = pc[h][u].y; }
+                st_panel(pr, vr); st_panel(pr + TR * LD, vi);
+            }
+        }
+        __syncwarp();
+    }
+    // ---- un-permute on the way out: Y[kof[i]][rowof[j]] = a_ij ----
+    {
+        const int yj0 = rowof[lane], yj1 = rowof[lane + 32];
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const int r = erow<TR>(i), yi = kof[i];
+            if (yi < n) {
+                if (lane < n && yj0 < n) Yb[yi * n + yj0] = mk<T>(M[r * LD + lane], M[(r + TR) * LD + lane]);
+                if (lane + 32 < n && yj1 < n) Yb[yi * n + yj1] = mk<T>(M[r * LD + lane + 32], M[(r + TR) * LD + lane + 32]);
+            }
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && info) info[mat] = bad;
+}
+
+template <typename T, int NT>
+static cudaError_t launch_iw(const void *A, int n, void *Y, int64_t batch, int *info, cudaStream_t s)
+{
+    // as many warps (= matrices) per CTA as 227 KB of shared memory hold, one CTA per SM
+    const int wpc = (int)std::min<size_t>(8, (227 * 1024) / IwLayout<T, NT>::BYTES);       // order 53: 8 x 28 928 B (FP32), 4 x 54 016 B (FP64)
+    const size_t smem = wpc * IwLayout<T, NT>::BYTES;
+    cudaError_t e = cudaFuncSetAttribute(cinverse_warp_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cinverse_warp_kernel<T, NT><<<(unsigned)((batch + wpc - 1) / wpc), 32 * wpc, smem, s>>>((const cx<T> *)A, n, (cx<T> *)Y, info, batch);
+    return cudaGetLastError();
+}
+
+// orders 33 .. 64
+cudaError_t launch_cinverse_tc(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s)
+{
+    const int nt = (order + 7) / 8;
+#define IW(T)                                                                            \
+    switch (nt) {                                                                        \
+    case 5: return launch_iw<T, 5>(A, order, Y, batch, info, s);                         \
+    case 6: return launch_iw<T, 6>(A, order, Y, batch, info, s);                         \
+    case 7: return launch_iw<T, 7>(A, order, Y, batch, info, s);                         \
+    default: return launch_iw<T, 8>(A, order, Y, batch, info, s);                        \
+    }
+    if (dt == WIFI_F32) { IW(float) }
+    IW(double)
+#undef IW
+}
+
+}  // namespace wifi

@@ -7,6 +7,7 @@
 //   cinverse_kernel     batched inverse, orders <= 32: the shared-memory LU, one CTA per matrix.
 //   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
+#include <cstdlib>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -537,6 +538,7 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     g_last_launches = 1;
     const int ld = 2 * order + 1;
     cudaError_t e;
+    if (order > 32 && !getenv("WIFI_INV_OLD")) return launch_cinverse_tc(dt, A, order, Y, batch, info, s);   // warp per matrix, tensor-core updates
     if (order > 32) {                                           // register-resident Gauss-Jordan
         // FP32: 4 x 8 tiles on 128 threads, FP64: 4 x 4 tiles on 256 threads, NB = 4 columns per block step (NB = 8: 11 % slower in FP32 --
         // the one-warp panel factorization gets longer -- and spills in FP64; 5 or 6 CTAs/SM by register cap: no gain)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 
-def blocked_gj_inverse(A, NB=4):
+def blocked_gj_inverse(A, NB=4, fused_pivot_row=False):
     n0 = A.shape[0]
     N = -(-n0 // NB) * NB
     a = np.zeros((N, N), complex); a[:n0, :n0] = A
@@ -20,11 +20,23 @@ def blocked_gj_inverse(A, NB=4):
             cand = np.where(~used)[0]
             r = cand[np.argmax(np.abs(P[cand, s]))]
             inv = 1.0 / P[r, s]
-            c = P[:, s] * inv; c[r] = -inv
-            Cp[:, s] = c; Cp[r, s] += 1.0               # C' = c + e_(r_s)
-            rho = P[r, :].copy(); rho[s] = 1.0
-            P[r, :] = 0; P[:, s] = 0
-            P -= np.outer(c, rho)
+            if fused_pivot_row:
+                # cinverse_warp_kernel (csrc/wifi_inverse_tc.cu): C'_(r_s) = (p - 1) / p makes the pivot row an ordinary row --
+                # rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is special
+                t = P[:, s].copy(); t[r] -= 1.0
+                c = t * inv
+                Cp[:, s] = c
+                rho = P[r, :].copy()
+                for u in range(NB):
+                    if u != s:
+                        P[:, u] -= c * rho[u]
+                P[:, s] = -c; P[r, s] = inv
+            else:
+                c = P[:, s] * inv; c[r] = -inv
+                Cp[:, s] = c; Cp[r, s] += 1.0               # C' = c + e_(r_s)
+                rho = P[r, :].copy(); rho[s] = 1.0
+                P[r, :] = 0; P[:, s] = 0
+                P -= np.outer(c, rho)
             used[r] = True; rowof[K + s] = r; kof[r] = K + s; rs.append(r)
         rho = np.zeros((NB, N), complex)
         for s in range(NB):                             # rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t); c^(t)[r_s] = C'[r_s][t] for t < s
@@ -38,11 +50,12 @@ def blocked_gj_inverse(A, NB=4):
 
 @pytest.mark.parametrize("n", [33, 47, 53, 56, 64])
 @pytest.mark.parametrize("NB", [2, 4])
-def test_blocked_gauss_jordan_model(n, NB):
+@pytest.mark.parametrize("fused", [False, True])
+def test_blocked_gauss_jordan_model(n, NB, fused):
     rng = np.random.default_rng(n * 10 + NB)
     A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
-    Y = blocked_gj_inverse(A, NB)
+    Y = blocked_gj_inverse(A, NB, fused)
     ref = np.linalg.inv(A)
     assert np.abs(Y - ref).max() / np.abs(ref).max() < 1e-12
     B = A.copy(); B[0, 0] = 0                          # a zero leading element: un-pivoted elimination (the reference's determinant) fails here
-    assert np.abs(blocked_gj_inverse(B, NB) @ B - np.eye(n)).max() < 1e-11
+    assert np.abs(blocked_gj_inverse(B, NB, fused) @ B - np.eye(n)).max() < 1e-11
