@@ -36,7 +36,7 @@ template <typename T, int NT> struct IwLayout {
     static constexpr int LD = N8 + ((N8 % 16 == 0) ? 8 : 0);              // row stride of the planes: LD mod 16 == 8 -> conflict-free accumulator tiles
     static constexpr int ROWS = 2 * N8;
     static constexpr int RLD = N8 + 4;                                    // row stride of R~ in complex values (RLD mod 8 == 4: conflict-free B fragments)
-    static constexpr size_t BYTES = sizeof(T) * ((size_t)ROWS * LD + 2 * N8 * NB + 2 * NB * RLD) + 2 * 64;     // + rowof, kof (bytes)
+    static constexpr size_t BYTES = sizeof(T) * ((size_t)ROWS * LD + 2 * N8 * NB + 2 * NB * RLD) + 2 * 64 + 16;     // + rowof, kof, rs (bytes)
 };
 
 __device__ __forceinline__ float iw_rcp(float d)
@@ -110,42 +110,42 @@ __device__ __forceinline__ void st_crow(double2 *p, const double2 (&c)[2]) { p[0
 // plane row of the real part of complex row i (the imaginary part sits TR rows below)
 template <int TR> __device__ __forceinline__ int erow(int i) { return (i / TR) * (2 * TR) + (i % TR); }
 
-// ---- step 4, FP32: all NT x NT tiles, 3xTF32 ----
+// ---- step 4, FP32: row tiles RT0 .. RT0+NR-1 (8 complex rows each) x all NT column tiles, 3xTF32 ----
 // Software-pipelined over the column tiles: the accumulators of column tile ct + 1 are loaded and their MMAs issued BEFORE the
 // results of ct are stored, so the store never waits for a tensor-core result (ncu, first version: a quarter of all stall samples
 // sat on the STS behind the HMMA chain).
-template <int NT> __device__ __forceinline__ void iw_update(float *M, const float2 *Cn, const float2 *Rho, int lane)
+template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(float *M, const float2 *Cn, const float2 *Rho, int lane)
 {
     using L = IwLayout<float, NT>;
     const int g = lane >> 2, t = lane & 3;
-    uint32_t arh[NT], arl[NT], aih[NT], ail[NT], nih[NT], nil[NT];
+    uint32_t arh[NR], arl[NR], aih[NR], ail[NR], nih[NR], nil[NR];
 #pragma unroll
-    for (int rt = 0; rt < NT; ++rt) {
-        const float2 c = Cn[(8 * rt + g) * 4 + t];                         // -C'[8 rt + g][t]
-        split_tf32(c.x, arh[rt], arl[rt]);
-        split_tf32(c.y, aih[rt], ail[rt]);
-        nih[rt] = aih[rt] ^ 0x80000000u; nil[rt] = ail[rt] ^ 0x80000000u;
+    for (int q = 0; q < NR; ++q) {
+        const float2 c = Cn[(8 * (RT0 + q) + g) * 4 + t];                  // -C'[8 rt + g][t]
+        split_tf32(c.x, arh[q], arl[q]);
+        split_tf32(c.y, aih[q], ail[q]);
+        nih[q] = aih[q] ^ 0x80000000u; nil[q] = ail[q] ^ 0x80000000u;
     }
-    float *const p0 = M + (g * L::LD + 2 * t);
+    float *const p0 = M + ((16 * RT0 + g) * L::LD + 2 * t);
     const float2 *const r0 = Rho + t * L::RLD + g;
-    float acc[2][NT][4];
-    auto issue = [&](int ct, float (&a)[NT][4]) {
+    float acc[2][NR][4];
+    auto issue = [&](int ct, float (&a)[NR][4]) {
         const float2 b = r0[8 * ct];
         uint32_t brh, brl, bih, bil;
         split_tf32(b.x, brh, brl);
         split_tf32(b.y, bih, bil);
         const float *p = p0 + 8 * ct;
 #pragma unroll
-        for (int rt = 0; rt < NT; ++rt) {
-            const float2 re = lds_acc(p + rt * 16 * L::LD), im = lds_acc(p + (rt * 16 + 8) * L::LD);
-            a[rt][0] = re.x; a[rt][1] = re.y; a[rt][2] = im.x; a[rt][3] = im.y;
+        for (int q = 0; q < NR; ++q) {
+            const float2 re = lds_acc(p + q * 16 * L::LD), im = lds_acc(p + (q * 16 + 8) * L::LD);
+            a[q][0] = re.x; a[q][1] = re.y; a[q][2] = im.x; a[q][3] = im.y;
         }
 #pragma unroll
-        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arl[rt], ail[rt], nil[rt], arl[rt], brh, bih);       // A_lo B_hi
+        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arl[q], ail[q], nil[q], arl[q], brh, bih);       // A_lo B_hi
 #pragma unroll
-        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arh[rt], aih[rt], nih[rt], arh[rt], brl, bil);       // A_hi B_lo
+        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[q], aih[q], nih[q], arh[q], brl, bil);       // A_hi B_lo
 #pragma unroll
-        for (int rt = 0; rt < NT; ++rt) mma_tf32(a[rt], arh[rt], aih[rt], nih[rt], arh[rt], brh, bih);       // A_hi B_hi
+        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[q], aih[q], nih[q], arh[q], brh, bih);       // A_hi B_hi
     };
     issue(0, acc[0]);
 #pragma unroll
@@ -153,40 +153,40 @@ template <int NT> __device__ __forceinline__ void iw_update(float *M, const floa
         if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
         float *p = p0 + 8 * ct;
 #pragma unroll
-        for (int rt = 0; rt < NT; ++rt) {
-            sts_acc(p + rt * 16 * L::LD, acc[ct & 1][rt][0], acc[ct & 1][rt][1]);
-            sts_acc(p + (rt * 16 + 8) * L::LD, acc[ct & 1][rt][2], acc[ct & 1][rt][3]);
+        for (int q = 0; q < NR; ++q) {
+            sts_acc(p + q * 16 * L::LD, acc[ct & 1][q][0], acc[ct & 1][q][1]);
+            sts_acc(p + (q * 16 + 8) * L::LD, acc[ct & 1][q][2], acc[ct & 1][q][3]);
         }
     }
 }
 
-// ---- step 4, FP64: 2 NT x NT tiles of 8 x 8 doubles, one DMMA each; pipelined like the FP32 form ----
-template <int NT> __device__ __forceinline__ void iw_update(double *M, const double2 *Cn, const double2 *Rho, int lane)
+// ---- step 4, FP64: row tiles RT0 .. RT0+NR-1 (4 complex rows each; 2 NT in all) x all NT column tiles, one DMMA each ----
+template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(double *M, const double2 *Cn, const double2 *Rho, int lane)
 {
     using L = IwLayout<double, NT>;
     const int g = lane >> 2, t = lane & 3;
     // A[g][k]: Re rows (g < 4): k < 2 -> Re c, k >= 2 -> -Im c;  Im rows: k < 2 -> Im c, k >= 2 -> Re c;  c = -C'[4 rt + (g & 3)][k & 1]
     const int apart = (g >> 2) ^ (t >> 1);
     const bool aneg = g < 4 && t >= 2;
-    double af[2 * NT];
+    double af[NR];
 #pragma unroll
-    for (int rt = 0; rt < 2 * NT; ++rt) {
-        const double v = reinterpret_cast<const double *>(Cn + (4 * rt + (g & 3)) * 2 + (t & 1))[apart];
-        af[rt] = aneg ? -v : v;
+    for (int q = 0; q < NR; ++q) {
+        const double v = reinterpret_cast<const double *>(Cn + (4 * (RT0 + q) + (g & 3)) * 2 + (t & 1))[apart];
+        af[q] = aneg ? -v : v;
     }
-    double *const p0 = M + (g * L::LD + 2 * t);
+    double *const p0 = M + ((8 * RT0 + g) * L::LD + 2 * t);
     const double *const r0 = reinterpret_cast<const double *>(Rho + (t & 1) * L::RLD + g) + (t >> 1);
-    double acc[2][2 * NT][2];
-    auto issue = [&](int ct, double (&a)[2 * NT][2]) {
+    double acc[2][NR][2];
+    auto issue = [&](int ct, double (&a)[NR][2]) {
         const double bf = r0[16 * ct];                                       // R~[t & 1][8 ct + g], Re (t < 2) or Im
         const double *p = p0 + 8 * ct;
 #pragma unroll
-        for (int rt = 0; rt < 2 * NT; ++rt) {
-            const double2 v = lds_acc(p + rt * 8 * L::LD);
-            a[rt][0] = v.x; a[rt][1] = v.y;
+        for (int q = 0; q < NR; ++q) {
+            const double2 v = lds_acc(p + q * 8 * L::LD);
+            a[q][0] = v.x; a[q][1] = v.y;
         }
 #pragma unroll
-        for (int rt = 0; rt < 2 * NT; ++rt) mma_f64(a[rt], af[rt], bf);
+        for (int q = 0; q < NR; ++q) mma_f64(a[q], af[q], bf);
     };
     issue(0, acc[0]);
 #pragma unroll
@@ -194,30 +194,44 @@ template <int NT> __device__ __forceinline__ void iw_update(double *M, const dou
         if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
         double *p = p0 + 8 * ct;
 #pragma unroll
-        for (int rt = 0; rt < 2 * NT; ++rt) sts_acc(p + rt * 8 * L::LD, acc[ct & 1][rt][0], acc[ct & 1][rt][1]);
+        for (int q = 0; q < NR; ++q) sts_acc(p + q * 8 * L::LD, acc[ct & 1][q][0], acc[ct & 1][q][1]);
     }
 }
 
+// the update of one matrix split between the two warps of its pair: warp 0 (which also factors the panels) takes the smaller half
+template <int NT> __device__ __forceinline__ void iw_update_half(float *M, const float2 *Cn, const float2 *Rho, int lane, int w)
+{
+    if (w == 0) iw_update<NT, 0, NT / 2>(M, Cn, Rho, lane);
+    else iw_update<NT, NT / 2, NT - NT / 2>(M, Cn, Rho, lane);
+}
+template <int NT> __device__ __forceinline__ void iw_update_half(double *M, const double2 *Cn, const double2 *Rho, int lane, int w)
+{
+    if (w == 0) iw_update<NT, 0, NT - 1>(M, Cn, Rho, lane);                 // 2 NT row tiles of 4 complex rows: NT - 1 and NT + 1
+    else iw_update<NT, NT - 1, NT + 1>(M, Cn, Rho, lane);
+}
+
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
 template <typename T, int NT>
-__global__ void __launch_bounds__(256) cinverse_warp_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info, int64_t batch)
+__global__ void __launch_bounds__(512) cinverse_warp_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info, int64_t batch)
 {
     using L = IwLayout<T, NT>;
     constexpr int NB = L::NB, TR = L::TR, N8 = L::N8, LD = L::LD;
     extern __shared__ __align__(16) unsigned char iw_smem[];
-    const int64_t mat = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp = one matrix; warps never meet
+    const int pair = threadIdx.x >> 6, w = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+    const int64_t mat = (int64_t)blockIdx.x * (blockDim.x >> 6) + pair;   // two warps = one matrix; pairs never meet
     if (mat >= batch) return;
-    T *M = reinterpret_cast<T *>(iw_smem + (threadIdx.x >> 5) * L::BYTES);                // [2 N8][LD] real planes
+    T *M = reinterpret_cast<T *>(iw_smem + pair * L::BYTES);              // [2 N8][LD] real planes
     cx<T> *Cn = reinterpret_cast<cx<T> *>(M + (size_t)L::ROWS * LD);     // [N8][NB]: -C'
     cx<T> *Rho = Cn + N8 * NB;                                           // [NB][RLD]: transformed pivot rows
-    unsigned char *rowof = reinterpret_cast<unsigned char *>(Rho + NB * L::RLD), *kof = rowof + 64;
-    const int lane = threadIdx.x & 31;
+    unsigned char *rowof = reinterpret_cast<unsigned char *>(Rho + NB * L::RLD), *kof = rowof + 64, *rs = kof + 64;
     const cx<T> *Ab = A + mat * n * n;
     cx<T> *Yb = Y + mat * n * n;
     const cx<T> zero = mk<T>((T)0, (T)0), one = mk<T>((T)1, (T)0);
 
     // ---- load: [A, 0; 0, I] into the planes (rows / columns n .. N8-1 carry a unit diagonal and pivot on themselves) ----
-    // (lane = columns lane, lane + 32; eight rows = sixteen loads in flight before the first store)
-    for (int i0 = 0; i0 < N8; i0 += 8) {
+    // (lane = columns lane, lane + 32; eight rows = sixteen loads in flight before the first store; the warps alternate row groups)
+    for (int i0 = 8 * w; i0 < N8; i0 += 16) {
         cx<T> v[8][2];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -237,121 +251,121 @@ __global__ void __launch_bounds__(256) cinverse_warp_kernel(const cx<T> *__restr
             }
         }
     }
-    rowof[lane] = (unsigned char)lane; rowof[lane + 32] = (unsigned char)(lane + 32);
-    kof[lane] = (unsigned char)lane; kof[lane + 32] = (unsigned char)(lane + 32);
-    unsigned usedw = 0;                                                  // bit h: row lane + 32 h has been a pivot row (or lies beyond N8)
+    if (w == 0) {
+        rowof[lane] = (unsigned char)lane; rowof[lane + 32] = (unsigned char)(lane + 32);
+        kof[lane] = (unsigned char)lane; kof[lane + 32] = (unsigned char)(lane + 32);
+    }
+    unsigned usedw = 0;                                                  // warp 0; bit h: row lane + 32 h has been a pivot row (or lies beyond N8)
     if (lane >= N8) usedw |= 1u;
     if (lane + 32 >= N8) usedw |= 2u;
     int bad = 0;
-    __syncwarp();
+    pair_sync(pair);
 
 #pragma unroll 1
     for (int K = 0; K < N8; K += NB) {
-        // ---- 1. panel columns K .. K+NB-1 of rows lane, lane + 32 ----
         cx<T> pc[2][NB];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = lane + 32 * h;
-#pragma unroll
-            for (int u = 0; u < NB; ++u) pc[h][u] = zero;
-            if (i < N8) {
-                const T *pr = M + erow<TR>(i) * LD + K;
-                T vr[NB], vi[NB];
-                ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
-#pragma unroll
-                for (int u = 0; u < NB; ++u) pc[h][u] = mk<T>(vr[u], vi[u]);
-            }
-        }
-        // ---- 2. NB scalar Gauss-Jordan steps on the panel, in registers ----
-        int rsel[NB];
-        cx<T> cn[2][NB];
-#pragma unroll
-        for (int s_ = 0; s_ < NB; ++s_) {
-            unsigned key = 0;
+        if (w == 0) {
+            // ---- 1. panel columns K .. K+NB-1 of rows lane, lane + 32 ----
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
-                if (!((usedw >> h) & 1u) && kh > key) key = kh;
-            }
-            const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
-            const int hr = r >> 5, ol = r & 31;
-            rsel[s_] = r;
-            cx<T> rho[NB];
+                const int i = lane + 32 * h;
 #pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                const cx<T> v = hr ? pc[1][u] : pc[0][u];
-                rho[u].x = __shfl_sync(0xffffffffu, v.x, ol);
-                rho[u].y = __shfl_sync(0xffffffffu, v.y, ol);
-            }
-            const cx<T> piv = rho[s_];
-            const T den = cabs2(piv), rden = iw_rcp(den);
-            const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
-            bad |= !(den > (T)0);
-            // Column s of C' is c + e_(r_s) with c_i = a_is / p and c_(r_s) = -1 / p, i.e. C'_(r_s) = (p - 1) / p: with THAT multiplier the
-            // pivot row needs no zeroing -- rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is special
-            // (a_is <- -c_i, a_(r_s)s <- 1 / p).
+                for (int u = 0; u < NB; ++u) pc[h][u] = zero;
+                if (i < N8) {
+                    const T *pr = M + erow<TR>(i) * LD + K;
+                    T vr[NB], vi[NB];
+                    ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const bool mine = (lane + 32 * h) == r;
-                cx<T> tq = pc[h][s_];
-                if (mine) tq.x -= (T)1;
-                const cx<T> c = cmul(tq, inv);
-                cn[h][s_] = mk<T>(-c.x, -c.y);
-#pragma unroll
-                for (int u = 0; u < NB; ++u)
-                    if (u != s_) cfms(pc[h][u], c, rho[u]);
-                pc[h][s_] = mine ? inv : cn[h][s_];
-                if (mine) usedw |= 1u << h;
-            }
-            if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-            if (lane + 32 * h < N8) st_crow(Cn + (lane + 32 * h) * NB, cn[h]);
-        __syncwarp();
-        // ---- 3. pivot rows (lane = columns lane, lane + 32): rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t), c^(t)[r_s] = -Cn[r_s][t] ----
-        {
-            cx<T> rho[NB][2];
-#pragma unroll
-            for (int s_ = 0; s_ < NB; ++s_) {
-                const T *pr = M + erow<TR>(rsel[s_]) * LD, *pi = pr + TR * LD;
-                cx<T> gm[NB];
-#pragma unroll
-                for (int tt = 0; tt < s_; ++tt) gm[tt] = Cn[rsel[s_] * NB + tt];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = lane + 32 * h;
-                    cx<T> v = j < N8 ? mk<T>(pr[j], pi[j]) : zero;
-#pragma unroll
-                    for (int tt = 0; tt < s_; ++tt) cfma(v, gm[tt], rho[tt][h]);        // v -= c rho = v + Cn rho
-                    rho[s_][h] = v;
-                    if (j < N8) Rho[s_ * L::RLD + j] = v;
+                    for (int u = 0; u < NB; ++u) pc[h][u] = mk<T>(vr[u], vi[u]);
                 }
             }
+            // ---- 2. NB scalar Gauss-Jordan steps on the panel, in registers ----
+            cx<T> cn[2][NB];
+#pragma unroll
+            for (int s_ = 0; s_ < NB; ++s_) {
+                unsigned key = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
+                    if (!((usedw >> h) & 1u) && kh > key) key = kh;
+                }
+                const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
+                const int hr = r >> 5, ol = r & 31;
+                cx<T> rho[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const cx<T> v = hr ? pc[1][u] : pc[0][u];
+                    rho[u].x = __shfl_sync(0xffffffffu, v.x, ol);
+                    rho[u].y = __shfl_sync(0xffffffffu, v.y, ol);
+                }
+                const cx<T> piv = rho[s_];
+                const T den = cabs2(piv), rden = iw_rcp(den);
+                const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
+                bad |= !(den > (T)0);
+                // Column s of C' is c + e_(r_s) with c_i = a_is / p and c_(r_s) = -1 / p, i.e. C'_(r_s) = (p - 1) / p: with THAT multiplier the
+                // pivot row needs no zeroing -- rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is special
+                // (a_is <- -c_i, a_(r_s)s <- 1 / p).
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const bool mine = (lane + 32 * h) == r;
+                    cx<T> tq = pc[h][s_];
+                    if (mine) tq.x -= (T)1;
+                    const cx<T> c = cmul(tq, inv);
+                    cn[h][s_] = mk<T>(-c.x, -c.y);
+#pragma unroll
+                    for (int u = 0; u < NB; ++u)
+                        if (u != s_) cfms(pc[h][u], c, rho[u]);
+                    pc[h][s_] = mine ? inv : cn[h][s_];
+                    if (mine) usedw |= 1u << h;
+                }
+                if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); rs[s_] = (unsigned char)r; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (lane + 32 * h < N8) st_crow(Cn + (lane + 32 * h) * NB, cn[h]);
         }
-        __syncwarp();
-        // ---- 4. rank-NB update of the whole matrix on the tensor cores ----
-        iw_update<NT>(M, Cn, Rho, lane);
-        __syncwarp();
-        // ---- 5. the panel columns take the factored panel ----
+        pair_sync(pair);
+        // ---- 3. pivot rows, warp w = columns lane + 32 w: rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t), c^(t)[r_s] = -Cn[r_s][t] ----
+        {
+            const int j = lane + 32 * w;
+            cx<T> rho[NB];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = lane + 32 * h;
-            if (i < N8) {
-                T *pr = M + erow<TR>(i) * LD + K;
-                T vr[NB], vi[NB];
+            for (int s_ = 0; s_ < NB; ++s_) {
+                const int r = rs[s_];
+                const T *pr = M + erow<TR>(r) * LD;
+                cx<T> v = j < N8 ? mk<T>(pr[j], pr[TR * LD + j]) : zero;
 #pragma unroll
-                for (int u = 0; u < NB; ++u) { vr[u] = pc[h][u].x; vi[u] = pc[h][u].y; }
-                st_panel(pr, vr); st_panel(pr + TR * LD, vi);
+                for (int tt = 0; tt < s_; ++tt) cfma(v, Cn[r * NB + tt], rho[tt]);      // v -= c rho = v + Cn rho
+                rho[s_] = v;
+                if (j < N8) Rho[s_ * L::RLD + j] = v;
             }
         }
-        __syncwarp();
+        pair_sync(pair);
+        // ---- 4. rank-NB update of the whole matrix on the tensor cores, half of the row tiles per warp ----
+        iw_update_half<NT>(M, Cn, Rho, lane, w);
+        pair_sync(pair);
+        // ---- 5. the panel columns take the factored panel (warp 0; it is also the only reader of the next panel) ----
+        if (w == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if (i < N8) {
+                    T *pr = M + erow<TR>(i) * LD + K;
+                    T vr[NB], vi[NB];
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) { vr[u] = pc[h][u].x; vi[u] = pc[h][u].y; }
+                    st_panel(pr, vr); st_panel(pr + TR * LD, vi);
+                }
+            }
+            __syncwarp();
+        }
     }
-    // ---- un-permute on the way out: Y[kof[i]][rowof[j]] = a_ij ----
+    pair_sync(pair);
+    // ---- un-permute on the way out: Y[kof[i]][rowof[j]] = a_ij (the warps alternate rows) ----
     {
         const int yj0 = rowof[lane], yj1 = rowof[lane + 32];
 #pragma unroll 4
-        for (int i = 0; i < n; ++i) {
+        for (int i = w; i < n; i += 2) {
             const int r = erow<TR>(i), yi = kof[i];
             if (yi < n) {
                 if (lane < n && yj0 < n) Yb[yi * n + yj0] = mk<T>(M[r * LD + lane], M[(r + TR) * LD + lane]);
@@ -360,18 +374,18 @@ __global__ void __launch_bounds__(256) cinverse_warp_kernel(const cx<T> *__restr
         }
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0 && info) info[mat] = bad;
+    if (w == 0 && lane == 0 && info) info[mat] = bad;
 }
 
 template <typename T, int NT>
 static cudaError_t launch_iw(const void *A, int n, void *Y, int64_t batch, int *info, cudaStream_t s)
 {
-    // as many warps (= matrices) per CTA as 227 KB of shared memory hold, one CTA per SM
-    const int wpc = (int)std::min<size_t>(8, (227 * 1024) / IwLayout<T, NT>::BYTES);       // order 53: 8 x 28 928 B (FP32), 4 x 54 016 B (FP64)
+    // as many warp pairs (= matrices) per CTA as 227 KB of shared memory hold, one CTA per SM
+    const int wpc = (int)std::min<size_t>(8, (227 * 1024) / IwLayout<T, NT>::BYTES);       // order 53: 8 x 28 944 B (FP32), 4 x 54 032 B (FP64)
     const size_t smem = wpc * IwLayout<T, NT>::BYTES;
     cudaError_t e = cudaFuncSetAttribute(cinverse_warp_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cinverse_warp_kernel<T, NT><<<(unsigned)((batch + wpc - 1) / wpc), 32 * wpc, smem, s>>>((const cx<T> *)A, n, (cx<T> *)Y, info, batch);
+    cinverse_warp_kernel<T, NT><<<(unsigned)((batch + wpc - 1) / wpc), 64 * wpc, smem, s>>>((const cx<T> *)A, n, (cx<T> *)Y, info, batch);
     return cudaGetLastError();
 }
 
