@@ -1,7 +1,7 @@
 // wifi_inverse_tc.cu -- batched inverse() (utils.c:141-170) for orders 33..64 with the trailing updates on the tensor cores.
 //
-// ONE WARP PER MATRIX, the matrix resident in shared memory, no CTA barrier anywhere: the blocked in-place Gauss-Jordan with
-// implicit partial pivoting of tests/test_inverse_blocked_model.py,
+// TWO WARPS PER MATRIX, the matrix resident in shared memory, no CTA barrier (named 64-thread barriers per pair): the blocked
+// in-place Gauss-Jordan with implicit partial pivoting of tests/test_inverse_blocked_model.py,
 //        A  <-  A - C' R~      per NB pivot columns (the panel columns then take the factored panel),
 // C' = the NB multiplier vectors (+ e_(r_s): stands in for zeroing the pivot rows), R~ = the NB pivot rows after a unit-lower-
 // triangular transform.  A complex rank-NB update is a real rank-2NB product: with the matrix stored as real planes -- per row
@@ -14,12 +14,17 @@
 //         R~[t][8 ct + g]; C: (c0, c1) = Re, (c2, c3) = Im of a[8 rt + g][8 ct + 2t, +1].
 //   FP64  mma.sync.m8n8k4.f64 (DMMA), NB = 2; row tile = 4 complex rows.  Lane (g, t): A = +-Re/Im of C'[4 rt + (g & 3)][t & 1],
 //         B = Re/Im of R~[t & 1][8 ct + g], C = a[4 rt + (g & 3)][8 ct + 2t, +1] (Re for g < 4, Im for g >= 4).
-// Per block step the warp (1) reads the panel columns (lane = rows lane, lane + 32), (2) factors the panel in registers -- per
+// Per block step: (1) warp 0 reads the panel columns (lane = rows lane, lane + 32) and (2) factors the panel in registers -- per
 // column one redux.sync arg-max over the rows not used yet, the pivot row's NB values by shuffle, one reciprocal -- and publishes
-// -C', (3) reads the NB pivot rows and transforms them (lane = columns lane, lane + 32), (4) runs the NT x NT tile updates with
-// the accumulators streamed through shared memory (conflict-free row stride), (5) writes the factored panel back.
-// The register-resident CTA-per-matrix kernel this replaces (cinverse_blk_kernel, rounds 1-2) was bound by its two CTA barriers
-// and the one-warp panel per block step: 9.4 M (FP32) / 4.8 M (FP64) matrices/s = 15 % of the FMA peaks.
+// -C'; (3) both warps read and transform the NB pivot rows (warp w = columns lane + 32 w); (4) the tile updates, row tiles split
+// between the warps, accumulators streamed through shared memory (conflict-free row stride) in a software pipeline; (5) warp 0
+// writes the factored panel back.  FP64 groups two panels into an outer block so that all but one tile column make ONE pass
+// through shared memory per four pivot columns (the kernel is bound by shared-memory wavefronts; see the loop comment).
+// History (order 53, matrices/s through the API, FP32 / FP64): CTA per matrix, matrix in registers, FFMA / DFMA updates (rounds
+// 1-2) 9.3 M / 4.8 M -> one warp per matrix, tensor-core updates 13.5 M / 6.1 M -> + software-pipelined accumulator streaming,
+// batched global loads, fused pivot-row multiplier 18.2 M / 6.9 M -> + warp pairs (order 64: 9.1 -> 11.4 M) -> + outer blocks in
+// FP64 17.8 M / 8.4 M.  Measured and rejected: outer blocks in FP32 (7 instead of 8 matrices per SM: 13.7 M), four panels per
+// outer block in FP64 (3 instead of 4 matrices per SM: 6.6 M).
 #include <algorithm>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
@@ -27,16 +32,17 @@
 namespace wifi {
 
 template <typename T> struct IwT;
-template <> struct IwT<float> { static constexpr int NB = 4, TR = 8; };     // pivot columns per block step, complex rows per row tile
-template <> struct IwT<double> { static constexpr int NB = 2, TR = 4; };
+template <> struct IwT<float> { static constexpr int NB = 4, TR = 8, NP = 1; };     // pivot columns per inner panel, complex rows per row tile,
+template <> struct IwT<double> { static constexpr int NB = 2, TR = 4, NP = 2; };    // inner panels per outer block
 
 template <typename T, int NT> struct IwLayout {
-    static constexpr int NB = IwT<T>::NB, TR = IwT<T>::TR;
+    static constexpr int NB = IwT<T>::NB, TR = IwT<T>::TR, NP = IwT<T>::NP;
     static constexpr int N8 = 8 * NT;                                     // padded order (column tiles of 8)
     static constexpr int LD = N8 + ((N8 % 16 == 0) ? 8 : 0);              // row stride of the planes: LD mod 16 == 8 -> conflict-free accumulator tiles
     static constexpr int ROWS = 2 * N8;
     static constexpr int RLD = N8 + 4;                                    // row stride of R~ in complex values (RLD mod 8 == 4: conflict-free B fragments)
-    static constexpr size_t BYTES = sizeof(T) * ((size_t)ROWS * LD + 2 * N8 * NB + 2 * NB * RLD) + 2 * 64 + 16;     // + rowof, kof, rs (bytes)
+    static constexpr size_t BYTES = sizeof(T) * ((size_t)ROWS * LD + 2 * NP * N8 * NB + 2 * NP * NB * RLD) + 2 * 64 + 16;     // + rowof, kof, rs (bytes)
+    static constexpr int WPC = (227 * 1024) / BYTES < 8 ? (int)((227 * 1024) / BYTES) : 8;       // matrices (warp pairs) per CTA: what 227 KB hold
 };
 
 __device__ __forceinline__ float iw_rcp(float d)
@@ -110,30 +116,36 @@ __device__ __forceinline__ void st_crow(double2 *p, const double2 (&c)[2]) { p[0
 // plane row of the real part of complex row i (the imaginary part sits TR rows below)
 template <int TR> __device__ __forceinline__ int erow(int i) { return (i / TR) * (2 * TR) + (i % TR); }
 
-// ---- step 4, FP32: row tiles RT0 .. RT0+NR-1 (8 complex rows each) x all NT column tiles, 3xTF32 ----
-// Software-pipelined over the column tiles: the accumulators of column tile ct + 1 are loaded and their MMAs issued BEFORE the
-// results of ct are stored, so the store never waits for a tensor-core result (ncu, first version: a quarter of all stall samples
-// sat on the STS behind the HMMA chain).
-template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(float *M, const float2 *Cn, const float2 *Rho, int lane)
+// ---- tile updates, FP32: row tiles RT0 .. RT0+NR-1 (8 complex rows each) x NC column tiles, block steps KS0 .. KS0+NKS-1, 3xTF32 ----
+// Column tile i of the call is cfirst + i, stepping over cskip.  Software-pipelined over the column tiles: the accumulators of the
+// next tile column are loaded and their MMAs issued BEFORE the results of the current one are stored, so a store never waits for a
+// tensor-core result (ncu, first version: a quarter of all stall samples sat on the STS behind the HMMA chain).
+template <int NT, int RT0, int NR, int KS0, int NKS, int NC>
+__device__ __forceinline__ void iw_update(float *M, const float2 *Cn, const float2 *Rho, int lane, int cfirst, int cskip)
 {
     using L = IwLayout<float, NT>;
     const int g = lane >> 2, t = lane & 3;
-    uint32_t arh[NR], arl[NR], aih[NR], ail[NR], nih[NR], nil[NR];
+    uint32_t arh[NKS][NR], arl[NKS][NR], aih[NKS][NR], ail[NKS][NR];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) {
-        const float2 c = Cn[(8 * (RT0 + q) + g) * 4 + t];                  // -C'[8 rt + g][t]
-        split_tf32(c.x, arh[q], arl[q]);
-        split_tf32(c.y, aih[q], ail[q]);
-        nih[q] = aih[q] ^ 0x80000000u; nil[q] = ail[q] ^ 0x80000000u;
-    }
+    for (int ks = 0; ks < NKS; ++ks)
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const float2 c = Cn[(KS0 + ks) * L::N8 * 4 + (8 * (RT0 + q) + g) * 4 + t];        // -C'[8 rt + g][4 ks + t]
+            split_tf32(c.x, arh[ks][q], arl[ks][q]);
+            split_tf32(c.y, aih[ks][q], ail[ks][q]);
+        }
     float *const p0 = M + ((16 * RT0 + g) * L::LD + 2 * t);
-    const float2 *const r0 = Rho + t * L::RLD + g;
+    const float2 *const r0 = Rho + (KS0 * 4 + t) * L::RLD + g;
+    auto col = [&](int i) { const int c = cfirst + i; return c + (c >= cskip ? 1 : 0); };
     float acc[2][NR][4];
     auto issue = [&](int ct, float (&a)[NR][4]) {
-        const float2 b = r0[8 * ct];
-        uint32_t brh, brl, bih, bil;
-        split_tf32(b.x, brh, brl);
-        split_tf32(b.y, bih, bil);
+        uint32_t brh[NKS], brl[NKS], bih[NKS], bil[NKS];
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+            const float2 b = r0[ks * 4 * L::RLD + 8 * ct];
+            split_tf32(b.x, brh[ks], brl[ks]);
+            split_tf32(b.y, bih[ks], bil[ks]);
+        }
         const float *p = p0 + 8 * ct;
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
@@ -141,44 +153,53 @@ template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(flo
             a[q][0] = re.x; a[q][1] = re.y; a[q][2] = im.x; a[q][3] = im.y;
         }
 #pragma unroll
-        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arl[q], ail[q], nil[q], arl[q], brh, bih);       // A_lo B_hi
+        for (int ks = 0; ks < NKS; ++ks) {
 #pragma unroll
-        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[q], aih[q], nih[q], arh[q], brl, bil);       // A_hi B_lo
+            for (int q = 0; q < NR; ++q) mma_tf32(a[q], arl[ks][q], ail[ks][q], ail[ks][q] ^ 0x80000000u, arl[ks][q], brh[ks], bih[ks]);       // A_lo B_hi
 #pragma unroll
-        for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[q], aih[q], nih[q], arh[q], brh, bih);       // A_hi B_hi
+            for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[ks][q], aih[ks][q], aih[ks][q] ^ 0x80000000u, arh[ks][q], brl[ks], bil[ks]);       // A_hi B_lo
+#pragma unroll
+            for (int q = 0; q < NR; ++q) mma_tf32(a[q], arh[ks][q], aih[ks][q], aih[ks][q] ^ 0x80000000u, arh[ks][q], brh[ks], bih[ks]);       // A_hi B_hi
+        }
     };
-    issue(0, acc[0]);
+    issue(col(0), acc[0]);
 #pragma unroll
-    for (int ct = 0; ct < NT; ++ct) {
-        if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
-        float *p = p0 + 8 * ct;
+    for (int i = 0; i < NC; ++i) {
+        if (i + 1 < NC) issue(col(i + 1), acc[(i + 1) & 1]);
+        float *p = p0 + 8 * col(i);
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
-            sts_acc(p + q * 16 * L::LD, acc[ct & 1][q][0], acc[ct & 1][q][1]);
-            sts_acc(p + (q * 16 + 8) * L::LD, acc[ct & 1][q][2], acc[ct & 1][q][3]);
+            sts_acc(p + q * 16 * L::LD, acc[i & 1][q][0], acc[i & 1][q][1]);
+            sts_acc(p + (q * 16 + 8) * L::LD, acc[i & 1][q][2], acc[i & 1][q][3]);
         }
     }
 }
 
-// ---- step 4, FP64: row tiles RT0 .. RT0+NR-1 (4 complex rows each; 2 NT in all) x all NT column tiles, one DMMA each ----
-template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(double *M, const double2 *Cn, const double2 *Rho, int lane)
+// ---- tile updates, FP64: row tiles RT0 .. RT0+NR-1 (4 complex rows each; 2 NT in all), one DMMA per tile and block step ----
+template <int NT, int RT0, int NR, int KS0, int NKS, int NC>
+__device__ __forceinline__ void iw_update(double *M, const double2 *Cn, const double2 *Rho, int lane, int cfirst, int cskip)
 {
     using L = IwLayout<double, NT>;
     const int g = lane >> 2, t = lane & 3;
-    // A[g][k]: Re rows (g < 4): k < 2 -> Re c, k >= 2 -> -Im c;  Im rows: k < 2 -> Im c, k >= 2 -> Re c;  c = -C'[4 rt + (g & 3)][k & 1]
+    // A[g][k]: Re rows (g < 4): k < 2 -> Re c, k >= 2 -> -Im c;  Im rows: k < 2 -> Im c, k >= 2 -> Re c;  c = -C'[4 rt + (g & 3)][2 ks + (k & 1)]
     const int apart = (g >> 2) ^ (t >> 1);
     const bool aneg = g < 4 && t >= 2;
-    double af[NR];
+    double af[NKS][NR];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) {
-        const double v = reinterpret_cast<const double *>(Cn + (4 * (RT0 + q) + (g & 3)) * 2 + (t & 1))[apart];
-        af[q] = aneg ? -v : v;
-    }
+    for (int ks = 0; ks < NKS; ++ks)
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const double v = reinterpret_cast<const double *>(Cn + (KS0 + ks) * L::N8 * 2 + (4 * (RT0 + q) + (g & 3)) * 2 + (t & 1))[apart];
+            af[ks][q] = aneg ? -v : v;
+        }
     double *const p0 = M + ((8 * RT0 + g) * L::LD + 2 * t);
-    const double *const r0 = reinterpret_cast<const double *>(Rho + (t & 1) * L::RLD + g) + (t >> 1);
+    const double *const r0 = reinterpret_cast<const double *>(Rho + (KS0 * 2 + (t & 1)) * L::RLD + g) + (t >> 1);
+    auto col = [&](int i) { const int c = cfirst + i; return c + (c >= cskip ? 1 : 0); };
     double acc[2][NR][2];
     auto issue = [&](int ct, double (&a)[NR][2]) {
-        const double bf = r0[16 * ct];                                       // R~[t & 1][8 ct + g], Re (t < 2) or Im
+        double bf[NKS];
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) bf[ks] = r0[ks * 4 * L::RLD + 16 * ct];              // R~[2 ks + (t & 1)][8 ct + g], Re (t < 2) or Im
         const double *p = p0 + 8 * ct;
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
@@ -186,45 +207,69 @@ template <int NT, int RT0, int NR> __device__ __forceinline__ void iw_update(dou
             a[q][0] = v.x; a[q][1] = v.y;
         }
 #pragma unroll
-        for (int q = 0; q < NR; ++q) mma_f64(a[q], af[q], bf);
+        for (int ks = 0; ks < NKS; ++ks)
+#pragma unroll
+            for (int q = 0; q < NR; ++q) mma_f64(a[q], af[ks][q], bf[ks]);
     };
-    issue(0, acc[0]);
+    issue(col(0), acc[0]);
 #pragma unroll
-    for (int ct = 0; ct < NT; ++ct) {
-        if (ct + 1 < NT) issue(ct + 1, acc[(ct + 1) & 1]);
-        double *p = p0 + 8 * ct;
+    for (int i = 0; i < NC; ++i) {
+        if (i + 1 < NC) issue(col(i + 1), acc[(i + 1) & 1]);
+        double *p = p0 + 8 * col(i);
 #pragma unroll
-        for (int q = 0; q < NR; ++q) sts_acc(p + q * 8 * L::LD, acc[ct & 1][q][0], acc[ct & 1][q][1]);
+        for (int q = 0; q < NR; ++q) sts_acc(p + q * 8 * L::LD, acc[i & 1][q][0], acc[i & 1][q][1]);
     }
 }
 
-// the update of one matrix split between the two warps of its pair: warp 0 (which also factors the panels) takes the smaller half
-template <int NT> __device__ __forceinline__ void iw_update_half(float *M, const float2 *Cn, const float2 *Rho, int lane, int w)
+// the tile updates of one matrix split between the two warps of its pair by row tiles: warp 0 (which also factors the panels) takes
+// the smaller half.  KS0 / NKS: block steps applied; NC column tiles starting at cfirst, stepping over cskip.
+template <int NT, int KS0, int NKS, int NC>
+__device__ __forceinline__ void iw_update_half(float *M, const float2 *Cn, const float2 *Rho, int lane, int w, int cfirst, int cskip)
 {
-    if (w == 0) iw_update<NT, 0, NT / 2>(M, Cn, Rho, lane);
-    else iw_update<NT, NT / 2, NT - NT / 2>(M, Cn, Rho, lane);
+    if (w == 0) iw_update<NT, 0, NT / 2, KS0, NKS, NC>(M, Cn, Rho, lane, cfirst, cskip);
+    else iw_update<NT, NT / 2, NT - NT / 2, KS0, NKS, NC>(M, Cn, Rho, lane, cfirst, cskip);
 }
-template <int NT> __device__ __forceinline__ void iw_update_half(double *M, const double2 *Cn, const double2 *Rho, int lane, int w)
+template <int NT, int KS0, int NKS, int NC>
+__device__ __forceinline__ void iw_update_half(double *M, const double2 *Cn, const double2 *Rho, int lane, int w, int cfirst, int cskip)
 {
-    if (w == 0) iw_update<NT, 0, NT - 1>(M, Cn, Rho, lane);                 // 2 NT row tiles of 4 complex rows: NT - 1 and NT + 1
-    else iw_update<NT, NT - 1, NT + 1>(M, Cn, Rho, lane);
+    if (w == 0) iw_update<NT, 0, NT - 1, KS0, NKS, NC>(M, Cn, Rho, lane, cfirst, cskip);     // 2 NT row tiles of 4 complex rows: NT - 1 and NT + 1
+    else iw_update<NT, NT - 1, NT + 1, KS0, NKS, NC>(M, Cn, Rho, lane, cfirst, cskip);
 }
 
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(512) cinverse_warp_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info, int64_t batch)
+// the panel columns K .. K+NB-1 take the factored panel (warp 0, rows lane and lane + 32; warp 0 is also the only reader of the next panel)
+template <typename T, int NT> __device__ __forceinline__ void iw_store_panel(T *M, int K, int lane, const cx<T> (&pc)[2][IwT<T>::NB])
 {
     using L = IwLayout<T, NT>;
-    constexpr int NB = L::NB, TR = L::TR, N8 = L::N8, LD = L::LD;
+    constexpr int NB = L::NB;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < L::N8) {
+            T *pr = M + erow<L::TR>(i) * L::LD + K;
+            T vr[NB], vi[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) { vr[u] = pc[h][u].x; vi[u] = pc[h][u].y; }
+            st_panel(pr, vr); st_panel(pr + L::TR * L::LD, vi);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(64 * IwLayout<T, NT>::WPC) cinverse_warp_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info, int64_t batch)
+{
+    using L = IwLayout<T, NT>;
+    constexpr int NB = L::NB, NP = L::NP, OB = NB * NP, TR = L::TR, N8 = L::N8, LD = L::LD;
     extern __shared__ __align__(16) unsigned char iw_smem[];
     const int pair = threadIdx.x >> 6, w = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
     const int64_t mat = (int64_t)blockIdx.x * (blockDim.x >> 6) + pair;   // two warps = one matrix; pairs never meet
     if (mat >= batch) return;
     T *M = reinterpret_cast<T *>(iw_smem + pair * L::BYTES);              // [2 N8][LD] real planes
-    cx<T> *Cn = reinterpret_cast<cx<T> *>(M + (size_t)L::ROWS * LD);     // [N8][NB]: -C'
-    cx<T> *Rho = Cn + N8 * NB;                                           // [NB][RLD]: transformed pivot rows
-    unsigned char *rowof = reinterpret_cast<unsigned char *>(Rho + NB * L::RLD), *kof = rowof + 64, *rs = kof + 64;
+    cx<T> *Cn = reinterpret_cast<cx<T> *>(M + (size_t)L::ROWS * LD);     // [NP][N8][NB]: -C' of the inner panels of one outer block
+    cx<T> *Rho = Cn + NP * N8 * NB;                                      // [OB][RLD]: transformed pivot rows of one outer block
+    unsigned char *rowof = reinterpret_cast<unsigned char *>(Rho + OB * L::RLD), *kof = rowof + 64, *rs = kof + 64;
     const cx<T> *Ab = A + mat * n * n;
     cx<T> *Yb = Y + mat * n * n;
     const cx<T> zero = mk<T>((T)0, (T)0), one = mk<T>((T)1, (T)0);
@@ -261,106 +306,117 @@ __global__ void __launch_bounds__(512) cinverse_warp_kernel(const cx<T> *__restr
     int bad = 0;
     pair_sync(pair);
 
+    // An OUTER block = NP inner panels of NB pivot columns inside one tile column ct0.  Each inner panel is factored, its pivot
+    // rows are transformed, and its rank-NB update is applied to tile column ct0 ONLY (the next inner panel lives there); the other
+    // NT - 1 tile columns take the rank-(NP NB) update of the whole outer block in ONE pass over their accumulators -- half the
+    // shared-memory traffic of one pass per inner panel (the limiter, ncu: 54 % / 73 % of the LSU wavefront budget in FP32 / FP64).
+    // Pivot row s of the outer block, rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t): in the columns of ct0 the terms of EARLIER
+    // inner panels are already in a[r_s] (narrow updates), elsewhere none is (tests/test_inverse_blocked_model.py, lookahead form).
 #pragma unroll 1
-    for (int K = 0; K < N8; K += NB) {
+    for (int K0 = 0; K0 < N8; K0 += OB) {
+        const int ct0 = K0 >> 3;
+        const int jmine = lane + 32 * w;
+        const bool in0 = (jmine >> 3) == ct0;
+        cx<T> rho[OB];
         cx<T> pc[2][NB];
-        if (w == 0) {
-            // ---- 1. panel columns K .. K+NB-1 of rows lane, lane + 32 ----
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-#pragma unroll
-                for (int u = 0; u < NB; ++u) pc[h][u] = zero;
-                if (i < N8) {
-                    const T *pr = M + erow<TR>(i) * LD + K;
-                    T vr[NB], vi[NB];
-                    ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) pc[h][u] = mk<T>(vr[u], vi[u]);
-                }
-            }
-            // ---- 2. NB scalar Gauss-Jordan steps on the panel, in registers ----
-            cx<T> cn[2][NB];
-#pragma unroll
-            for (int s_ = 0; s_ < NB; ++s_) {
-                unsigned key = 0;
+        for (int p = 0; p < NP; ++p) {
+            const int K = K0 + p * NB;
+            if (w == 0) {
+                // ---- 1. panel columns K .. K+NB-1 of rows lane, lane + 32 ----
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
-                    if (!((usedw >> h) & 1u) && kh > key) key = kh;
-                }
-                const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
-                const int hr = r >> 5, ol = r & 31;
-                cx<T> rho[NB];
+                    const int i = lane + 32 * h;
 #pragma unroll
-                for (int u = 0; u < NB; ++u) {
-                    const cx<T> v = hr ? pc[1][u] : pc[0][u];
-                    rho[u].x = __shfl_sync(0xffffffffu, v.x, ol);
-                    rho[u].y = __shfl_sync(0xffffffffu, v.y, ol);
-                }
-                const cx<T> piv = rho[s_];
-                const T den = cabs2(piv), rden = iw_rcp(den);
-                const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
-                bad |= !(den > (T)0);
-                // Column s of C' is c + e_(r_s) with c_i = a_is / p and c_(r_s) = -1 / p, i.e. C'_(r_s) = (p - 1) / p: with THAT multiplier the
-                // pivot row needs no zeroing -- rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is special
-                // (a_is <- -c_i, a_(r_s)s <- 1 / p).
+                    for (int u = 0; u < NB; ++u) pc[h][u] = zero;
+                    if (i < N8) {
+                        const T *pr = M + erow<TR>(i) * LD + K;
+                        T vr[NB], vi[NB];
+                        ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const bool mine = (lane + 32 * h) == r;
-                    cx<T> tq = pc[h][s_];
-                    if (mine) tq.x -= (T)1;
-                    const cx<T> c = cmul(tq, inv);
-                    cn[h][s_] = mk<T>(-c.x, -c.y);
-#pragma unroll
-                    for (int u = 0; u < NB; ++u)
-                        if (u != s_) cfms(pc[h][u], c, rho[u]);
-                    pc[h][s_] = mine ? inv : cn[h][s_];
-                    if (mine) usedw |= 1u << h;
+                        for (int u = 0; u < NB; ++u) pc[h][u] = mk<T>(vr[u], vi[u]);
+                    }
                 }
-                if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); rs[s_] = (unsigned char)r; }
+                // ---- 2. NB scalar Gauss-Jordan steps on the panel, in registers ----
+                cx<T> cn[2][NB];
+#pragma unroll
+                for (int s_ = 0; s_ < NB; ++s_) {
+                    unsigned key = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
+                        if (!((usedw >> h) & 1u) && kh > key) key = kh;
+                    }
+                    const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
+                    const int hr = r >> 5, ol = r & 31;
+                    cx<T> prow[NB];
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        const cx<T> v = hr ? pc[1][u] : pc[0][u];
+                        prow[u].x = __shfl_sync(0xffffffffu, v.x, ol);
+                        prow[u].y = __shfl_sync(0xffffffffu, v.y, ol);
+                    }
+                    const cx<T> piv = prow[s_];
+                    const T den = cabs2(piv), rden = iw_rcp(den);
+                    const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
+                    bad |= !(den > (T)0);
+                    // Column s of C' is c + e_(r_s) with c_i = a_is / p and c_(r_s) = -1 / p, i.e. C'_(r_s) = (p - 1) / p: with THAT multiplier
+                    // the pivot row needs no zeroing -- rho_u - ((p - 1) / p) rho_u = rho_u / p -- and only the pivot column itself is
+                    // special (a_is <- -c_i, a_(r_s)s <- 1 / p).
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool mine = (lane + 32 * h) == r;
+                        cx<T> tq = pc[h][s_];
+                        if (mine) tq.x -= (T)1;
+                        const cx<T> c = cmul(tq, inv);
+                        cn[h][s_] = mk<T>(-c.x, -c.y);
+#pragma unroll
+                        for (int u = 0; u < NB; ++u)
+                            if (u != s_) cfms(pc[h][u], c, prow[u]);
+                        pc[h][s_] = mine ? inv : cn[h][s_];
+                        if (mine) usedw |= 1u << h;
+                    }
+                    if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); rs[p * NB + s_] = (unsigned char)r; }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (lane + 32 * h < N8) st_crow(Cn + p * N8 * NB + (lane + 32 * h) * NB, cn[h]);
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (lane + 32 * h < N8) st_crow(Cn + (lane + 32 * h) * NB, cn[h]);
-        }
-        pair_sync(pair);
-        // ---- 3. pivot rows, warp w = columns lane + 32 w: rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t), c^(t)[r_s] = -Cn[r_s][t] ----
-        {
-            const int j = lane + 32 * w;
-            cx<T> rho[NB];
+            pair_sync(pair);
+            // ---- 3. pivot rows of this inner panel, warp w = columns lane + 32 w ----
 #pragma unroll
             for (int s_ = 0; s_ < NB; ++s_) {
-                const int r = rs[s_];
+                const int S = p * NB + s_;
+                const int r = rs[S];
                 const T *pr = M + erow<TR>(r) * LD;
-                cx<T> v = j < N8 ? mk<T>(pr[j], pr[TR * LD + j]) : zero;
+                cx<T> v = jmine < N8 ? mk<T>(pr[jmine], pr[TR * LD + jmine]) : zero;
 #pragma unroll
-                for (int tt = 0; tt < s_; ++tt) cfma(v, Cn[r * NB + tt], rho[tt]);      // v -= c rho = v + Cn rho
-                rho[s_] = v;
-                if (j < N8) Rho[s_ * L::RLD + j] = v;
-            }
-        }
-        pair_sync(pair);
-        // ---- 4. rank-NB update of the whole matrix on the tensor cores, half of the row tiles per warp ----
-        iw_update_half<NT>(M, Cn, Rho, lane, w);
-        pair_sync(pair);
-        // ---- 5. the panel columns take the factored panel (warp 0; it is also the only reader of the next panel) ----
-        if (w == 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                if (i < N8) {
-                    T *pr = M + erow<TR>(i) * LD + K;
-                    T vr[NB], vi[NB];
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) { vr[u] = pc[h][u].x; vi[u] = pc[h][u].y; }
-                    st_panel(pr, vr); st_panel(pr + TR * LD, vi);
+                for (int tt = 0; tt < S; ++tt) {
+                    cx<T> cf = Cn[(tt / NB) * N8 * NB + r * NB + (tt % NB)];       // -c^(tt)[r_s]
+                    if (tt < p * NB && in0) cf = zero;                             // already applied to tile column ct0
+                    cfma(v, cf, rho[tt]);
                 }
+                rho[S] = v;
+                if (jmine < N8) Rho[S * L::RLD + jmine] = v;
             }
-            __syncwarp();
+            pair_sync(pair);
+            if (NP == 1) break;                                    // one inner panel: a single pass over all tile columns below
+            // ---- 4a. rank-NB update of tile column ct0 (half of the row tiles per warp) ----
+            iw_update_half<NT, 0, 1, 1>(M, Cn + p * N8 * NB, Rho + p * NB * L::RLD, lane, w, ct0, 99);
+            pair_sync(pair);
+            // ---- 5. the panel columns take the factored panel (warp 0; it is also the only reader of the next panel) ----
+            if (w == 0) iw_store_panel<T, NT>(M, K, lane, pc);
+        }
+        // ---- 4b. rank-(NP NB) update of the other NT - 1 tile columns (NP = 1: of all NT), one pass over their accumulators ----
+        if (NP > 1) {
+            iw_update_half<NT, 0, NP, NT - 1>(M, Cn, Rho, lane, w, 0, ct0);
+            pair_sync(pair);
+        } else {
+            iw_update_half<NT, 0, 1, NT>(M, Cn, Rho, lane, w, 0, 99);
+            pair_sync(pair);
+            if (w == 0) iw_store_panel<T, NT>(M, K0, lane, pc);
         }
     }
-    pair_sync(pair);
     // ---- un-permute on the way out: Y[kof[i]][rowof[j]] = a_ij (the warps alternate rows) ----
     {
         const int yj0 = rowof[lane], yj1 = rowof[lane + 32];
@@ -381,7 +437,7 @@ template <typename T, int NT>
 static cudaError_t launch_iw(const void *A, int n, void *Y, int64_t batch, int *info, cudaStream_t s)
 {
     // as many warp pairs (= matrices) per CTA as 227 KB of shared memory hold, one CTA per SM
-    const int wpc = (int)std::min<size_t>(8, (227 * 1024) / IwLayout<T, NT>::BYTES);       // order 53: 8 x 28 944 B (FP32), 4 x 54 032 B (FP64)
+    const int wpc = IwLayout<T, NT>::WPC;       // order 53: 8 x 28 944 B (FP32), 4 x 57 744 B (FP64)
     const size_t smem = wpc * IwLayout<T, NT>::BYTES;
     cudaError_t e = cudaFuncSetAttribute(cinverse_warp_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

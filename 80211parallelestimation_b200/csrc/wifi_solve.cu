@@ -3,11 +3,10 @@
 //   gj_solve            CTA-cooperative LU with partial pivoting + back-substitution on [A | B] held in shared
 //                       memory; the pivot arg-max is a warp-shuffle reduction.
 //   filter_form_kernel  W = R (R + diag d)^-1 in double-double, once per batch (main.c:183-201 intent).
-//   cinverse_blk_kernel batched inverse, orders 33..64: blocked in-place Gauss-Jordan with implicit pivoting, the matrix in registers.
+//   (batched inverse, orders 33..64: wifi_inverse_tc.cu)
 //   cinverse_kernel     batched inverse, orders <= 32: the shared-memory LU, one CTA per matrix.
 //   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
-#include <cstdlib>
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
 
@@ -279,258 +278,6 @@ __global__ void __launch_bounds__(INV_THREADS) cinverse_kernel(const cx<T> *__re
     if (threadIdx.x == 0 && info) info[blockIdx.x] = sing;
 }
 
-// Register-resident batched inverse for 32 < n <= 64: in-place Gauss-Jordan with implicit partial pivoting.
-// Every step of the in-place form updates the WHOLE n x n matrix (the right half of [A | I] moves into the columns the left
-// half vacates), so a thread can own a fixed 4 x TC tile in registers for all n steps: no shrinking window, no row swaps.
-// Thread layout (NTX = 64 / TC threads along a row): tile row i = ty + 16 m, tile column j = tx + NTX c; a warp holds all 16 ty
-// of two adjacent tx.  Scalar step k (pivot row r = the largest |a_ik| among the rows not used yet, pivot p = a_rk):
-//     c_i = a_ik / p (c_r = -1 / p),  row_j = a_rj (row_k = 1),  row r and column k cleared,  a_ij -= c_i row_j  for all i, j
-// leaves a_rj / p in row r, 1 / p at (r, k) and -a_ik / p in column k.  The physical result holds A^-1 with both index sets
-// permuted: Y[kof[i]][rowof[j]] = a_ij, rowof[k] = pivot row of step k, kof = its inverse.  cinverse_blk_kernel below runs NB of
-// these steps as one rank-NB update; the one-column-at-a-time kernel of round 1 (two CTA barriers, a pivot search and a row
-// publication per column: 82 k warp instructions per 53 x 53 matrix, a third of them FMAs) is gone.
-// 1 / d from the hardware's approximate reciprocal refined by Newton steps, inline (the IEEE division is a ~30-instruction
-// subroutine call on the critical path of every pivot).  ~1 ulp; 0, denormal or infinite d give inf / NaN, which a singular
-// (flagged) or out-of-range matrix produced before.
-__device__ __forceinline__ float pivot_rcp(float d)
-{
-    float x;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(d));
-    return fmaf(x, fmaf(-d, x, 1.0f), x);
-}
-__device__ __forceinline__ double pivot_rcp(double d)
-{
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-    x = fma(x, fma(-d, x, 1.0), x);
-    return fma(x, fma(-d, x, 1.0), x);
-}
-__device__ __forceinline__ unsigned pivot_bits(float v) { return __float_as_uint(v); }
-__device__ __forceinline__ unsigned pivot_bits(double v) { return (unsigned)__double2hiint(v); }
-
-// ------------------------------------------------------------------------------------------------------------------------
-// Blocked register-resident inverse (orders 33..64): the in-place Gauss-Jordan above, NB columns at a time.
-//
-// NB scalar steps with pivot columns k_s and pivot rows r_s compose into ONE rank-NB update of the whole matrix,
-//        A  <-  A - C' R~      (outside the panel columns; the panel columns take the factored panel),
-// where column s of C' is the multiplier vector c^(s) of step s (as the scalar algorithm forms it: a_ik / p, -1/p at the pivot
-// row) plus 1 at row r_s -- the "+1" replaces the zeroing of the pivot rows -- and row s of R~ is pivot row r_s as it stands
-// after the steps t < s:  rho^(s) = a[r_s] - sum_{t<s} c^(t)[r_s] rho^(t).  (Derived from Z(A) - c rho^T per scalar step with Z
-// zeroing the pivot row and column; checked against numpy.linalg.inv in tests/test_inverse_blocked_model.py.)
-// One block step:
-//   1. the owners of the panel's NB columns write them to shared memory                                        [CTA barrier]
-//   2. warp 0 factors the n x NB panel ALONE, in registers (lane = rows lane, lane + 32): per column one redux.sync arg-max over
-//      the unused rows (implicit partial pivoting, as above), the pivot row's NB values by shuffle, one reciprocal; it publishes
-//      C', the factored panel, the pivot rows and the NB x NB coefficients c^(t)[r_s]                           [CTA barrier]
-//   3. the owners of the pivot rows publish them raw; the column positions of a thread's tile and the threads that hold those
-//      columns of ANY row sit in one warp (a warp = all 16 ty of two adjacent tx), so the triangular transform raw -> rho runs
-//      per warp on its own 2 TC columns between two __syncwarp()s -- no CTA barrier
-//   4. rank-NB update of the thread's 4 x TC tile: NB (4 + TC) shared-memory values for 4 TC NB complex FMAs.
-// Two CTA barriers per NB columns instead of two per column, the pivot search / scaling / row publication amortised over NB
-// columns, and no per-thread pivot bookkeeping at all.
-// Predicated shared-memory stores of one tile row as opaque instructions: written as `if (m == r >> 4) store a[m][..]` the compiler
-// merges the four branches into a[r >> 4][..] -- a run-time register index that puts the whole tile into local memory.
-__device__ __forceinline__ void sts_pair_if(int pred, float2 *dst, float2 v0, float2 v1)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
-                 ::"r"(pred), "r"((uint32_t)__cvta_generic_to_shared(dst)), "f"(v0.x), "f"(v0.y), "f"(v1.x), "f"(v1.y) : "memory");
-}
-__device__ __forceinline__ void sts_pair_if(int pred, double2 *dst, double2 v0, double2 v1)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v2.f64 [%1], {%2, %3};\n\t@q st.shared.v2.f64 [%1+16], {%4, %5};\n\t}"
-                 ::"r"(pred), "r"((uint32_t)__cvta_generic_to_shared(dst)), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y) : "memory");
-}
-
-// four values (the 4 rows of one tile column, 16 rows apart) under ONE predicate
-__device__ __forceinline__ void sts4_if(int pred, float2 *dst, float2 v0, float2 v1, float2 v2, float2 v3)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v2.f32 [%1], {%2, %3};\n\t@q st.shared.v2.f32 [%1+128], {%4, %5};\n\t"
-                 "@q st.shared.v2.f32 [%1+256], {%6, %7};\n\t@q st.shared.v2.f32 [%1+384], {%8, %9};\n\t}"
-                 ::"r"(pred), "r"((uint32_t)__cvta_generic_to_shared(dst)), "f"(v0.x), "f"(v0.y), "f"(v1.x), "f"(v1.y), "f"(v2.x), "f"(v2.y), "f"(v3.x), "f"(v3.y) : "memory");
-}
-__device__ __forceinline__ void sts4_if(int pred, double2 *dst, double2 v0, double2 v1, double2 v2, double2 v3)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.shared.v2.f64 [%1], {%2, %3};\n\t@q st.shared.v2.f64 [%1+256], {%4, %5};\n\t"
-                 "@q st.shared.v2.f64 [%1+512], {%6, %7};\n\t@q st.shared.v2.f64 [%1+768], {%8, %9};\n\t}"
-                 ::"r"(pred), "r"((uint32_t)__cvta_generic_to_shared(dst)), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y), "d"(v2.x), "d"(v2.y), "d"(v3.x), "d"(v3.y) : "memory");
-}
-__device__ __forceinline__ void lds4_if(int pred, const float2 *src, float2 &v0, float2 &v1, float2 &v2, float2 &v3)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %8, 0;\n\t@q ld.shared.v2.f32 {%0, %1}, [%9];\n\t@q ld.shared.v2.f32 {%2, %3}, [%9+128];\n\t"
-                 "@q ld.shared.v2.f32 {%4, %5}, [%9+256];\n\t@q ld.shared.v2.f32 {%6, %7}, [%9+384];\n\t}"
-                 : "+f"(v0.x), "+f"(v0.y), "+f"(v1.x), "+f"(v1.y), "+f"(v2.x), "+f"(v2.y), "+f"(v3.x), "+f"(v3.y)
-                 : "r"(pred), "r"((uint32_t)__cvta_generic_to_shared(src)) : "memory");
-}
-__device__ __forceinline__ void lds4_if(int pred, const double2 *src, double2 &v0, double2 &v1, double2 &v2, double2 &v3)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %8, 0;\n\t@q ld.shared.v2.f64 {%0, %1}, [%9];\n\t@q ld.shared.v2.f64 {%2, %3}, [%9+256];\n\t"
-                 "@q ld.shared.v2.f64 {%4, %5}, [%9+512];\n\t@q ld.shared.v2.f64 {%6, %7}, [%9+768];\n\t}"
-                 : "+d"(v0.x), "+d"(v0.y), "+d"(v1.x), "+d"(v1.y), "+d"(v2.x), "+d"(v2.y), "+d"(v3.x), "+d"(v3.y)
-                 : "r"(pred), "r"((uint32_t)__cvta_generic_to_shared(src)) : "memory");
-}
-template <typename T, int TC, int NB, int MINB>
-__global__ void __launch_bounds__(16 * (WIFI_MAX_ORDER / TC), MINB) cinverse_blk_kernel(const cx<T> *__restrict__ A, int n, cx<T> *__restrict__ Y, int *info)
-{
-    constexpr int NTX = WIFI_MAX_ORDER / TC;          // threads along a row; tile column c holds column tx + NTX c
-    constexpr int NW = 16 * NTX / 32;                 // warps
-    __shared__ __align__(16) cx<T> Pn[2][NB][WIFI_MAX_ORDER];        // panel columns (double-buffered on the block parity), then the factored panel
-    __shared__ __align__(16) cx<T> Cb[NB][WIFI_MAX_ORDER];           // C', column s = multiplier vector of step s (+1 at its pivot row)
-    __shared__ __align__(16) cx<T> Rr[NB][WIFI_MAX_ORDER];           // pivot rows, raw then transformed; column j at position (j % NTX) TC + j / NTX
-    __shared__ int rs[NB], rowof[WIFI_MAX_ORDER], kof[WIFI_MAX_ORDER], sing;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ty = lane & 15, tx = (warp << 1) | (lane >> 4);
-    const cx<T> *Ab = A + (int64_t)blockIdx.x * n * n;
-    cx<T> *Yb = Y + (int64_t)blockIdx.x * n * n;
-    const int n_pad = (n + NB - 1) / NB * NB;          // rows / columns n .. n_pad-1 carry a unit diagonal and pivot on themselves
-    const cx<T> zero = mk<T>((T)0, (T)0), one = mk<T>((T)1, (T)0);
-    cx<T> a[4][TC];
-    bool live[TC];
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int c = 0; c < TC; ++c) {
-            const int i = ty + 16 * m, j = tx + NTX * c;
-            a[m][c] = (i < n && j < n) ? Ab[i * n + j] : ((i == j && i < n_pad) ? one : zero);
-        }
-#pragma unroll
-    for (int c = 0; c < TC; ++c) live[c] = tx + NTX * c < n_pad;
-    if (threadIdx.x < WIFI_MAX_ORDER) { rowof[threadIdx.x] = threadIdx.x; kof[threadIdx.x] = threadIdx.x; }
-    if (threadIdx.x == 0) sing = 0;
-    unsigned usedw = 0;                                // warp 0: bit h = row lane + 32 h has been a pivot row (or lies beyond n_pad)
-    if (lane >= n_pad) usedw |= 1u;
-    if (lane + 32 >= n_pad) usedw |= 2u;
-    // ONE rolled loop over the block steps (a body per tile column, with every register index static, is 8 x 2 100 instructions = 270 KB of
-    // code here): the panel column of a thread is picked by predicated stores / loads over its TC tile columns instead
-    {
-#pragma unroll 1
-        for (int K = 0; K < n_pad; K += NB) {
-            const int pb = (K / NB) & 1;
-            // ---- 1. panel columns -> shared memory ----
-#pragma unroll
-            for (int c = 0; c < TC; ++c) {
-                const int sc = tx + NTX * c - K;
-                const int mine = (unsigned)sc < (unsigned)NB;
-                sts4_if(mine, &Pn[pb][mine ? sc : 0][ty], a[0][c], a[1][c], a[2][c], a[3][c]);      // rows ty + 16 m: 16 elements apart
-            }
-            __syncthreads();
-            // ---- 2. warp 0: the n x NB panel, NB scalar Gauss-Jordan steps in registers ----
-            if (warp == 0) {
-                cx<T> pc[2][NB];
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) pc[h][u] = Pn[pb][u][lane + 32 * h];
-                int rsel[NB];
-                int bad = 0;
-#pragma unroll
-                for (int s_ = 0; s_ < NB; ++s_) {
-                    unsigned key = 0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const unsigned kh = 0x80000000u | (pivot_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
-                        if (!((usedw >> h) & 1u) && kh > key) key = kh;
-                    }
-                    const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
-                    const int hr = r >> 5, ol = r & 31;
-                    rsel[s_] = r;
-                    cx<T> rho[NB];
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) {
-                        const cx<T> v = hr ? pc[1][u] : pc[0][u];
-                        rho[u].x = __shfl_sync(0xffffffffu, v.x, ol);
-                        rho[u].y = __shfl_sync(0xffffffffu, v.y, ol);
-                    }
-                    const cx<T> piv = rho[s_];
-                    const T den = cabs2(piv), rden = pivot_rcp(den);
-                    const cx<T> inv = mk<T>(piv.x * rden, -piv.y * rden);
-                    bad |= !(den > (T)0);
-                    rho[s_] = one;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const bool mine = (lane + 32 * h) == r;
-                        const cx<T> c = mine ? mk<T>(-inv.x, -inv.y) : cmul(pc[h][s_], inv);
-                        Cb[s_][lane + 32 * h] = mine ? mk<T>(c.x + (T)1, c.y) : c;       // C' = c + e_(r_s): stands in for zeroing the pivot row
-                        pc[h][s_] = zero;
-#pragma unroll
-                        for (int u = 0; u < NB; ++u) {
-                            if (mine) pc[h][u] = zero;
-                            cfms(pc[h][u], c, rho[u]);
-                        }
-                        if (mine) usedw |= 1u << h;
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) Pn[pb][u][lane + 32 * h] = pc[h][u];   // the factored panel = the final panel columns
-                if (lane < NB) {
-                    int r = rsel[0];
-#pragma unroll
-                    for (int u = 1; u < NB; ++u) if (lane == u) r = rsel[u];
-                    rs[lane] = r; rowof[K + lane] = r; kof[r] = K + lane;
-                }
-                if (lane == 0 && bad) sing = 1;
-            }
-            __syncthreads();
-            // ---- 3. pivot rows: raw values from their owners, transformed per warp (rho^(s) = raw_s - sum_{t<s} G[s][t] rho^(t)) ----
-#pragma unroll
-            for (int s_ = 0; s_ < NB; ++s_) {
-                const int r = rs[s_];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    const int mine = (ty + 16 * m) == r;
-#pragma unroll
-                    for (int c = 0; c < TC; c += 2) sts_pair_if(mine, &Rr[s_][tx * TC + c], a[m][c], a[m][c + 1]);
-                }
-            }
-            __syncwarp();
-            if (lane < 2 * TC) {
-                const int q = (warp << 1) * TC + lane;           // this warp's 2 TC column positions
-                cx<T> rho[NB];
-#pragma unroll
-                for (int s_ = 0; s_ < NB; ++s_) {
-                    cx<T> v = Rr[s_][q];
-#pragma unroll
-                    for (int t = 0; t < s_; ++t) cfms(v, Cb[t][rs[s_]], rho[t]);         // c^(t)[r_s], t < s (r_s != r_t: no "+1" there)
-                    rho[s_] = v;
-                    Rr[s_][q] = v;
-                }
-            }
-            __syncwarp();
-            // ---- 4. rank-NB update of the tile; the panel column takes the factored panel ----
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                cx<T> cr[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) cr[m] = Cb[u][ty + 16 * m];
-#pragma unroll
-                for (int c = 0; c < TC; ++c) {
-                    if (live[c]) {
-                        const cx<T> rw = Rr[u][tx * TC + c];
-#pragma unroll
-                        for (int m = 0; m < 4; ++m) cfms(a[m][c], cr[m], rw);
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < TC; ++c) {
-                const int sc = tx + NTX * c - K;
-                const int mine = (unsigned)sc < (unsigned)NB;
-                lds4_if(mine, &Pn[pb][mine ? sc : 0][ty], a[0][c], a[1][c], a[2][c], a[3][c]);
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int c = 0; c < TC; ++c) {
-            const int i = ty + 16 * m, j = tx + NTX * c;
-            if (i < n && j < n) Yb[kof[i] * n + rowof[j]] = a[m][c];
-        }
-    if (threadIdx.x == 0 && info) info[blockIdx.x] = sing;
-    (void)NW;
-}
-
 cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, int64_t batch, int *info, cudaStream_t s)
 {
     g_last_launches = 0;
@@ -538,14 +285,8 @@ cudaError_t launch_cinverse(wifi_dtype dt, const void *A, int order, void *Y, in
     g_last_launches = 1;
     const int ld = 2 * order + 1;
     cudaError_t e;
-    if (order > 32 && !getenv("WIFI_INV_OLD")) return launch_cinverse_tc(dt, A, order, Y, batch, info, s);   // warp per matrix, tensor-core updates
-    if (order > 32) {                                           // register-resident Gauss-Jordan
-        // FP32: 4 x 8 tiles on 128 threads, FP64: 4 x 4 tiles on 256 threads, NB = 4 columns per block step (NB = 8: 11 % slower in FP32 --
-        // the one-warp panel factorization gets longer -- and spills in FP64; 5 or 6 CTAs/SM by register cap: no gain)
-        if (dt == WIFI_F32) cinverse_blk_kernel<float, 8, 4, 4><<<(unsigned)batch, 128, 0, s>>>((const float2 *)A, order, (float2 *)Y, info);
-        else cinverse_blk_kernel<double, 4, 4, 2><<<(unsigned)batch, 256, 0, s>>>((const double2 *)A, order, (double2 *)Y, info);
-        return cudaGetLastError();
-    }
+    // orders 33..64: warp pair per matrix, matrix in shared memory, trailing updates on the tensor cores (wifi_inverse_tc.cu)
+    if (order > 32) return launch_cinverse_tc(dt, A, order, Y, batch, info, s);
     if (dt == WIFI_F32) {
         size_t smem = sizeof(float2) * ((size_t)order * ld + order);
         e = cudaFuncSetAttribute(cinverse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,4 +1,4 @@
-"""CPU model of the blocked in-place Gauss-Jordan inverse of csrc/wifi_solve.cu (cinverse_blk_kernel): NB scalar steps with
+"""CPU model of the blocked in-place Gauss-Jordan inverse of csrc/wifi_inverse_tc.cu (cinverse_warp_kernel): NB scalar steps with
 implicit partial pivoting composed into one rank-NB update  A <- A - C' R~  (C' = the multiplier vectors + e_(r_s), R~ = the
 pivot rows after a unit-lower-triangular transform), panel columns replaced by the factored panel, result un-permuted at the
 end.  Checks the algebra the kernel relies on against numpy.linalg.inv (replaces inverse(), utils.c:141-170)."""
@@ -59,3 +59,60 @@ def test_blocked_gauss_jordan_model(n, NB, fused):
     assert np.abs(Y - ref).max() / np.abs(ref).max() < 1e-12
     B = A.copy(); B[0, 0] = 0                          # a zero leading element: un-pivoted elimination (the reference's determinant) fails here
     assert np.abs(blocked_gj_inverse(B, NB, fused) @ B - np.eye(n)).max() < 1e-11
+
+
+def lookahead_gj_inverse(A, NB, OB):
+    """The outer-block form of cinverse_warp_kernel (FP64: NB = 2, OB = 4): the inner panels of an outer block are factored one
+    after the other, each applying its rank-NB update to the 8-wide TILE COLUMN that holds the block only; every other column
+    takes the rank-OB update of the whole outer block in one pass.  Pivot row s of the block is transformed with all earlier
+    pivots of the block outside the tile column, and with the pivots of its own inner panel inside it (the earlier panels'
+    updates are already in the matrix there)."""
+    n0 = A.shape[0]
+    N = -(-n0 // 8) * 8
+    a = np.zeros((N, N), complex); a[:n0, :n0] = A
+    for i in range(n0, N):
+        a[i, i] = 1.0
+    used = np.zeros(N, bool); rowof = np.zeros(N, int); kof = np.zeros(N, int)
+    for K0 in range(0, N, OB):
+        Cp = np.zeros((N, OB), complex); rho = np.zeros((OB, N), complex); rs = []
+        in0 = np.zeros(N, bool); in0[8 * (K0 // 8):8 * (K0 // 8) + 8] = True
+        for p in range(OB // NB):
+            Kp = K0 + p * NB
+            P = a[:, Kp:Kp + NB].copy()
+            for s in range(NB):
+                cand = np.where(~used)[0]
+                r = cand[np.argmax(np.abs(P[cand, s]))]
+                inv = 1.0 / P[r, s]
+                t = P[:, s].copy(); t[r] -= 1.0
+                c = t * inv
+                Cp[:, p * NB + s] = c
+                prow = P[r, :].copy()
+                for u in range(NB):
+                    if u != s:
+                        P[:, u] -= c * prow[u]
+                P[:, s] = -c; P[r, s] = inv
+                used[r] = True; rowof[Kp + s] = r; kof[r] = Kp + s; rs.append(r)
+            for s in range(NB):
+                S = p * NB + s
+                v = a[rs[S], :].copy()
+                for t in range(S):
+                    m = np.ones(N, bool)
+                    if t < p * NB:
+                        m[in0] = False                  # already applied to the tile column by the narrow updates
+                    v[m] -= Cp[rs[S], t] * rho[t][m]
+                rho[S] = v
+            a[:, in0] -= Cp[:, p * NB:(p + 1) * NB] @ rho[p * NB:(p + 1) * NB][:, in0]
+            a[:, Kp:Kp + NB] = P
+        a[:, ~in0] -= Cp @ rho[:, ~in0]
+    Y = np.zeros((N, N), complex)
+    Y[np.ix_(kof, rowof)] = a
+    return Y[:n0, :n0]
+
+
+@pytest.mark.parametrize("n", [33, 40, 53, 64])
+@pytest.mark.parametrize("NB,OB", [(2, 4), (4, 8), (2, 8)])
+def test_lookahead_gauss_jordan_model(n, NB, OB):
+    rng = np.random.default_rng(n * 10 + NB + OB)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    ref = np.linalg.inv(A)
+    assert np.abs(lookahead_gj_inverse(A, NB, OB) - ref).max() / np.abs(ref).max() < 1e-12
