@@ -343,7 +343,8 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
         ctx.mmse_eig_prepare(R, absx2)
         He = torch.empty_like(tx0)
         s2n = ctx.synth_frames(n, prec, first_frame=shard_lo, per_frame_sigma=True, want=("sigma2",))["sigma2"]
-        X.rate("mmse_perframe_eig_" + prec, lambda: ctx.mmse_perframe_eig(tx0, rx0, s2n, out=He), n, 159 * cbytes + cbytes // 2, 2 * 22472, config="configs[3]",
+        X.rate("mmse_perframe_eig_" + prec, lambda: ctx.mmse_perframe_eig(tx0, rx0, s2n, out=He), n, 159 * cbytes + cbytes // 2, 2 * 22472,
+               *((37.2, mp["fp64_dmma_tflops"]) if prec == "f64" else (None, None)), config="configs[3]",
                note="per-frame sigma2 for frames that share |tx_k|^2: two shared 53x53 complex products (2 x 22 472 flop) + a per-frame scaling "
                     "instead of the 4.4e5-flop solve; hbm_frac is on the algorithmic 159 c + sigma2 per frame")
         del He
