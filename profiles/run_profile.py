@@ -39,6 +39,11 @@ def main():
                 m = 1 << 17
                 cdt = torch.complex64 if prec == "f32" else torch.complex128
                 ctx.frontend(torch.randn(m, 1200, dtype=cdt, device="cuda"), torch.randn(m, 160, dtype=cdt, device="cuda"))
+            if want("rx_chain") and rep == 0:
+                m = 1 << 17
+                cdt = torch.complex64 if prec == "f32" else torch.complex128
+                mk = lambda wd: torch.randn(m, wd, dtype=cdt, device="cuda")
+                ctx.rx_chain(mk(1200), mk(160), mk(1200), mk(160))
             if (want("cmatmul") or want("cinverse")) and rep == 0:
                 g = torch.Generator(device="cuda").manual_seed(7)
                 cdt = torch.complex64 if prec == "f32" else torch.complex128
