@@ -16,13 +16,18 @@
  *     inputs.h frame stored in tests/golden/.
  *   - orc_equalize and the *_matlab estimators: pinned against the reference's
  *     matlab.mat goldens (H_EST_*, eq_symbols).
- *   - orc_mmse_*: PARITY UNPINNED by the reference's own artifacts: the C
- *     PS_MMSE (main.c:148-212) returns NaN on every input (utils.c:6 hermitian is
- *     not a conjugate, utils.c:117 addition ignores M2, utils.c:543-569 has no
- *     pivoting) and matlab.mat holds no MMSE output.  The oracle restates the
- *     intended formula (WiFi_channel_estimation_PS_MMSE.m:16-33 == the north-star
- *     H = R (R + s2 (X X^H)^-1)^-1 (rx/tx)) and is cross-checked by a 40-digit
- *     mpmath evaluation and the rank-1 closed form (tests/golden/make_golden.py).
+ *   - orc_mmse_*: the reference's own PS_MMSE body (main.c:148-212) returns NaN on
+ *     every input (utils.c:6 hermitian is not a conjugate, utils.c:117 addition
+ *     ignores M2, utils.c:543-569 has no pivoting) and matlab.mat holds no MMSE
+ *     output, so there is no estimator-level reference output.  The oracle
+ *     restates the intended formula (WiFi_channel_estimation_PS_MMSE.m:16-33 ==
+ *     the north-star H = R (R + s2 (X X^H)^-1)^-1 (rx/tx)) and is pinned
+ *     ROUTINE BY ROUTINE: against PS_MMSE composed from the reference's own
+ *     compiled multiply / multiplyVxVeqM / identity / inverse as the .m text
+ *     prescribes (tests/golden/mmse_ref_composed.npz: 3e-13 on a full-rank
+ *     covariance, 5e-9 on the inputs.h frame = the accuracy of the reference's
+ *     un-pivoted cofactor inverse there), and against a 40-digit mpmath
+ *     evaluation and the rank-1 closed form (tests/golden/make_golden.py).
  *
  * Data convention of every entry point: complex arrays are interleaved
  * (re, im) `double`; arithmetic inside is `long double _Complex`; matrices are

@@ -14,6 +14,11 @@ Files written:
   mmse_kat.npz        intended-MMSE known answers: 40-digit mpmath evaluation (full 53x53
                       solve and rank-1 closed form) on the inputs.h frame + a general-R,
                       per-frame-sigma case.  (The reference has no usable MMSE output.)
+  mmse_ref_composed.npz   PS_MMSE of OFDM block 0 of the inputs.h frame computed with the REFERENCE'S OWN COMPILED ROUTINES
+                      (multiply, multiplyVxVeqM, identity, inverse: utils.c:16-31,55-65,84-93,141-170), composed as its MATLAB twin
+                      prescribes (WiFi_channel_estimation_PS_MMSE.m:25-32); only the conjugate transposes and the M1 + M2 are
+                      done by this script, because hermitian() and addition() are defective as written (utils.c:6,117).
+                      `python tests/golden/make_golden.py composed` writes this file alone (two cofactor inverses: ~15 s).
 """
 import os
 import sys
@@ -29,8 +34,46 @@ from oracle.pyoracle import Reference, NSC, NBLK  # noqa: E402
 import synth  # noqa: E402
 
 
+def mmse_composed(ref, inp, H_ls):
+    """WiFi_channel_estimation_PS_MMSE.m:16-32 for OFDM block 0 (main.c:30-33), every product and the inverse by the reference."""
+    tx0, rx0, ow2 = inp["tx_symb"][:NSC], inp["rx_symb"][:NSC], float(inp["ow2"])
+    t = np.arange(NSC)
+    F = np.exp(-2j * np.pi * np.outer(t, t) / NSC)                       # .m:17-23 == main.c:22-26
+    Fh = F.conj().T                                                      # F' (by the script: utils.c:6 is not a conjugate transpose)
+    ht = ref.multiply(Fh / NSC, H_ls.reshape(NSC, 1))                    # ifft(H_EST, 53)                           .m:27
+    Rhh = ref.outer(ht, ht.conj().T)                                     # ifft(H_EST) * ifft(H_EST)'  (multiplyVxVeqM, main.c:189)
+    X4 = np.diag(tx0)                                                    # .m:29
+    FR = ref.multiply(F, Rhh)
+    FRFh = ref.multiply(FR, Fh)                                          # F Rhh F'
+    Rhy = ref.multiply(ref.multiply(Rhh, Fh), X4)                        # .m:30   (X4, not X4': the .m text as written)
+    Ryy = ref.multiply(ref.multiply(X4, FRFh), X4.conj().T) + ref.identity(NSC, ow2)      # .m:31 (M1 + M2 by the script: utils.c:117)
+    Ryy_inv = ref.inverse(Ryy)                                           # pinv of a Hermitian PD matrix = its inverse      .m:32
+    H_m = ref.multiply(ref.multiply(ref.multiply(F, Rhy), Ryy_inv), rx0.reshape(NSC, 1)).ravel()
+    # the north-star form R (R + ow2 (X X^H)^-1)^-1 (rx/tx), R = F Rhh F', with the same routines
+    A = FRFh + np.diag(ow2 / np.abs(tx0) ** 2)
+    H_ns = ref.multiply(ref.multiply(FRFh, ref.inverse(A)), (rx0 / tx0).reshape(NSC, 1)).ravel()
+    # a better-conditioned system (shared full-rank covariance, 37 dB SNR: cond ~ 1e4) pins the formula itself to ~1e-12: on the
+    # inputs.h frame the reference's own un-pivoted cofactor inverse of Ryy (cond 4e6, rank-one R) is only good to ~2e-9
+    fr = synth.make_frames(1, seed=53, sigma2=2e-4)
+    Rg = synth.channel_covariance()
+    gtx, grx = fr["tx_symb"][0, 0, :], fr["rx_symb"][0, 0, :]
+    Ag = Rg + np.diag(2e-4 / np.abs(gtx) ** 2)
+    Ag_inv = ref.inverse(Ag)
+    gen_H = ref.multiply(ref.multiply(Rg, Ag_inv), (grx / gtx).reshape(NSC, 1)).ravel()
+    return {"H_ls": H_ls, "matlab_form": H_m, "north_star_form": H_ns, "R": FRFh, "Ryy_residual": np.abs(Ryy_inv @ Ryy - np.eye(NSC)).max(),
+            "gen_R": Rg, "gen_tx": gtx, "gen_rx": grx, "gen_sigma2": np.array(2e-4), "gen_H": gen_H,
+            "gen_residual": np.abs(Ag_inv @ Ag - np.eye(NSC)).max()}
+
+
 def main():
     ref = Reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "composed":
+        inp = ref.inputs()
+        H_ls = ref.estimate("lt_ls", inp["tx_preamble_fft"], inp["rx_preamble_fft"])
+        c = mmse_composed(ref, inp, H_ls)
+        np.savez(os.path.join(HERE, "mmse_ref_composed.npz"), **c)
+        print("mmse_ref_composed.npz written; |Ryy^-1 Ryy - I| =", c["Ryy_residual"])
+        return
     rng = np.random.default_rng(0x80211)
 
     # ---- 1. inputs.h ----
@@ -139,6 +182,7 @@ def main():
     k["gen_tx"], k["gen_rx"], k["gen_sigma2"] = fr8["tx_symb"][:, 0, :], fr8["rx_symb"][:, 0, :], fr8["sigma2"]
     k["gen_H"] = np.stack([mmse_mp(Rgm, k["gen_tx"][f], k["gen_rx"][f], k["gen_sigma2"][f]) for f in range(8)])
     np.savez(os.path.join(HERE, "mmse_kat.npz"), **k)
+    np.savez(os.path.join(HERE, "mmse_ref_composed.npz"), **mmse_composed(ref, inp, out["lt_ls"]))
     print("golden vectors written to", HERE)
 
 

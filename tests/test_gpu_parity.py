@@ -392,6 +392,31 @@ def test_mmse_perframe_kat(ctx, wifi, gold):
         assert rel_err(got, k["gen_H"]) < 1e-10              # 40-digit mpmath
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_mmse_vs_reference_routines(ctx, wifi, gold, prec):
+    """Every PS_MMSE path of the device against PS_MMSE composed from the reference's own compiled multiply / inverse
+    (tests/golden/mmse_ref_composed.npz; see test_oracle.py::test_mmse_pinned_by_the_references_own_routines)."""
+    c, g = gold["mmse_ref_composed"], gold["inputs_h"]
+    cd = CDT[prec]
+    tol = TOL[prec]
+    R, s2 = c["gen_R"], float(c["gen_sigma2"])
+    tx, rx = c["gen_tx"][None].astype(cd), c["gen_rx"][None].astype(cd)
+    s2a = np.array([s2], np.float64 if prec == "f64" else np.float32)
+    if prec == "f64":                       # (FP32 inputs would have to be re-rounded before the reference sees them: FP64 only for the solve)
+        for fl in (wifi.SOLVE_PIVOT, wifi.SOLVE_HPD):
+            assert rel_err(host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2a), flags=fl))[0], c["gen_H"]) < tol
+        ctx.mmse_eig_prepare(R, np.abs(c["gen_tx"]) ** 2)
+        assert rel_err(host(ctx.mmse_perframe_eig(dev(tx), dev(rx), dev(s2a)))[0], c["gen_H"]) < 2e-10
+    ctx.mmse_filter_form(dev(R), dev(s2 / np.abs(c["gen_tx"]) ** 2), want_W=False)
+    got = host(ctx.mmse_shared(dev(tx), dev(rx)))[0]
+    assert rel_err(got, c["gen_H"], 1e-3) < (tol if prec == "f64" else 2e-4)       # FP32: the inputs were rounded after the reference saw them
+    # inputs.h, main.c:148 convention (closed form on the device): the reference's cofactor inverse is good to ~5e-9 there
+    tx0, rx0 = g["tx_symb"][:53][None].astype(cd), g["rx_symb"][:53][None].astype(cd)
+    ow2 = np.array([float(g["ow2"])], np.float64 if prec == "f64" else np.float32)
+    got = host(ctx.mmse_cconv(dev(tx0), dev(rx0), dev(ow2), dev(c["H_ls"][None].astype(cd))))[0]
+    assert rel_err(got, c["north_star_form"]) < (2e-8 if prec == "f64" else tol)
+
+
 def test_mmse_cconv_inputs_h(ctx, gold):
     g, r, k = gold["inputs_h"], gold["ref_c_outputs"], gold["mmse_kat"]
     tx0, rx0 = g["tx_symb"][:53].reshape(1, NSC), g["rx_symb"][:53].reshape(1, NSC)
@@ -463,8 +488,8 @@ def test_mmse_cconv_closed_form(ctx, oracle, prec, n):
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_mmse_matlab_mode(ctx, oracle, gold, prec):
     """WiFi_channel_estimation_PS_MMSE.m as written (one 53x53 system per OFDM block, blocks 1..4 averaged) on the matlab.mat
-    frame and on synthetic frames, against the oracle's restatement of the .m text.  (matlab.mat holds no MMSE output:
-    parity unpinned by the reference's artifacts)"""
+    frame and on synthetic frames, against the oracle's restatement of the .m text.  (matlab.mat holds no MMSE output; the .m
+    formula itself is pinned by the reference's own compiled routines, tests/golden/mmse_ref_composed.npz)"""
     m, g = gold["matlab_mat"], gold["inputs_h"]
     cases = [(m["tx_symb"].T.reshape(1, NBLK, NSC), m["rx_symb"].T.reshape(1, NBLK, NSC), m["H_EST_LT_LS"].reshape(1, NSC), np.array([float(g["ow2"])]))]
     fr = synth.make_frames(5, seed=9, sigma2="perframe")

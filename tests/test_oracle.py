@@ -138,6 +138,28 @@ def test_mmse_known_answers(oracle, gold):
     assert rel_err(got, k["gen_H"]) < 1e-13
 
 
+def test_mmse_pinned_by_the_references_own_routines(oracle, gold):
+    """PS_MMSE composed from the reference's own COMPILED multiply / multiplyVxVeqM / identity / inverse (utils.c:16-31,55-65,
+    84-93,141-170) as WiFi_channel_estimation_PS_MMSE.m:25-32 prescribes -- only the conjugate transposes and the M1 + M2 are the
+    generating script's, because utils.c:6,117 are defective as written (tests/golden/make_golden.py mmse_composed).
+    (i) a full-rank covariance at 37 dB: the oracle's per-frame solve and its shared filter equal the reference-routine result to
+    1e-12 -- this pins the FORMULA; (ii) the inputs.h frame in main.c:148's convention (rank-one R, cond(Ryy) 4e6): both the .m
+    text and the north-star form, to the 5e-9 the reference's un-pivoted cofactor inverse itself reaches there
+    (|Ryy^-1 Ryy - I| = 1.7e-9 is stored next to the vectors)."""
+    c, g = gold["mmse_ref_composed"], gold["inputs_h"]
+    s2 = float(c["gen_sigma2"])
+    tx, rx = c["gen_tx"][None], c["gen_rx"][None]
+    assert float(c["gen_residual"]) < 1e-12
+    assert rel_err(oracle.mmse_perframe(c["gen_R"], tx, rx, np.array([s2]))[0], c["gen_H"]) < 1e-12
+    W = oracle.mmse_filter(c["gen_R"], s2 / np.abs(c["gen_tx"]) ** 2)
+    assert rel_err(oracle.mmse_apply(W, rx / tx)[0], c["gen_H"]) < 1e-12
+    tx0, rx0, ow2 = g["tx_symb"][:53], g["rx_symb"][:53], float(g["ow2"])
+    assert rel_err(oracle.mmse_cconv(tx0, rx0, ow2, c["H_ls"]), c["north_star_form"]) < 2e-8
+    assert rel_err(oracle.mmse_matlab_block(tx0, rx0, ow2, c["H_ls"]), c["matlab_form"]) < 2e-8
+    assert rel_err(c["matlab_form"], c["north_star_form"]) < 2e-8          # the reference's routines agree with each other
+    assert rel_err(oracle.mmse_perframe(c["R"], tx0[None], rx0[None], np.array([ow2]))[0], c["north_star_form"]) < 2e-8
+
+
 def test_mmse_shared_filter_equals_perframe(oracle):
     fr = synth.make_frames(6, seed=3)
     R = synth.channel_covariance()
