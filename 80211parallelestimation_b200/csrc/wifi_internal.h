@@ -51,6 +51,8 @@ cudaError_t launch_cinverse_tc(wifi_dtype dt, const void *A, int order, void *Y,
 cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                                        const void *sigma2, const void *Hls_for_R, void *H, int64_t n_frames, int *info, int fast32,
                                        cudaStream_t s);
+cudaError_t launch_mmse_pivot_tc(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H,
+                                 int64_t n_frames, int *info, cudaStream_t s);   // shared R, FP64 arithmetic: warp-pair LU, DMMA updates (wifi_inverse_tc.cu)
 cudaError_t launch_mmse_perframe_hpd(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
                                      const void *sigma2, void *H, int64_t n_frames, int fast32, cudaStream_t s);
 

@@ -1,4 +1,5 @@
-// wifi_inverse_tc.cu -- batched inverse() (utils.c:141-170) for orders 33..64 with the trailing updates on the tensor cores.
+// wifi_inverse_tc.cu -- batched inverse() (utils.c:141-170) for orders 33..64, and the general (pivoted) per-frame PS_MMSE solve at
+// the end of the file, with the trailing updates on the tensor cores.
 //
 // TWO WARPS PER MATRIX, the matrix resident in shared memory, no CTA barrier (named 64-thread barriers per pair): the blocked
 // in-place Gauss-Jordan with implicit partial pivoting of tests/test_inverse_blocked_model.py,
@@ -459,6 +460,272 @@ cudaError_t launch_cinverse_tc(wifi_dtype dt, const void *A, int order, void *Y,
     if (dt == WIFI_F32) { IW(float) }
     IW(double)
 #undef IW
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// General per-frame PS_MMSE solve (any non-singular R + D: the WIFI_SOLVE_PIVOT path) on the same machinery, FP64 arithmetic:
+//   A = R + diag(sigma2 / |tx_k|^2),  y = rx / tx,  A z = y  by LU with partial pivoting + back-substitution,  H = y - D z
+// (Gauss-Jordan is not usable here: its forward error in z is not the image of a small backward error).
+// A warp pair per frame; [A | y] lives in shared memory as the real planes above (56 x 56: y is column 54, rows / columns 53..55
+// carry a unit diagonal); implicit pivoting -- no row swaps: a row that has been a pivot row gets zero multipliers from then on and
+// simply stops changing, so U stays in place for the back-substitution.  Per block of two columns: warp 0 factors the panel in
+// registers (multipliers l_i = a_ik / p of the rows still to be eliminated, zero for the others), both warps form the two pivot
+// rows, and the rank-2 update of the column tiles right of the panel is one DMMA per 8 x 8 real tile, accumulators streamed
+// through shared memory in the software pipeline of iw_update.  Back-substitution: warp 0, the right-hand side in registers
+// (lane = rows lane, lane + 32), one shuffle broadcast per unknown.  Replaces the CTA-per-frame shared-memory LU for a shared R
+// (that kernel stays for the rank-one calling convention of main.c:148 and the FP32-arithmetic opt-in).
+struct PvL {
+    static constexpr int NT = 7, N8 = 56, TR = 4, LD = 56, RLD = 60, ROWS = 112, YC = 54, WPC = 4;
+    static constexpr size_t BYTES = sizeof(double) * ((size_t)ROWS * LD + 4 * N8 + 4 * RLD + 2 * N8 + 2 * N8) + 2 * 64 + 16;
+};
+
+template <int RT0, int NR>
+__device__ __forceinline__ void pv_update(double *M, const double2 *Cn, const double2 *Rho, int lane, int c0, int nc)
+{
+    const int g = lane >> 2, t = lane & 3;
+    const int apart = (g >> 2) ^ (t >> 1);
+    const bool aneg = g < 4 && t >= 2;
+    double af[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+        const double v = reinterpret_cast<const double *>(Cn + (4 * (RT0 + q) + (g & 3)) * 2 + (t & 1))[apart];
+        af[q] = aneg ? -v : v;
+    }
+    double *const p0 = M + ((8 * RT0 + g) * PvL::LD + 2 * t);
+    const double *const r0 = reinterpret_cast<const double *>(Rho + (t & 1) * PvL::RLD + g) + (t >> 1);
+    auto issue = [&](int ct, double (&a)[NR][2]) {
+        const double bf = r0[16 * ct];
+        const double *p = p0 + 8 * ct;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const double2 v = lds_acc(p + q * 8 * PvL::LD);
+            a[q][0] = v.x; a[q][1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) mma_f64(a[q], af[q], bf);
+    };
+    auto store = [&](int ct, const double (&a)[NR][2]) {
+        double *p = p0 + 8 * ct;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) sts_acc(p + q * 8 * PvL::LD, a[q][0], a[q][1]);
+    };
+    double accA[NR][2], accB[NR][2];
+    issue(c0, accA);
+#pragma unroll 1
+    for (int i = 0; i < nc; i += 2) {
+        if (i + 1 < nc) issue(c0 + i + 1, accB);
+        store(c0 + i, accA);
+        if (i + 1 < nc) {
+            if (i + 2 < nc) issue(c0 + i + 2, accA);
+            store(c0 + i + 1, accB);
+        }
+    }
+}
+
+template <typename TIO>
+__global__ void __launch_bounds__(64 * PvL::WPC) mmse_pivot_tc_kernel(const cx<TIO> *__restrict__ R, const cx<TIO> *__restrict__ tx,
+                                                                     const cx<TIO> *__restrict__ rx, int64_t frame_stride,
+                                                                     const TIO *__restrict__ sigma2, cx<TIO> *__restrict__ H, int *info,
+                                                                     int64_t n_frames)
+{
+    constexpr int N8 = PvL::N8, TR = PvL::TR, LD = PvL::LD, YC = PvL::YC;
+    extern __shared__ __align__(16) unsigned char iw_smem[];
+    const int pair = threadIdx.x >> 6, w = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * PvL::WPC + pair;
+    if (f >= n_frames) return;
+    double *M = reinterpret_cast<double *>(iw_smem + pair * PvL::BYTES);
+    double2 *Cn = reinterpret_cast<double2 *>(M + (size_t)PvL::ROWS * LD);      // [N8][2]: -l
+    double2 *Rho = Cn + N8 * 2;                                                 // [2][RLD]: the two pivot rows of the block
+    double2 *zv = Rho + 2 * PvL::RLD;                                           // [N8] solution
+    double2 *pinv = zv + N8;                                                    // [N8] 1 / pivot of column k
+    unsigned char *rowof = reinterpret_cast<unsigned char *>(pinv + N8), *kof = rowof + 64, *rs = kof + 64;
+    const cx<TIO> *txf = tx + f * frame_stride, *rxf = rx + f * frame_stride;
+    const double s2 = (double)sigma2[f];
+    auto wd = [](cx<TIO> v) { return make_double2((double)v.x, (double)v.y); };
+    const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
+
+    // ---- load [R + D | . | y | .]: lane = columns lane, lane + 32; the warps alternate groups of eight rows ----
+    for (int i0 = 8 * w; i0 < N8; i0 += 16) {
+        double2 v[8][2], tq[8], rq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q;
+            tq[q] = one; rq[q] = zero;
+            if (i < NSC) { tq[q] = wd(txf[i]); rq[q] = wd(rxf[i]); }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                v[q][h] = (i == j) ? one : zero;
+                if (i < NSC && j < NSC) v[q][h] = wd(R[i * NSC + j]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q, r = erow<TR>(i);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                double2 a = v[q][h];
+                if (i < NSC && j == i) a.x += s2 / cabs2(tq[q]);
+                if (i < NSC && j == YC) a = cdiv(rq[q], tq[q]);
+                if (j < N8) { M[r * LD + j] = a.x; M[(r + TR) * LD + j] = a.y; }
+            }
+        }
+    }
+    if (w == 0) {
+        rowof[lane] = (unsigned char)lane; rowof[lane + 32] = (unsigned char)(lane + 32);
+        kof[lane] = (unsigned char)lane; kof[lane + 32] = (unsigned char)(lane + 32);
+    }
+    unsigned usedw = 0;
+    if (lane >= N8) usedw |= 1u;
+    if (lane + 32 >= N8) usedw |= 2u;
+    int bad = 0;
+    pair_sync(pair);
+
+#pragma unroll 1
+    for (int K = 0; K < YC; K += 2) {
+        if (w == 0) {
+            double2 pc[2][2], cn[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                pc[h][0] = pc[h][1] = zero;
+                if (i < N8) {
+                    const double *pr = M + erow<TR>(i) * LD + K;
+                    double vr[2], vi[2];
+                    ld_panel(pr, vr); ld_panel(pr + TR * LD, vi);
+                    pc[h][0] = make_double2(vr[0], vi[0]); pc[h][1] = make_double2(vr[1], vi[1]);
+                }
+            }
+#pragma unroll
+            for (int s_ = 0; s_ < 2; ++s_) {
+                unsigned key = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned kh = 0x80000000u | (iw_bits(cabs2(pc[h][s_])) & 0x7fffffc0u) | (unsigned)(63 - (lane + 32 * h));
+                    if (!((usedw >> h) & 1u) && kh > key) key = kh;
+                }
+                const int r = 63 - (int)(__reduce_max_sync(0xffffffffu, key) & 63u);
+                const int hr = r >> 5, ol = r & 31;
+                double2 prow[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double2 v = hr ? pc[1][u] : pc[0][u];
+                    prow[u].x = __shfl_sync(0xffffffffu, v.x, ol);
+                    prow[u].y = __shfl_sync(0xffffffffu, v.y, ol);
+                }
+                const double2 piv = prow[s_];
+                const double den = cabs2(piv), rden = iw_rcp(den);
+                const double2 inv = make_double2(piv.x * rden, -piv.y * rden);
+                bad |= !(den > 0.0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h;
+                    const bool elim = !((usedw >> h) & 1u) && i != r;            // rows still to be eliminated
+                    const double2 l = elim ? cmul(pc[h][s_], inv) : zero;
+                    cn[h][s_] = make_double2(-l.x, -l.y);
+                    if (s_ == 0) cfms(pc[h][1], l, prow[1]);
+                    if (i == r) usedw |= 1u << h;
+                }
+                if (lane == 0) { rowof[K + s_] = (unsigned char)r; kof[r] = (unsigned char)(K + s_); rs[s_] = (unsigned char)r; pinv[K + s_] = inv; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (lane + 32 * h < N8) st_crow(Cn + (lane + 32 * h) * 2, cn[h]);
+        }
+        pair_sync(pair);
+        {   // the two pivot rows, warp w = columns lane + 32 w: rho0 = a[r0], rho1 = a[r1] - l0[r1] rho0
+            const int j = lane + 32 * w;
+            const int r0 = rs[0], r1 = rs[1];
+            if (j < N8) {
+                const double *p0 = M + erow<TR>(r0) * LD, *p1 = M + erow<TR>(r1) * LD;
+                const double2 v0 = make_double2(p0[j], p0[TR * LD + j]);
+                double2 v1 = make_double2(p1[j], p1[TR * LD + j]);
+                cfma(v1, Cn[r1 * 2], v0);
+                Rho[j] = v0; Rho[PvL::RLD + j] = v1;
+            }
+        }
+        pair_sync(pair);
+        {   // rank-2 update of the column tiles that still hold live columns (K + 2 ..), row tiles split 6 + 8
+            const int c0 = (K + 2) >> 3, nc = PvL::NT - c0;
+            if (w == 0) pv_update<0, PvL::NT - 1>(M, Cn, Rho, lane, c0, nc);
+            else pv_update<PvL::NT - 1, PvL::NT + 1>(M, Cn, Rho, lane, c0, nc);
+        }
+        pair_sync(pair);
+    }
+    if (w != 0) return;
+    // ---- back-substitution (warp 0): z_k = y'[r_k] / p_k;  y'[i] -= U[i][k] z_k for the pivot rows of earlier columns ----
+    double2 yv[2];
+    int kofv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        yv[h] = zero; kofv[h] = -1;
+        if (i < N8) { const double *pr = M + erow<TR>(i) * LD + YC; yv[h] = make_double2(pr[0], pr[TR * LD]); kofv[h] = kof[i]; }
+    }
+#pragma unroll 1
+    for (int k = NSC - 1; k >= 0; --k) {
+        const int r = rowof[k], hr = r >> 5, ol = r & 31;
+        const double2 ys = hr ? yv[1] : yv[0];
+        const double2 yr = make_double2(__shfl_sync(0xffffffffu, ys.x, ol), __shfl_sync(0xffffffffu, ys.y, ol));
+        const double2 zk = cmul(yr, pinv[k]);
+        if (lane == 0) zv[k] = zk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (kofv[h] >= 0 && kofv[h] < k) {
+                const double *pr = M + erow<TR>(i) * LD + k;
+                cfms(yv[h], make_double2(pr[0], pr[TR * LD]), zk);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- H = y - D z; a bin whose noise term dominates the diagonal (d_k > R_kk: the DC bin) takes H_k = sum_j R_kj z_j ----
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        bool viaR = false;
+        if (i < NSC) {
+            const double2 t = wd(txf[i]), rr = wd(rxf[i]);
+            const double d = s2 / cabs2(t);
+            viaR = d > (double)R[i * NSC + i].x;
+            if (!viaR) {
+                const double2 y = cdiv(rr, t), z = zv[i];
+                H[f * NSC + i] = mk<TIO>((TIO)(y.x - d * z.x), (TIO)(y.y - d * z.y));
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, viaR);
+        while (m) {
+            const int i2 = (__ffs(m) - 1) + 32 * h;
+            m &= m - 1;
+            double2 acc = zero;
+            for (int j = lane; j < NSC; j += 32) cfma(acc, wd(R[i2 * NSC + j]), zv[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); }
+            if (lane == 0) H[f * NSC + i2] = mk<TIO>((TIO)acc.x, (TIO)acc.y);
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && info && bad) atomicExch(info, 1);
+}
+
+// shared R, FP64 arithmetic (complex64 or complex128 storage)
+cudaError_t launch_mmse_pivot_tc(wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H,
+                                 int64_t n_frames, int *info, cudaStream_t s)
+{
+    const size_t smem = PvL::WPC * PvL::BYTES;
+    const unsigned grid = (unsigned)((n_frames + PvL::WPC - 1) / PvL::WPC);
+    cudaError_t e;
+    if (dt == WIFI_F32) {
+        if ((e = cudaFuncSetAttribute(mmse_pivot_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        mmse_pivot_tc_kernel<float><<<grid, 64 * PvL::WPC, smem, s>>>((const float2 *)R, (const float2 *)tx, (const float2 *)rx, frame_stride,
+                                                                      (const float *)sigma2, (float2 *)H, info, n_frames);
+    } else {
+        if ((e = cudaFuncSetAttribute(mmse_pivot_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        mmse_pivot_tc_kernel<double><<<grid, 64 * PvL::WPC, smem, s>>>((const double2 *)R, (const double2 *)tx, (const double2 *)rx, frame_stride,
+                                                                       (const double *)sigma2, (double2 *)H, info, n_frames);
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace wifi

@@ -5,7 +5,8 @@
 //   filter_form_kernel  W = R (R + diag d)^-1 in double-double, once per batch (main.c:183-201 intent).
 //   (batched inverse, orders 33..64: wifi_inverse_tc.cu)
 //   cinverse_kernel     batched inverse, orders <= 32: the shared-memory LU, one CTA per matrix.
-//   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D): one CTA per frame.
+//   mmse_pivot_kernel   per-frame MMSE, general (any non-singular R + D), one CTA per frame: the rank-one calling convention of main.c:148
+//                       and the FP32-arithmetic opt-in; a shared R in FP64 arithmetic goes to mmse_pivot_tc_kernel (wifi_inverse_tc.cu).
 // The register-resident un-pivoted fast path for Hermitian-PSD R lives in wifi_solve_hpd.cu.
 #include "wifi_common.cuh"
 #include "wifi_internal.h"
@@ -385,6 +386,8 @@ cudaError_t launch_mmse_perframe_pivot(wifi_dtype dt, const void *R, const void 
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
     if (dt == WIFI_F32 && fast32) return launch_pivot<float, float>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
+    // shared R in FP64 arithmetic: the warp-pair LU with tensor-core updates (wifi_inverse_tc.cu)
+    if (!Hls_for_R) return launch_mmse_pivot_tc(dt, R, tx, rx, frame_stride, sigma2, H, n_frames, info, s);
     if (dt == WIFI_F32) return launch_pivot<float, double>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
     return launch_pivot<double, double>(R, tx, rx, frame_stride, sigma2, Hls_for_R, H, n_frames, info, s);
 }

@@ -373,7 +373,7 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
             del Hc
             npv = min(npf, 1 << 15)
             X.rate("mmse_perframe_pivot_" + prec, lambda: ctx.mmse_perframe(Rp, tx0[:npv], rx0[:npv], s2[:npv], flags=wifi.SOLVE_PIVOT, out=Hp[:npv]), npv,
-                   159 * cbytes, 441949, 37.2, mp["fp64_fma_tflops"], config="configs[3], general R", arithmetic="FP64")
+                   159 * cbytes, 441949, 37.2, mp["fp64_dmma_tflops"], config="configs[3], general R", arithmetic="FP64 (pivoted LU, trailing updates on DMMA)")
             # utils.c routines, batched: 53 x 53 complex multiply() and inverse() through the mirror of the
             # reference interface (allocation of the result and, for inverse, the singularity check included)
             nb = 8192
