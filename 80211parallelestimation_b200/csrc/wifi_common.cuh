@@ -78,14 +78,13 @@ template <typename T> __device__ __forceinline__ cx<T> lt_ls_one(cx<T> tx, cx<T>
     return cdiv(mk<T>(c * rx.x, c * rx.y), mk<T>(c * tx.x, c * tx.y));
 }
 
-// r / h for the FP32 equalizer with one reciprocal (MUFU.RCP + Newton step, relative error ~1e-7, branch-free); the IEEE
-// '/' of cdiv() is ~12 instructions and a slow-path branch per real divide.  0/0 still yields NaN.
+// r / h for the FP32 equalizer with one reciprocal (MUFU.RCP, 1 ulp, branch-free); the IEEE '/' of cdiv() is ~12 instructions
+// and a slow-path branch per real divide.  0/0 still yields NaN.
 __device__ __forceinline__ float2 eq_div(float2 a, float2 b)
 {
     const float den = fmaf(b.x, b.x, b.y * b.y);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-    r = fmaf(r, fmaf(-den, r, 1.0f), r);
     return make_float2(fmaf(a.x, b.x, a.y * b.y) * r, fmaf(a.y, b.x, -a.x * b.y) * r);
 }
 __device__ __forceinline__ double2 eq_div(double2 a, double2 b) { return cdiv(a, b); }

@@ -122,6 +122,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+          "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -170,15 +182,15 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-// rx/tx with ONE reciprocal: MUFU.RCP + a Newton step (relative error ~1e-7, branch-free; 0/0 still yields NaN like
-// the reference).  The IEEE '/' expands to ~12 instructions and a slow-path branch per real divide, which made the LS
-// divide two thirds of this kernel's instruction count.
+// rx/tx with ONE reciprocal: MUFU.RCP (rcp.approx: 1 ulp; branch-free; 0/0 still yields NaN like the reference).  The IEEE '/'
+// expands to ~12 instructions and a slow-path branch per real divide, which made the LS divide two thirds of this kernel's
+// instruction count; the Newton step round 1 kept after the MUFU cost another 2 x 53 instructions per frame for nothing the
+// 1e-4 bound can see (0.2322 -> 0.2248 ms per 1 Mi frames without it: the converter warps are issue- and latency-bound).
 __device__ __forceinline__ float2 cdiv_fast(float2 a, float2 b)
 {
     const float den = fmaf(b.x, b.x, b.y * b.y);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-    r = fmaf(r, fmaf(-den, r, 1.0f), r);
     return make_float2(fmaf(a.x, b.x, a.y * b.y) * r, fmaf(a.y, b.x, -a.x * b.y) * r);
 }
 // LS divide of one float4 (two complex bins) when FUSED, identity otherwise
@@ -206,12 +218,12 @@ struct TcResid {
     float Rdd, md;              // R_dd and 1/|x_d|^2 of the null bin
 };
 
-// 1/x with the hardware approximation and one Newton step
+// 1/x with the hardware approximation (1 ulp)
 __device__ __forceinline__ float rcp_fast(float x)
 {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
+    return r;
 }
 
 template <bool FUSED, bool STASH, bool MID>
@@ -320,16 +332,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
                 const uint32_t dcol = lane_base + ((pt & 1) ? TC_COL_D1 : TC_COL_D0);
                 float2 *rowo = reinterpret_cast<float2 *>(buf + lane * TC_ROWF);
+                // 32 accumulator columns per tcgen05.ld and wait (four round trips to tensor memory per tile instead of seven)
 #pragma unroll
-                for (int g = 0; g < TC_N / 16; ++g) {
-                    uint32_t v[16];
-                    tmem_ld16(dcol + 16 * g, v);
+                for (int g = 0; g < 3; ++g) {
+                    uint32_t v[32];
+                    tmem_ld32(dcol + 32 * g, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        int cc = g * 8 + c;
-                        if (cc < NSC) rowo[cc] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
-                    }
+                    for (int c = 0; c < 16; ++c) rowo[g * 16 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                }
+                {
+                    uint32_t v[16];
+                    tmem_ld16(dcol + 96, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) rowo[48 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
                 }
                 if (STASH && res.dc >= 0) rowo[NSC - 1] = yd_keep;        // y_d of the null bin rides in the unused column 52 of u
                 if (MID && res.dc >= 0) rowo[res.dc] = hd_stash;           // the null bin's H_d (border formula)
@@ -481,8 +498,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
                     hi[2 * c] = hx; hi[2 * c + 1] = hy;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c]) : "f"(v.x - __uint_as_float(hx)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo[2 * c + 1]) : "f"(v.y - __uint_as_float(hy)));
+
+                    // the residual goes to tensor memory as plain FP32 bits: kind::tf32 reads the upper 19 bits of the word
+                    lo[2 * c] = __float_as_uint(v.x - __uint_as_float(hx));
+                    lo[2 * c + 1] = __float_as_uint(v.y - __uint_as_float(hy));
+
                 }
                 tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
                 tmem_st16(lane_base + TC_COL_ALO + 16 * g, lo);
