@@ -494,14 +494,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         v = make_float2(v.x - sc * (v.x - (pp.x * m_zd.x - pp.y * m_zd.y)), v.y - sc * (v.y - (pp.x * m_zd.y + pp.y * m_zd.x)));
                         if (res.dc >= 0 && cc == NSC - 1) v = make_float2(0.f, 0.f);       // column 52 carried y_d, not an eigen component
                     }
-                    uint32_t hx, hy;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hx) : "f"(v.x));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hy) : "f"(v.y));
-                    hi[2 * c] = hx; hi[2 * c + 1] = hy;
-
-                    // the residual goes to tensor memory as plain FP32 bits: kind::tf32 reads the upper 19 bits of the word
-                    lo[2 * c] = __float_as_uint(v.x - __uint_as_float(hx));
-                    lo[2 * c + 1] = __float_as_uint(v.y - __uint_as_float(hy));
+                    // hi = v rounded to the 11 significant bits of TF32 by Veltkamp's splitting, c = v (2^13 + 1), hi = c - (c - v): three
+                    // FP32 instructions and NaN-safe (cvt.rna.tf32.f32 is FOUR SASS instructions here -- add, mask, and an FSETP + SEL pair
+                    // that keeps the canonical NaN 0x7fffffff from rounding up into -0; ncu: 106 of each per warp and tile).  The residual
+                    // goes to tensor memory as plain FP32 bits: kind::tf32 reads the upper 19 bits of the word.
+                    // (__fmul_rn / __fsub_rn: no FMA contraction -- the rounding of each step IS the algorithm)
+                    const float cx_ = __fmul_rn(v.x, 8193.0f), cy_ = __fmul_rn(v.y, 8193.0f);
+                    const float hx = __fsub_rn(cx_, __fsub_rn(cx_, v.x)), hy = __fsub_rn(cy_, __fsub_rn(cy_, v.y));
+                    hi[2 * c] = __float_as_uint(hx); hi[2 * c + 1] = __float_as_uint(hy);
+                    lo[2 * c] = __float_as_uint(v.x - hx);
+                    lo[2 * c + 1] = __float_as_uint(v.y - hy);
 
                 }
                 tmem_st16(lane_base + TC_COL_AHI + 16 * g, hi);
