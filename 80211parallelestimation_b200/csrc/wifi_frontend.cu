@@ -204,6 +204,17 @@ template <typename T> struct ChainOut {
 constexpr int RC_WT = 3 * NSC * 4;           // interpolation weights staged per CTA: [est][k][4]
 constexpr int RC_WARP_C = 4 * FE_TS + 2 * 56;   // complex values of shared memory per warp: tile + H_lt + H_linear
 
+// complex divides of the chain kernel: FP32 with one hardware reciprocal (eq_div: 1-2 ulp, 0/0 -> NaN like the IEEE form, a
+// quarter of its instructions -- the FP32 chain is issue-bound, ncu 66 % issue-active); FP64 the textbook cdiv
+__device__ __forceinline__ float2 rc_div(float2 a, float2 b) { return eq_div(a, b); }
+__device__ __forceinline__ double2 rc_div(double2 a, double2 b) { return cdiv(a, b); }
+// main.c:69-72 as written: c = Re(tx) - Im(tx), H = (c rx) / (c tx); Re(tx) == Im(tx) gives 0/0 = NaN
+template <typename T> __device__ __forceinline__ cx<T> rc_lt_ls(cx<T> tx, cx<T> rx)
+{
+    const T c = tx.x - tx.y;
+    return rc_div(mk<T>(c * rx.x, c * rx.y), mk<T>(c * tx.x, c * tx.y));
+}
+
 template <typename T> __device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(FE_THREADS, MINB) rx_chain_kernel(const cx<T> 
         {
             // pilot LS (main.c:82-84): lane i & 3 divides pilot i, lanes 0..3 broadcast
             const int pk = WIFI_P0 + (WIFI_P1 - WIFI_P0) * (lane & 3);
-            const cx<T> mine = cdiv(tile[3 * NSC + pk], tile[2 * NSC + pk]);
+            const cx<T> mine = rc_div(tile[3 * NSC + pk], tile[2 * NSC + pk]);
             cx<T> hp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) hp[i] = mk<T>(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i));
@@ -286,9 +297,9 @@ __global__ void __launch_bounds__(FE_THREADS, MINB) rx_chain_kernel(const cx<T> 
                 if (k < NSC) {
                     const cx<T> x0 = tile[2 * NSC + k];
                     r0[h] = tile[3 * NSC + k];
-                    hl[h] = k == DCBIN ? mk<T>(0, 0) : lt_ls_one<T>(tile[k], tile[NSC + k]);          // main.c:66-75
+                    hl[h] = k == DCBIN ? mk<T>(0, 0) : rc_lt_ls<T>(tile[k], tile[NSC + k]);          // main.c:66-75
                     if (out.H_lt) st_stream(out.H_lt + f * NSC + k, hl[h]);
-                    if (out.H_ls0) st_stream(out.H_ls0 + f * NSC + k, cdiv(r0[h], x0));
+                    if (out.H_ls0) st_stream(out.H_ls0 + f * NSC + k, rc_div(r0[h], x0));
                     const T *w = wt + k * 4;
                     const cx<T> lin = mk<T>(w[0] * hp[0].x + w[1] * hp[1].x + w[2] * hp[2].x + w[3] * hp[3].x,
                                             w[0] * hp[0].y + w[1] * hp[1].y + w[2] * hp[2].y + w[3] * hp[3].y);
