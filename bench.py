@@ -33,7 +33,7 @@ METRIC = "MMSE channel estimates/sec (53-subcarrier frames)"
 UNIT = "frames/s"
 OW2 = 9.6172e-08
 AMP = 8.875
-# DRAM bytes of ONE mmse_shared_tc launch over 1 Mi frames from the ncu --set full capture (0.889 GB read + 0.388 GB written, profiles/r01f_ncu_kernels.txt)
+# DRAM bytes of ONE mmse_shared_tc launch over 1 Mi frames from the ncu --set full capture (0.8896 GB read + 0.3875 GB written, profiles/r02_ncu_kernels.txt)
 NCU_DRAM_BYTES_PER_MI_FRAMES = 1.2772e9
 
 
@@ -520,7 +520,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "mmse_shared (fused LS divide + 53x53 complex filter GEMM)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": int(NCU_DRAM_BYTES_PER_MI_FRAMES * n_local / (1 << 20)),
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 1 Mi frames "
-                                           "(profiles/r01f_ncu_kernels.txt), scaled to this launch's frame count",
+                                           "(profiles/r02_ncu_kernels.txt), scaled to this launch's frame count",
                          "peak_source": peaks["source"],
                          "algorithmic_bytes_per_frame": bytes_per_frame, "kernel_ms": kernel_ms,
                          "tensor_TFLOPs_3xTF32": n_local * 3 * 2 * 112 * 112 / (kernel_ms * 1e-3) / 1e12},
