@@ -94,7 +94,10 @@ template <typename T> __device__ __forceinline__ void fft4_rows(cx<T> *tile, con
     __syncwarp();
 }
 
-template <typename T>
+// PREF (FP32): the samples of the warp's NEXT group are requested into registers before the transforms of the current one (and
+// the group after that is pulled into L2) -- the kernel is bound by load latency (ncu: long_scoreboard 9 warps per issue); in
+// FP64 the 40 extra registers cost a CTA per SM, so there only the L2 prefetch is used.
+template <typename T, bool PREF>
 __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__restrict__ packet, const cx<T> *__restrict__ lptot,
                                                               cx<T> *__restrict__ symb, cx<T> *__restrict__ pre_fft, T *__restrict__ ow2,
                                                               int64_t n_frames)
@@ -112,13 +115,31 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__res
         tw[p] = mk<T>(c, s);
     }
     const int64_t n_groups = n_frames * 4;                       // 16 transforms per frame, 4 per group
-    for (int64_t g = (int64_t)blockIdx.x * FE_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * FE_WARPS) {
+    const int64_t gstride = (int64_t)gridDim.x * FE_WARPS;
+    const int n2 = 2 * lane;                                     // this lane's two consecutive samples of every transform
+    // the raw samples of one group: transform i of the group = OFDM block 4 q + i, or (q = 3, i = 3) the two long-training symbols
+    auto fetch = [&](int64_t g, cx<T> (&raw)[5][2]) {
+        const int64_t f = g >> 2;
+        const int q = (int)(g & 3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (4 * q + i < NBLK) ld_pair(packet + f * FE_PKT + (4 * q + i) * FE_BLK + FE_CP + n2, raw[i][0], raw[i][1]);
+            else {
+                ld_pair(lptot + f * FE_LP + 96 + n2, raw[3][0], raw[3][1]);
+                ld_pair(lptot + f * FE_LP + 32 + n2, raw[4][0], raw[4][1]);
+            }
+        }
+    };
+    cx<T> raw[5][2];
+    int64_t g = (int64_t)blockIdx.x * FE_WARPS + warp;
+    if (PREF && g < n_groups) fetch(g, raw);
+    for (; g < n_groups; g += gstride) {
         const int64_t f = g >> 2;
         const int q = (int)(g & 3);                              // transforms 4q .. 4q+3 of frame f; transform 15 = preamble
-        // HBM -> L2 for the warp's NEXT group (no registers, no shared memory): its loads below then cost an L2 latency.
+        // HBM -> L2 for a LATER group of this warp (no registers, no shared memory): its loads then cost an L2 latency.
         // lanes 0..3: one 64-sample block each; the preamble of a frame's last group: p1 and p2 (lanes 3, 4)
         {
-            const int64_t gn = g + (int64_t)gridDim.x * FE_WARPS;
+            const int64_t gn = g + (PREF ? 2 : 1) * gstride;
             if (gn < n_groups && lane < 5) {
                 const int64_t fn = gn >> 2;
                 const int bn = 4 * (int)(gn & 3) + lane;
@@ -128,27 +149,21 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__res
                 if (src) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(64 * sizeof(cx<T>))) : "memory");
             }
         }
-        // ---- A. samples -> tile (natural order), two consecutive samples per lane and load ----
+        // ---- A. samples -> tile (natural order), two consecutive samples per lane and transform ----
+        if (!PREF) fetch(g, raw);
         T nv = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int e = 2 * (i * 32 + lane);                   // 0..254: transform e / 64, samples e % 64 and + 1
-            const int tt = e >> 6, n = e & 63, b = 4 * q + tt;
-            cx<T> x0, x1;
-            if (b < NBLK) {
-                const cx<T> *src = packet + f * FE_PKT + b * FE_BLK + FE_CP + n;
-                ld_pair(src, x0, x1);
-            } else {
-                cx<T> p10, p11, p20, p21;
-                ld_pair(lptot + f * FE_LP + 96 + n, p10, p11);
-                ld_pair(lptot + f * FE_LP + 32 + n, p20, p21);
+            cx<T> x0 = raw[i][0], x1 = raw[i][1];
+            if (4 * q + i >= NBLK) {                             // (p1 + p2) / 2 and the noise estimate, WiFi_RX.m:19-31
+                const cx<T> p10 = raw[3][0], p11 = raw[3][1], p20 = raw[4][0], p21 = raw[4][1];
                 x0 = mk<T>((p10.x + p20.x) * (T)0.5, (p10.y + p20.y) * (T)0.5);
                 x1 = mk<T>((p11.x + p21.x) * (T)0.5, (p11.y + p21.y) * (T)0.5);
                 const T d0x = p20.x - p10.x, d0y = p20.y - p10.y, d1x = p21.x - p11.x, d1y = p21.y - p11.y;
                 nv += d0x * d0x + d0y * d0y + d1x * d1x + d1y * d1y;
             }
-            tile[tt * FE_TS + n] = x0;
-            tile[tt * FE_TS + n + 1] = x1;
+            tile[i * FE_TS + n2] = x0;
+            tile[i * FE_TS + n2 + 1] = x1;
         }
         if (q == 3 && ow2) {                                     // warp-uniform
 #pragma unroll
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const cx<T> *__res
             if (lane == 0) ow2[f] = nv * (T)(1.0 / 128.0);
         }
         __syncwarp();
+        if (PREF && g + gstride < n_groups) fetch(g + gstride, raw);
         fft4_rows<T>(tile, t, j, tw);                             // steps B-D
         const int n_data = q < 3 ? 4 : 3;                        // data rows in this group (group 3 ends with the preamble)
         cx<T> *dst = symb + (f * NBLK + 4 * q) * NSC;
@@ -178,10 +194,10 @@ cudaError_t launch_frontend(wifi_dtype dt, const void *packet, const void *lptot
     const int64_t need = (n_frames * 4 + FE_WARPS - 1) / FE_WARPS;
     const unsigned grid = (unsigned)std::min<int64_t>(need, 148 * 8);
     if (dt == WIFI_F32)
-        frontend_kernel<float><<<grid, FE_THREADS, 0, s>>>((const float2 *)packet, (const float2 *)lptot, (float2 *)symb, (float2 *)pre_fft,
+        frontend_kernel<float, true><<<grid, FE_THREADS, 0, s>>>((const float2 *)packet, (const float2 *)lptot, (float2 *)symb, (float2 *)pre_fft,
                                                            (float *)ow2, n_frames);
     else
-        frontend_kernel<double><<<grid, FE_THREADS, 0, s>>>((const double2 *)packet, (const double2 *)lptot, (double2 *)symb,
+        frontend_kernel<double, false><<<grid, FE_THREADS, 0, s>>>((const double2 *)packet, (const double2 *)lptot, (double2 *)symb,
                                                             (double2 *)pre_fft, (double *)ow2, n_frames);
     return cudaGetLastError();
 }
