@@ -300,20 +300,18 @@ static int mmse_eig(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx
         ctx->eig_u_bytes[slot] = need;
     }
     void *U = ctx->eig_u[slot];
-    if (dt == WIFI_F32) {
-        // u = (rx/tx) G^T with y_dc in the free column 52; then H = (u - s (.) (u - p z_d)) G2^T: the second launch reads u and
-        // sigma2 only (G2 G = I on the non-null bins, so y itself is G2 u and tx / rx are not needed again)
-        { Timed t(ctx, s); CK(launch_mmse_shared_tc_eig_u(ctx->eig[0], tx, rx, frame_stride, ctx->eig_dc, U, n, s)); }
-        Timed t(ctx, s);
-        CK(launch_mmse_shared_tc_eig_h(ctx->eig[1], U, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd, ctx->eig_md, H, n, s));
-        return WIFI_OK;
-    }
     int rc = gemm_with(ctx, ctx->eig[0], dt, tx, rx, frame_stride, U, n, s);            // u = (rx/tx) G^T
     if (rc) return rc;
-    // v = s (.) (u - p z_d) in the producer stage, c = v G2^T on the tensor cores, H = rx/tx - c in the epilogue
+    // v = s (.) (u - p z_d) in the converter / producer stage, c = v G2^T on the tensor cores, H = rx/tx - c in the epilogue: y stays
+    // exact and only the correction passes through the product (the alternative H = (u - v) G2^T, without the second read of tx / rx,
+    // was measured in round 2: faster, but ~2e-6 of the frame's peak everywhere instead of ~2e-6 of the correction -- rejected)
     Timed t(ctx, s);
-    CK(launch_mmse_shared_dmma_eig(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd,
-                                   ctx->eig_md, H, n, s));
+    if (dt == WIFI_F32)
+        CK(launch_mmse_shared_tc_eig_h(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd,
+                                       ctx->eig_md, H, n, s));
+    else
+        CK(launch_mmse_shared_dmma_eig(ctx->eig[1], U, tx, rx, frame_stride, ctx->eig_dc, sigma2, ctx->eig_lam, ctx->eig_p, ctx->eig_Rdd,
+                                       ctx->eig_md, H, n, s));
     return WIFI_OK;
 }
 

@@ -202,15 +202,19 @@ template <bool FUSED> __device__ __forceinline__ float4 ls_pair(float4 a, float4
     return make_float4(h0.x, h0.y, h1.x, h1.y);
 }
 
-// Eigen-domain per-frame MMSE (wifi_eig.cu), two launches of this kernel:
-//   STASH (first product, u = y G^T with the LS divide fused): the value y_d = rx_d/tx_d of the null bin `dc` rides along in the
-//         unused column 52 of u (with a null bin the eigen-problem has 52 pairs), so the second launch never touches tx / rx;
-//   MID   (second product): the input rows are u; because G2 G = I on the non-null bins, y = G2 u and
-//             H = y - G2 (s (.) (u - p z_d)) = G2 ( u - s (.) (u - p z_d) ),   s_i = sigma2 / (l_i + sigma2),
-//         so the converter forms v' = u - s (.) (u - p z_d) on its way into tensor memory and the epilogue is the plain one; the
-//         null bin's H_d (border formula) travels in a register from converter to epilogue.  1 700 B of traffic per frame less
-//         than subtracting the product from a re-computed rx/tx (round 1).
+// Eigen-domain per-frame MMSE (wifi_eig.cu), the second of its two launches of this kernel (the first is the plain fused product
+// u = (rx/tx) G^T):
+//   MID    the input rows are u; the converter accumulates beta, gamma over its frame's row, forms z_d and writes
+//          v = s (.) (u - p z_d), s_i = sigma2 / (l_i + sigma2), straight into the tensor-memory operand images; the null bin's H_d
+//          (border formula) travels in a register from converter to epilogue;
+//   RESID  the epilogue writes  H = rx/tx - acc  (acc = v G2^T): y = rx/tx is recomputed from the frames' own block vectors.
+// H = y - c keeps y EXACT and passes only the correction c through the 3xTF32 product, so the error is ~2e-6 of |c|, not of |y|.
+// (Round 2 measured the alternative H = (u - v) G2^T -- y reconstructed as G2 u, no second read of tx / rx: 2 120 instead of 2 968 B
+// of DRAM traffic per frame and 8 % faster, but ~2e-6 of the frame's PEAK everywhere: 3e-4 at the survey's floor 1e-3 on one frame
+// in ~300 against 6e-6 here.  Parity first: rejected.)
 struct TcResid {
+    const float2 *tx, *rx;      // the frames' block vectors
+    int64_t stride;
     int dc;                     // null bin index or -1
     const float *sigma2;        // [n]
     const double *lam;          // [53] eigenvalues
@@ -226,7 +230,7 @@ __device__ __forceinline__ float rcp_fast(float x)
     return r;
 }
 
-template <bool FUSED, bool STASH, bool MID>
+template <bool FUSED, bool RESID, bool MID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     mmse_shared_tc_kernel(const float *__restrict__ Bhi_g, const float *__restrict__ Blo_g, const float2 *__restrict__ a_in,
                           const float2 *__restrict__ rx, int64_t frame_stride, float2 *__restrict__ H, int64_t n_frames, int aligned16,
@@ -296,7 +300,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
         const bool vec_ok = (frame_stride == NSC) && aligned16;
         float2 hd_stash = make_float2(0.f, 0.f);             // MID: H of the null bin of this lane's frame, from converter to epilogue
-        float2 yd_keep = make_float2(0.f, 0.f);              // STASH: y of the null bin of this lane's frame, from converter to epilogue
         for (int it = group; it < my_tiles + 2; it += 2) {
             // ---- 0. pull this warp's chunk of THIS tile from HBM into L2 now (no registers, no shared memory): the transfer
             //         runs under the epilogue of the group's previous tile below, and the LDGs of step a. then hit L2.
@@ -325,6 +328,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // ---- c. epilogue of this group's previous tile (it-2); must precede this iteration's a_ready arrival ----
             if (it >= 2) {
                 const int pt = it - 2;
+                if (RESID && lane == 0 && res.stride == NSC) {           // the epilogue's own inputs: HBM -> L2 while the MMAs finish
+                    const int64_t fe = (blockIdx.x + (int64_t)pt * gridDim.x) * TC_M + quarter * 32;
+                    if (fe + 32 <= n_frames && ((((uintptr_t)res.tx) | ((uintptr_t)res.rx)) & 15) == 0) {
+                        l2_prefetch(res.tx + fe * NSC, TC_CHUNK_F * 4);
+                        l2_prefetch(res.rx + fe * NSC, TC_CHUNK_F * 4);
+                    }
+                }
                 mbar_wait(&sm.bar_mma_done[pt & 1], (pt >> 1) & 1);
                 tc_fence_after();
                 const int64_t tile = blockIdx.x + (int64_t)pt * gridDim.x;
@@ -332,27 +342,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
                 const uint32_t dcol = lane_base + ((pt & 1) ? TC_COL_D1 : TC_COL_D0);
                 float2 *rowo = reinterpret_cast<float2 *>(buf + lane * TC_ROWF);
-                // 32 accumulator columns per tcgen05.ld and wait (four round trips to tensor memory per tile instead of seven)
+                // RESID: the epilogue's own inputs (tx, rx of this chunk) in four batches of 7 + 7 vectors; the first batch is
+                // issued before the TMEM -> shared staging below and each next one before the previous is consumed
+                constexpr int RB = 7;
+                float4 qt[2][RB], qr[2][RB];
+                const bool rvec = RESID && valid == 32 && res.stride == NSC &&
+                                  ((((uintptr_t)res.tx) | ((uintptr_t)res.rx) | ((uintptr_t)H)) & 15) == 0;
+                const float4 *pt4 = RESID ? reinterpret_cast<const float4 *>(res.tx + f0 * NSC) + lane : nullptr;
+                const float4 *pr4 = RESID ? reinterpret_cast<const float4 *>(res.rx + f0 * NSC) + lane : nullptr;
+                if (rvec) {
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    uint32_t v[32];
-                    tmem_ld32(dcol + 32 * g, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) rowo[g * 16 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    for (int j = 0; j < RB; ++j) { qt[0][j] = ld_stream(pt4 + 32 * j); qr[0][j] = ld_stream(pr4 + 32 * j); }
                 }
-                {
-                    uint32_t v[16];
-                    tmem_ld16(dcol + 96, v);
-                    tmem_wait_ld();
+                if (RESID) {
+                    // (16 accumulator columns per tcgen05.ld here: the 36 vectors in flight above leave no room for 32)
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) rowo[48 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    for (int g = 0; g < TC_N / 16; ++g) {
+                        uint32_t v[16];
+                        tmem_ld16(dcol + 16 * g, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            int cc = g * 8 + c;
+                            if (cc < NSC) rowo[cc] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                        }
+                    }
+                } else {
+                    // 32 accumulator columns per tcgen05.ld and wait (four round trips to tensor memory per tile instead of seven)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        uint32_t v[32];
+                        tmem_ld32(dcol + 32 * g, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) rowo[g * 16 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    }
+                    {
+                        uint32_t v[16];
+                        tmem_ld16(dcol + 96, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) rowo[48 + c] = make_float2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    }
                 }
-                if (STASH && res.dc >= 0) rowo[NSC - 1] = yd_keep;        // y_d of the null bin rides in the unused column 52 of u
-                if (MID && res.dc >= 0) rowo[res.dc] = hd_stash;           // the null bin's H_d (border formula)
                 tc_fence_before();
                 __syncwarp();
-                if (valid == 32 && aligned16) {
+                if (RESID) {
+                    // H = rx/tx - acc, null bin from the register the converter left
+                    if (rvec) {
+                        const float4 *b4 = reinterpret_cast<const float4 *>(buf) + lane;
+                        float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC) + lane;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            if (b < 3) {
+#pragma unroll
+                                for (int j = 0; j < RB; ++j) {
+                                    const int i = (b + 1) * RB + j;
+                                    if (i < 26 || (i == 26 && lane < 16)) { qt[(b + 1) & 1][j] = ld_stream(pt4 + 32 * i); qr[(b + 1) & 1][j] = ld_stream(pr4 + 32 * i); }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < RB; ++j) {
+                                const int i = b * RB + j;
+                                if (i < 26 || (i == 26 && lane < 16)) {
+                                    const float4 y = ls_pair<true>(qt[b & 1][j], qr[b & 1][j]), c = b4[32 * i];
+                                    st_stream(po + 32 * i, make_float4(y.x - c.x, y.y - c.y, y.z - c.z, y.w - c.w));
+                                }
+                            }
+                        }
+                    } else {
+                        const float2 *b2 = reinterpret_cast<const float2 *>(buf);
+                        for (int e = lane; e < valid * NSC; e += 32) {
+                            const int r = e / NSC, k = e - r * NSC;
+                            const int64_t off = (f0 + r) * res.stride + k;
+                            const float2 y = cdiv_fast(ld_stream(res.rx + off), ld_stream(res.tx + off)), c = b2[e];
+                            H[f0 * NSC + e] = make_float2(y.x - c.x, y.y - c.y);
+                        }
+                    }
+                    if (MID && res.dc >= 0) {
+                        __syncwarp();                    // orders this warp's stores above before the one below (same addresses)
+                        if (lane < valid) H[(f0 + lane) * NSC + res.dc] = hd_stash;
+                    }
+                } else if (valid == 32 && aligned16) {
                     const float4 *b4 = reinterpret_cast<const float4 *>(buf);
                     float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC);
 #pragma unroll 9
@@ -372,7 +443,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int valid = (int)max((int64_t)0, min((int64_t)32, n_frames - f0));
             // MID: this lane's per-frame scalars, requested now and used after the chunk has been staged
             float m_s2 = 1.f;
-            if (MID && lane < valid) m_s2 = res.sigma2[f0 + lane];
+            float2 m_td = make_float2(1.f, 0.f), m_rd = make_float2(0.f, 0.f);
+            if (MID && lane < valid) {
+                m_s2 = res.sigma2[f0 + lane];
+                if (res.dc >= 0) { m_td = res.tx[(f0 + lane) * res.stride + res.dc]; m_rd = res.rx[(f0 + lane) * res.stride + res.dc]; }
+            }
             // ---- a. chunk -> private buffer (row-major [32][106] floats), LS divide fused; loads software-pipelined ----
             if (vec_ok && valid == 32) {
                 const float4 *pa = reinterpret_cast<const float4 *>(a_in + f0 * NSC) + lane;
@@ -447,7 +522,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
             }
             __syncwarp();
-            if (STASH && res.dc >= 0) yd_keep = reinterpret_cast<const float2 *>(buf + lane * TC_ROWF)[res.dc];
             // FUSED, on request: the four pilot LS values of my frame (H_ls[5, 19, 33, 47], main.c:82-84) go out as one 32-byte
             // record, hp_out[f][4] -- the interpolating estimators then need no pilot gather of their own (8 isolated values per
             // frame cost a 64-byte DRAM atom each: 512 B against these 32)
@@ -474,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     ga = fmaf((pp.x * pp.x + pp.y * pp.y), inv, ga);
                 }
                 if (res.dc >= 0) {
-                    const float2 yd = row[NSC - 1];                             // stashed by the first launch (STASH)
+                    const float2 yd = cdiv_fast(m_rd, m_td);
                     const float q = res.Rdd - ga, iden = rcp_fast(m_s2 * res.md + q);
                     const float2 dlt = make_float2(yd.x - br, yd.y - bi);
                     m_zd = make_float2(dlt.x * iden, dlt.y * iden);
@@ -488,11 +562,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int c = 0; c < 8; ++c) {
                     int cc = g * 8 + c;
                     float2 v = (cc < NSC) ? row[cc] : make_float2(0.f, 0.f);
-                    if (MID && cc < NSC) {                                    // v'_i = u_i - s_i (u_i - p_i z_d), s_i = s2 / (l_i + s2)
+                    if (MID && cc < NSC) {                                    // v_i = s_i (u_i - p_i z_d), s_i = s2 / (l_i + s2)
                         const float sc = m_s2 * rcp_fast(sm.lam[cc] + m_s2);
                         const float2 pp = sm.pv[cc];
-                        v = make_float2(v.x - sc * (v.x - (pp.x * m_zd.x - pp.y * m_zd.y)), v.y - sc * (v.y - (pp.x * m_zd.y + pp.y * m_zd.x)));
-                        if (res.dc >= 0 && cc == NSC - 1) v = make_float2(0.f, 0.f);       // column 52 carried y_d, not an eigen component
+                        v = make_float2(sc * (v.x - (pp.x * m_zd.x - pp.y * m_zd.y)), sc * (v.y - (pp.x * m_zd.y + pp.y * m_zd.x)));
                     }
                     // hi = v rounded to the 11 significant bits of TF32 by Veltkamp's splitting, c = v (2^13 + 1), hi = c - (c - v): three
                     // FP32 instructions and NaN-safe (cvt.rna.tf32.f32 is FOUR SASS instructions here -- add, mask, and an FSETP + SEL pair
@@ -525,7 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-template <bool FUSED, bool STASH, bool MID>
+template <bool FUSED, bool RESID, bool MID>
 static cudaError_t launch_tc(const FilterImages &img, const void *a, const void *rx, int64_t frame_stride, void *H, int64_t n_frames,
                              const TcResid &res, cudaStream_t s, void *hp_out = nullptr)
 {
@@ -533,9 +606,9 @@ static cudaError_t launch_tc(const FilterImages &img, const void *a, const void 
     const int64_t n_tiles = (n_frames + TC_M - 1) / TC_M;
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, 148);
     const int aligned16 = ((((uintptr_t)a) | ((uintptr_t)rx) | ((uintptr_t)H)) & 15) == 0;
-    cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, STASH, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mmse_shared_tc_kernel<FUSED, RESID, MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mmse_shared_tc_kernel<FUSED, STASH, MID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
+    mmse_shared_tc_kernel<FUSED, RESID, MID><<<grid, TC_THREADS, smem, s>>>(img.Bhi, img.Blo, (const float2 *)a, (const float2 *)rx, frame_stride,
                                                                        (float2 *)H, n_frames, aligned16, res, (float2 *)hp_out);
     return cudaGetLastError();
 }
@@ -546,31 +619,21 @@ cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *a, const 
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const TcResid none = {-1, nullptr, nullptr, nullptr, 0.f, 0.f};
+    const TcResid none = {nullptr, nullptr, 0, -1, nullptr, nullptr, nullptr, 0.f, 0.f};
     return rx ? launch_tc<true, false, false>(img, a, rx, frame_stride, H, n_frames, none, s, hp_out)
               : launch_tc<false, false, false>(img, a, nullptr, frame_stride, H, n_frames, none, s);
 }
 
-// Eigen-domain per-frame MMSE, first product: u = (rx/tx) G^T (img = G); with a null bin `dc`, u[f][52] = rx_dc/tx_dc.
-cudaError_t launch_mmse_shared_tc_eig_u(const FilterImages &img, const void *tx, const void *rx, int64_t frame_stride, int dc, void *u,
+// Eigen-domain per-frame MMSE, second product: H = rx/tx - (s (.) (u - p z_d)) G2^T (img = G2), null bin from the border formula.
+cudaError_t launch_mmse_shared_tc_eig_h(const FilterImages &img, const void *u, const void *tx, const void *rx, int64_t frame_stride, int dc,
+                                        const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
                                         int64_t n_frames, cudaStream_t s)
 {
     g_last_launches = 0;
     if (n_frames == 0) return cudaSuccess;
     g_last_launches = 1;
-    const TcResid res = {dc, nullptr, nullptr, nullptr, 0.f, 0.f};
-    return launch_tc<true, true, false>(img, tx, rx, frame_stride, u, n_frames, res, s);
-}
-
-// Eigen-domain per-frame MMSE, second product: H = (u - s (.) (u - p z_d)) G2^T (img = G2), null bin from the border formula.
-cudaError_t launch_mmse_shared_tc_eig_h(const FilterImages &img, const void *u, int dc, const void *sigma2, const double *lam, const void *p,
-                                        double Rdd, double md, void *H, int64_t n_frames, cudaStream_t s)
-{
-    g_last_launches = 0;
-    if (n_frames == 0) return cudaSuccess;
-    g_last_launches = 1;
-    const TcResid res = {dc, (const float *)sigma2, lam, (const double2 *)p, (float)Rdd, (float)md};
-    return launch_tc<false, false, true>(img, u, nullptr, NSC, H, n_frames, res, s);
+    const TcResid res = {(const float2 *)tx, (const float2 *)rx, frame_stride, dc, (const float *)sigma2, lam, (const double2 *)p, (float)Rdd, (float)md};
+    return launch_tc<false, true, true>(img, u, nullptr, NSC, H, n_frames, res, s);
 }
 
 }  // namespace wifi

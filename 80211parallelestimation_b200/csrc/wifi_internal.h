@@ -61,10 +61,9 @@ cudaError_t launch_filter_fold(const void *W64, const void *tx64, void *Wout64, 
 cudaError_t launch_filter_install_tc(FilterImages &img, cudaStream_t s);     // W64 -> Bhi/Blo (UMMA canonical layout)
 cudaError_t launch_mmse_shared_tc(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                   int64_t n_frames, cudaStream_t s, void *hp_out = nullptr);   // FP32 I/O, 3xTF32 on tcgen05; hp_out [n][4]: pilot LS
-cudaError_t launch_mmse_shared_tc_eig_u(const FilterImages &img, const void *tx, const void *rx, int64_t frame_stride, int dc, void *u,
-                                        int64_t n_frames, cudaStream_t s);   // eigen-domain MMSE, 1st product: u = (rx/tx) G^T, u[f][52] = y_dc
-cudaError_t launch_mmse_shared_tc_eig_h(const FilterImages &img, const void *u, int dc, const void *sigma2, const double *lam, const void *p,
-                                        double Rdd, double md, void *H, int64_t n_frames, cudaStream_t s);   // 2nd: H = (u - s(.)(u - p z_d)) G2^T
+cudaError_t launch_mmse_shared_tc_eig_h(const FilterImages &img, const void *u, const void *tx, const void *rx, int64_t frame_stride, int dc,
+                                        const void *sigma2, const double *lam, const void *p, double Rdd, double md, void *H,
+                                        int64_t n_frames, cudaStream_t s);   // eigen-domain MMSE, 2nd product: H = rx/tx - (s (.) (u - p z_d)) G2^T
 cudaError_t launch_filter_install_dmma(FilterImages &img, cudaStream_t s);   // W64 -> B64
 cudaError_t launch_mmse_shared_dmma(const FilterImages &img, const void *tx_or_hls, const void *rx, int64_t frame_stride, void *H,
                                     int64_t n_frames, cudaStream_t s, void *hp_out = nullptr);   // FP64 I/O, DMMA m8n8k4; hp_out [n][4]: pilot LS
