@@ -46,6 +46,8 @@ SIGNATURES = {
     "wifi_mmse_perframe_batch": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
     "wifi_mmse_eig_prepare": [_vp, _vp, _vp],
     "wifi_mmse_perframe_eig_batch": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
+    "wifi_mmse_lowrank_prepare": [_vp, _vp, _vp],
+    "wifi_mmse_perframe_lowrank_batch": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_matlab_batch": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_batch": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],
@@ -71,6 +73,7 @@ SIGNATURES = {
     "wifi_pcie_probe": [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_d)],
     "wifi_mmse_perframe_host": [_vp, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i],
     "wifi_mmse_perframe_eig_host": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
+    "wifi_mmse_perframe_lowrank_host": [_vp, _i, _vp, _vp, _i64, _vp, _vp, _i64],
     "wifi_mmse_cconv_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_mmse_matlab_host": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64],
     "wifi_cmatmul_host": [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i64],

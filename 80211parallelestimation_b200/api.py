@@ -371,6 +371,35 @@ class WifiContext:
         self._ck(fn(self.h, dt, tx.ptr, rx.ptr, frame_stride, s.ptr, _ptr(H), n_frames))
         return H
 
+    def mmse_lowrank_prepare(self, R):
+        """Operands of mmse_perframe_lowrank from the covariance R (53x53 complex128): returns its numerical rank; raises WifiError
+        (INVALID) when the rank is 0 or above LOWRANK_MAX (use mmse_perframe / mmse_perframe_eig then)."""
+        import ctypes
+        import torch
+        r = R if _is_torch(R) else torch.from_numpy(np.ascontiguousarray(np.asarray(R, np.complex128))).cuda(self.device)
+        if r.dtype != torch.complex128:
+            raise TypeError("R must be complex128")
+        r = r.contiguous()
+        rank = ctypes.c_int(0)
+        self._sync_stream(True)
+        self._ck(self.lib.wifi_mmse_lowrank_prepare(self.h, r.data_ptr(), ctypes.addressof(rank)))
+        return rank.value
+
+    def mmse_perframe_lowrank(self, tx_symbols, rx_symbols, sigma2, frame_stride=NSC, n_frames=None, out=None):
+        """Per-frame PS_MMSE for a low-rank covariance (see mmse_lowrank_prepare): sigma2 and |tx_k|^2 free per frame, one launch."""
+        tx, rx = _Arg(tx_symbols), _Arg(rx_symbols)
+        dev, dt = _same(tx, rx)
+        if n_frames is None:
+            n_frames = tx.size // frame_stride
+        s = _Arg(sigma2, real=True)
+        if s.dt != dt or s.device != dev:
+            raise TypeError("sigma2 must match the precision and residency of the frames")
+        H = out if out is not None else tx.empty_like((n_frames, NSC))
+        self._sync_stream(dev)
+        fn = self.lib.wifi_mmse_perframe_lowrank_batch if dev else self.lib.wifi_mmse_perframe_lowrank_host
+        self._ck(fn(self.h, dt, tx.ptr, rx.ptr, frame_stride, s.ptr, _ptr(H), n_frames))
+        return H
+
     def mmse_cconv(self, tx_symbols, rx_symbols, ow2, H_ls, out=None):
         """PS_MMSE in the calling convention of main.c:148 (R_f = H_ls H_ls^H), batched over [n][53]."""
         tx, rx, h = _Arg(tx_symbols), _Arg(rx_symbols), _Arg(H_ls)

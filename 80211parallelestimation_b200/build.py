@@ -23,7 +23,7 @@ DROPIN_CXX = os.path.join(HERE, "libwifi_dropin_cxx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
-CU = ["wifi_ls.cu", "wifi_frontend.cu", "wifi_solve.cu", "wifi_inverse_tc.cu", "wifi_solve_hpd.cu", "wifi_gemm.cu", "wifi_gemm_tc.cu", "wifi_gemm_dmma.cu", "wifi_eig.cu", "wifi_synth.cu", "wifi_peaks.cu", "wifi_capi.cu"]
+CU = ["wifi_ls.cu", "wifi_frontend.cu", "wifi_solve.cu", "wifi_inverse_tc.cu", "wifi_solve_hpd.cu", "wifi_gemm.cu", "wifi_gemm_tc.cu", "wifi_gemm_dmma.cu", "wifi_eig.cu", "wifi_lowrank.cu", "wifi_synth.cu", "wifi_peaks.cu", "wifi_capi.cu"]
 
 
 def _newer(target, deps):

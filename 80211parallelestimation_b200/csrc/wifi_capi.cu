@@ -28,6 +28,7 @@ struct wifi_ctx {
     double *eig_lam; void *eig_p; double *eig_scal; int eig_valid; int eig_dc; double eig_Rdd, eig_md;
     void *eig_u[2]; size_t eig_u_bytes[2];   // scratch, one per pipeline stream (the two chunks of a *_host call are in flight at the
                                              // same time): [n][53] between the two eigen-domain products, [n][4] pilot records of estimate_all
+    void *lr_tab32, *lr_tab64; int lr_rank, lr_rank_padded;    // low-rank per-frame MMSE (wifi_lowrank.cu): tables of U, conj(U_i) U_j, 1/l
     int *d_info;             // device scratch: singularity flags
     int *h_info;             // pinned mirror
     char err[512];
@@ -165,6 +166,7 @@ int wifi_destroy(wifi_ctx *ctx)
     cudaFree(ctx->tab.w64); cudaFree(ctx->tab.w32);
     free_images(ctx->img); free_images(ctx->img_rx); free_images(ctx->eig[0]); free_images(ctx->eig[1]);
     cudaFree(ctx->eig_lam); cudaFree(ctx->eig_p); cudaFree(ctx->eig_scal); cudaFree(ctx->eig_u[0]); cudaFree(ctx->eig_u[1]);
+    cudaFree(ctx->lr_tab32); cudaFree(ctx->lr_tab64);
     cudaFree(ctx->d_info);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -356,6 +358,69 @@ int wifi_mmse_shared_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const v
     ENTER();
     NEED(n >= 0 && (n == 0 || (tx && rx && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
     return mmse_shared(ctx, dt, tx, rx, frame_stride, H, n, ctx->stream);
+}
+
+// ---- low-rank covariance: H = U (sigma2 L^-1 + U^H diag(|x|^2) U)^-1 U^H (conj(x) (.) rx), one launch (wifi_lowrank.cu) ----
+int wifi_mmse_lowrank_prepare(wifi_ctx *ctx, const void *R, int *rank_out)
+{
+    ENTER();
+    NEED(R);
+    ctx->lr_rank = 0;
+    if (rank_out) *rank_out = 0;
+    // eigen-decomposition of R itself: the eigen-domain set-up kernel with |x| = 1 (no null bin, S = R), into scratch of its own
+    const size_t nW = sizeof(double2) * WIFI_NSC * WIFI_NSC;
+    char *scr = nullptr;
+    const size_t off_w2 = nW, off_lam = 2 * nW, off_p = off_lam + 64 * sizeof(double), off_scal = off_p + 64 * sizeof(double2),
+                 off_ones = off_scal + 4 * sizeof(double), total = off_ones + 64 * sizeof(double);
+    if (cudaMalloc(&scr, total) != cudaSuccess) return fail(ctx, WIFI_ERR_NOMEM, "low-rank set-up scratch cudaMalloc(%zu) failed", total);
+    std::vector<double> hbuf(2 * WIFI_NSC * WIFI_NSC + 64, 1.0);
+    double *hV = hbuf.data(), *hlam = hbuf.data() + 2 * WIFI_NSC * WIFI_NSC;
+    int rc = WIFI_OK;
+    cudaError_t e = cudaMemcpyAsync(scr + off_ones, hlam, 64 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);      // 64 ones
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) {
+        Timed t(ctx, ctx->stream);
+        e = launch_eig_prepare(R, (const double *)(scr + off_ones), scr, scr + off_w2, (double *)(scr + off_lam), scr + off_p,
+                               (double *)(scr + off_scal), ctx->d_info, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hV, scr + off_w2, nW, cudaMemcpyDeviceToHost, ctx->stream);                // W2 = V (columns)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hlam, scr + off_lam, WIFI_NSC * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(scr);
+    if (e != cudaSuccess) return fail(ctx, WIFI_ERR_CUDA, "low-rank set-up: %s", cudaGetErrorString(e));
+    std::vector<float> t32;
+    std::vector<double> t64;
+    int padded = 0;
+    const int r = lowrank_build_tables(hV, hlam, &padded, t32, t64);
+    if (rank_out) *rank_out = r;
+    if (r == 0) return fail(ctx, WIFI_ERR_INVALID, "low-rank MMSE: the covariance has no positive eigenvalue");
+    if (r > WIFI_LOWRANK_MAX)
+        return fail(ctx, WIFI_ERR_INVALID, "low-rank MMSE: numerical rank %d of the covariance exceeds %d -- use wifi_mmse_perframe_* or wifi_mmse_eig_*", r,
+                    WIFI_LOWRANK_MAX);
+    cudaFree(ctx->lr_tab32); cudaFree(ctx->lr_tab64); ctx->lr_tab32 = ctx->lr_tab64 = nullptr;
+    CK(cudaMalloc(&ctx->lr_tab32, t32.size() * sizeof(float)));
+    CK(cudaMalloc(&ctx->lr_tab64, t64.size() * sizeof(double)));
+    CK(cudaMemcpy(ctx->lr_tab32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->lr_tab64, t64.data(), t64.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->lr_rank = r; ctx->lr_rank_padded = padded;
+    return rc;
+}
+
+static int mmse_lowrank(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2, void *H, int64_t n,
+                        cudaStream_t s)
+{
+    if (!ctx->lr_rank) return fail(ctx, WIFI_ERR_STATE, "no low-rank operands installed: call wifi_mmse_lowrank_prepare first");
+    Timed t(ctx, s);
+    CK(launch_mmse_lowrank(dt, ctx->lr_rank_padded, dt == WIFI_F32 ? ctx->lr_tab32 : ctx->lr_tab64, tx, rx, frame_stride, sigma2, H, n, s));
+    return WIFI_OK;
+}
+
+int wifi_mmse_perframe_lowrank_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                                     void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    return mmse_lowrank(ctx, dt, tx, rx, frame_stride, sigma2, H, n, ctx->stream);
 }
 
 static int mmse_perframe(wifi_ctx *ctx, wifi_dtype dt, const void *R, const void *tx, const void *rx, int64_t frame_stride,
@@ -939,6 +1004,19 @@ int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, co
     return host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), in_arr(sigma2, rsize(dt), rsize(dt)), out_arr(H, row)},
                          [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
                              return mmse_eig(ctx, dt, d[0], d[1], WIFI_NSC, d[2], d[3], nc, s, s == ctx->hstream[1] ? 1 : 0);
+                         });
+}
+
+int wifi_mmse_perframe_lowrank_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx, const void *rx, int64_t frame_stride, const void *sigma2,
+                                    void *H, int64_t n)
+{
+    ENTER();
+    NEED(n >= 0 && (n == 0 || (tx && rx && sigma2 && H)) && (dt == WIFI_F32 || dt == WIFI_F64) && frame_stride >= WIFI_NSC);
+    if (!ctx->lr_rank) return fail(ctx, WIFI_ERR_STATE, "no low-rank operands installed: call wifi_mmse_lowrank_prepare first");
+    const size_t row = WIFI_NSC * esize(dt), pitch = (size_t)frame_stride * esize(dt);
+    return host_pipeline(ctx, n, {in_arr(tx, row, pitch), in_arr(rx, row, pitch), in_arr(sigma2, rsize(dt), rsize(dt)), out_arr(H, row)},
+                         [&](std::vector<void *> &d, int64_t nc, int64_t, cudaStream_t s) {
+                             return mmse_lowrank(ctx, dt, d[0], d[1], WIFI_NSC, d[2], d[3], nc, s);
                          });
 }
 

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t d = tmem + ((it & 1) ? TC_COL_D1 : TC_COL_D0);
                 // The accumulator adds with truncation once per instruction, at the magnitude of the running sum: the 28 small
                 // cross products (~2^-11 of the result) go FIRST, while the sum is small, and the 14 hi x hi products last -- 14
-                // full-magnitude truncations per output instead of 42.  Measured on 18 949 frames against the long-double oracle: worst bin
+                // full-magnitude truncations per output instead of 42.  Measured on 18 949 frames against a long-double evaluation on the host: worst bin
                 // 5.0e-5 at floor 1e-3 (interleaved order: 1.44e-4), 1.2e-5 at floor 1e-2 (3.2e-5), 1.2e-6 of the frame's peak (2.5e-6);
                 // the launch takes the same time.
 #pragma unroll

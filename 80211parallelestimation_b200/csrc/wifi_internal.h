@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/wifi_b200.h"
 
 #define WIFI_DMMA_BS 116   /* row stride of the FP64 filter image in doubles (4 mod 16: conflict-free fragment loads) */
@@ -87,6 +88,12 @@ cudaError_t launch_error_stats(wifi_dtype dt, const void *H, const void *Href, i
 // eigen-domain per-frame MMSE (wifi_eig.cu)
 cudaError_t launch_eig_prepare(const void *R64, const double *absx2, void *W1, void *W2, double *lam, void *p, double *scal, int *info,
                                cudaStream_t s);
+
+// low-rank per-frame MMSE (wifi_lowrank.cu): tables from the eigen pairs of R (host), one launch per batch
+cudaError_t launch_mmse_lowrank(wifi_dtype dt, int rank_padded, const void *tab, const void *tx, const void *rx, int64_t frame_stride,
+                                const void *sigma2, void *H, int64_t n_frames, cudaStream_t s);
+
+int lowrank_build_tables(const double *V_re_im, const double *lam, int *rank_padded, std::vector<float> &t32, std::vector<double> &t64);
 
 // measured ceilings (wifi_peaks.cu): which = 0 FP32 FMA, 1 FP64 FMA, 2 FP64 DMMA (TFLOP/s), 3 streaming copy (GB/s)
 cudaError_t measure_peak(int which, double *value, cudaStream_t s);

@@ -1,0 +1,279 @@
+// wifi_lowrank.cu -- per-frame PS_MMSE for a LOW-RANK channel covariance, in one HBM-bound launch.
+//
+//   H_f = R (R + sigma2_f diag(1/|x_fk|^2))^-1 (rx_f / x_f)            (WiFi_channel_estimation_PS_MMSE.m:16-33, north-star form)
+//
+// A channel of L taps has a covariance of rank L: R = U L U^H with U 53 x r (r <= 8 here; the synthetic channel of SURVEY 8(d)
+// has r = 4).  The push-through identity  R (R + D)^-1 = U (L^-1 + U^H D^-1 U)^-1 U^H D^-1  with D^-1 = diag(|x_k|^2) / sigma2 gives
+//     t = U^H (conj(x) (.) rx)                       r complex values            (|x|^2 rx/x = conj(x) rx: no divide, no 1/x)
+//     G = U^H diag(|x|^2) U                          r x r Hermitian
+//     S = sigma2 L^-1 + G,   S w = t                 r x r Hermitian positive definite solve in registers
+//     H = U w
+// -- 8 kflop per frame at r = 4 instead of the 442 kflop of the 53 x 53 solve (wifi_solve_hpd.cu), on the frame's own 159 complex
+// values of traffic.  Both sigma2 AND the modulus pattern |x_k|^2 may differ per frame (QAM), which the eigen-domain path
+// (wifi_eig.cu: shared |x_k|^2 only) cannot do; a bin without transmit energy (the DC bin) simply contributes nothing.
+// S is well conditioned (G ~ |x|^2 I, sigma2/l tiny), so FP32 ARITHMETIC meets the 1e-4 bound here, where FP32 elimination of
+// the 53 x 53 matrix R + D (condition 1e7) cannot.
+//
+// Kernel: one persistent CTA of 8 warps per SM; a warp owns a chunk of 32 frames.
+//   a. coalesced element-wise pass over the chunk (lane = consecutive sub-carrier values): a = conj(x) rx and m = |x|^2 staged in
+//      the warp's private shared-memory tile (FP64: two slabs of 27 / 26 bins so that 8 warps fit);
+//   b. lane = frame: t and G accumulated over the bins from the tile (conflict-free: odd row stride) and the shared tables
+//      U_k, P_k = conj(U_ki) U_kj (broadcast loads);   c. S w = t by Hermitian elimination in registers;
+//   d. H = U w written back through the tile, coalesced streaming store.
+// The next chunk of the warp is pulled into L2 (cp.async.bulk.prefetch.L2) while the current one is processed.
+#include <algorithm>
+#include <cmath>
+#include <type_traits>
+#include <vector>
+#include "wifi_common.cuh"
+#include "wifi_internal.h"
+
+namespace wifi {
+
+constexpr int LR_WARPS = 8;
+template <typename T> struct LrSlab { static constexpr int W = sizeof(T) == 4 ? NSC : 27; };     // bins staged at a time
+template <typename T, int R> struct LrBatch { static constexpr int N = sizeof(T) == 4 ? 14 : (R > 4 ? 5 : 9); };   // element loads in flight per lane and array
+template <typename T, int R> struct LrUnroll { static constexpr int N = (sizeof(T) == 8 && R > 4) ? 1 : 2; };     // bins per trip of the accumulation loop (registers)
+// tables (in T): U[53][2 R] (re, im of U_kj) | P[53][R R] (|U_ki|^2, i < R; then re, im of conj(U_ki) U_kj, i < j) | 1 / l_j [R]
+template <int R> struct LrTab {
+    static constexpr int U = 0, P = NSC * 2 * R, L = P + NSC * R * R, SIZE = (L + R + 3) & ~3;
+};
+__host__ __device__ constexpr int lr_pair(int R, int i, int j) { return i * R - i * (i + 1) / 2 + (j - i - 1); }     // i < j
+
+template <typename T, int N> __device__ __forceinline__ void lr_load(const T *p, T (&v)[N])
+{
+    constexpr int PER = 16 / sizeof(T);
+    static_assert(N % PER == 0, "table rows are whole 16-byte vectors");
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+    for (int q = 0; q < N / PER; ++q) {
+        const V w = reinterpret_cast<const V *>(p)[q];
+        if constexpr (sizeof(T) == 4) { v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w; }
+        else { v[2 * q] = w.x; v[2 * q + 1] = w.y; }
+    }
+}
+
+__device__ __forceinline__ void lr_l2_prefetch(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(LR_WARPS * 32, 1)
+    mmse_lowrank_kernel(const T *__restrict__ tab_g, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx, int64_t stride,
+                        const T *__restrict__ sigma2, cx<T> *__restrict__ H, int64_t n, int aligned16)
+{
+    constexpr int SW = LrSlab<T>::W, NB = LrBatch<T, R>::N, UNR = LrUnroll<T, R>::N, NP = R * (R - 1) / 2;
+    using TB = LrTab<R>;
+    extern __shared__ __align__(16) unsigned char lr_smem[];
+    T *tab = reinterpret_cast<T *>(lr_smem);
+    cx<T> *A = reinterpret_cast<cx<T> *>(tab + TB::SIZE) + (threadIdx.x >> 5) * 32 * SW;                 // this warp's tile: a, later H
+    T *M = reinterpret_cast<T *>(reinterpret_cast<cx<T> *>(tab + TB::SIZE) + LR_WARPS * 32 * SW) + (threadIdx.x >> 5) * 32 * SW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < TB::SIZE; e += LR_WARPS * 32) tab[e] = tab_g[e];
+    __syncthreads();
+
+    const int64_t n_chunks = (n + 31) / 32, cstep = (int64_t)gridDim.x * LR_WARPS;
+    const bool dense = stride == NSC && aligned16;
+    constexpr uint32_t CHUNK_BYTES = 32 * NSC * sizeof(cx<T>);
+    // chunks are dealt so that the whole grid sweeps HBM as one moving window: (round * gridDim + block) * 8 + warp
+    for (int64_t chunk = (int64_t)blockIdx.x * LR_WARPS + warp; chunk < n_chunks; chunk += cstep) {
+        const int64_t f0 = chunk * 32;
+        const int valid = (int)min((int64_t)32, n - f0);
+        {
+            const int64_t fn = (chunk + cstep) * 32;
+            if (dense && lane == 0 && fn + 32 <= n) { lr_l2_prefetch(tx + fn * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fn * NSC, CHUNK_BYTES); }
+        }
+        T tr[R], ti[R], gd[R], gor[NP > 0 ? NP : 1], goi[NP > 0 ? NP : 1];
+#pragma unroll
+        for (int j = 0; j < R; ++j) tr[j] = ti[j] = gd[j] = (T)0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) gor[q] = goi[q] = (T)0;
+
+#pragma unroll
+        for (int s0 = 0; s0 < NSC; s0 += SW) {
+            const int kw = NSC - s0 < SW ? NSC - s0 : SW;                  // compile-time after unrolling
+            const int total = 32 * kw;
+            // ---- a. element-wise, coalesced: a = conj(x) rx, m = |x|^2 -> tile ----
+#pragma unroll 1
+            for (int base = lane; base < total; base += 32 * NB) {
+                cx<T> xv[NB], rv[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int idx = base + 32 * j;
+                    xv[j] = rv[j] = mk<T>((T)0, (T)0);
+                    if (idx < total) {
+                        const int fr = idx / kw, kk = idx - fr * kw;
+                        if (fr < valid) {
+                            const int64_t off = (f0 + fr) * stride + s0 + kk;
+                            xv[j] = ld_stream(tx + off);
+                            rv[j] = ld_stream(rx + off);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int idx = base + 32 * j;
+                    if (idx < total) {
+                        const int fr = idx / kw, kk = idx - fr * kw;
+                        const cx<T> x = xv[j], r = rv[j];
+                        A[fr * SW + kk] = mk<T>(fma(x.x, r.x, x.y * r.y), fma(x.x, r.y, -(x.y * r.x)));
+                        M[fr * SW + kk] = fma(x.x, x.x, x.y * x.y);
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- b. lane = frame: t += conj(U_k) a_k,  G += m_k P_k ----
+            const cx<T> *Ar = A + lane * SW;
+            const T *Mr = M + lane * SW;
+#pragma unroll UNR
+            for (int kk = 0; kk < kw; ++kk) {
+                const cx<T> a = Ar[kk];
+                const T m = Mr[kk];
+                T u[2 * R], p[R * R];
+                lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
+                lr_load<T, R * R>(tab + TB::P + (s0 + kk) * R * R, p);
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    tr[j] = fma(u[2 * j], a.x, tr[j]); tr[j] = fma(u[2 * j + 1], a.y, tr[j]);
+                    ti[j] = fma(u[2 * j], a.y, ti[j]); ti[j] = fma(-u[2 * j + 1], a.x, ti[j]);
+                    gd[j] = fma(m, p[j], gd[j]);
+                }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { gor[q] = fma(m, p[R + 2 * q], gor[q]); goi[q] = fma(m, p[R + 2 * q + 1], goi[q]); }
+            }
+            __syncwarp();
+        }
+
+        // ---- c. S = G + sigma2 / l on the diagonal;  S w = t by Hermitian elimination (upper triangle stored), back-substitution ----
+        {
+            const T s2 = lane < valid ? sigma2[f0 + lane] : (T)1;
+            T dinv[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) gd[j] = fma(s2, tab[TB::L + j], gd[j]);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const T inv = (T)1 / gd[k];
+                dinv[k] = inv;
+#pragma unroll
+                for (int i = k + 1; i < R; ++i) {
+                    const T sr = gor[lr_pair(R, k, i)], si = goi[lr_pair(R, k, i)];
+                    const T lr = sr * inv, li = -si * inv;                         // l = conj(S_ki) / S_kk
+                    const T tkr = tr[k], tki = ti[k];
+                    tr[i] -= lr * tkr - li * tki;
+                    ti[i] -= lr * tki + li * tkr;
+                    gd[i] -= (sr * sr + si * si) * inv;
+#pragma unroll
+                    for (int j = i + 1; j < R; ++j) {
+                        const T kr = gor[lr_pair(R, k, j)], ki = goi[lr_pair(R, k, j)];
+                        gor[lr_pair(R, i, j)] -= lr * kr - li * ki;
+                        goi[lr_pair(R, i, j)] -= lr * ki + li * kr;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = R - 1; k >= 0; --k) {
+                T ar = tr[k], ai = ti[k];
+#pragma unroll
+                for (int j = k + 1; j < R; ++j) {
+                    const T sr = gor[lr_pair(R, k, j)], si = goi[lr_pair(R, k, j)];
+                    ar -= sr * tr[j] - si * ti[j];
+                    ai -= sr * ti[j] + si * tr[j];
+                }
+                tr[k] = ar * dinv[k];                                              // w overwrites t
+                ti[k] = ai * dinv[k];
+            }
+        }
+
+        // ---- d. H = U w through the tile, coalesced streaming store ----
+#pragma unroll
+        for (int s0 = 0; s0 < NSC; s0 += SW) {
+            const int kw = NSC - s0 < SW ? NSC - s0 : SW;
+            const int total = 32 * kw;
+            cx<T> *Ar = A + lane * SW;
+#pragma unroll 2
+            for (int kk = 0; kk < kw; ++kk) {
+                T u[2 * R];
+                lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
+                T hr = (T)0, hi = (T)0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    hr = fma(u[2 * j], tr[j], hr); hr = fma(-u[2 * j + 1], ti[j], hr);
+                    hi = fma(u[2 * j], ti[j], hi); hi = fma(u[2 * j + 1], tr[j], hi);
+                }
+                Ar[kk] = mk<T>(hr, hi);
+            }
+            __syncwarp();
+            for (int idx = lane; idx < total; idx += 32) {
+                const int fr = idx / kw, kk = idx - fr * kw;
+                if (fr < valid) st_stream(H + (f0 + fr) * NSC + s0 + kk, A[fr * SW + kk]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <typename T, int R> static size_t lr_smem_bytes()
+{
+    return sizeof(T) * LrTab<R>::SIZE + (size_t)LR_WARPS * 32 * LrSlab<T>::W * (sizeof(cx<T>) + sizeof(T));
+}
+
+template <typename T, int R>
+static cudaError_t launch_lr(const void *tab, const void *tx, const void *rx, int64_t stride, const void *sigma2, void *H, int64_t n, cudaStream_t s)
+{
+    const size_t smem = lr_smem_bytes<T, R>();
+    auto kern = mmse_lowrank_kernel<T, R>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t n_chunks = (n + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_chunks + LR_WARPS - 1) / LR_WARPS, 148);
+    const int aligned16 = ((((uintptr_t)tx) | ((uintptr_t)rx)) & 15) == 0;
+    kern<<<grid, LR_WARPS * 32, smem, s>>>((const T *)tab, (const cx<T> *)tx, (const cx<T> *)rx, stride, (const T *)sigma2, (cx<T> *)H, n, aligned16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mmse_lowrank(wifi_dtype dt, int rank_padded, const void *tab, const void *tx, const void *rx, int64_t frame_stride,
+                                const void *sigma2, void *H, int64_t n_frames, cudaStream_t s)
+{
+    g_last_launches = 0;
+    if (n_frames == 0) return cudaSuccess;
+    g_last_launches = 1;
+    if (dt == WIFI_F32)
+        return rank_padded == 4 ? launch_lr<float, 4>(tab, tx, rx, frame_stride, sigma2, H, n_frames, s)
+                                : launch_lr<float, 8>(tab, tx, rx, frame_stride, sigma2, H, n_frames, s);
+    return rank_padded == 4 ? launch_lr<double, 4>(tab, tx, rx, frame_stride, sigma2, H, n_frames, s)
+                            : launch_lr<double, 8>(tab, tx, rx, frame_stride, sigma2, H, n_frames, s);
+}
+
+// Host side of wifi_mmse_lowrank_prepare: eigenvectors V [53][53] (columns; row-major double2) and eigenvalues lam [53] of R
+// (wifi_eig.cu with |x| = 1; eigenvalues below 64 eps l_max arrive as exact zeros) -> the kernel's tables in both precisions.
+// Returns the rank (0: R = 0; > WIFI_LOWRANK_MAX: unsupported, tables untouched).
+int lowrank_build_tables(const double *V /* re, im interleaved */, const double *lam, int *rank_padded, std::vector<float> &t32, std::vector<double> &t64)
+{
+    int idx[NSC], r = 0;
+    for (int i = 0; i < NSC; ++i) if (lam[i] > 0.0) idx[r++] = i;
+    std::sort(idx, idx + r, [&](int a, int b) { return lam[a] > lam[b]; });
+    if (r == 0 || r > WIFI_LOWRANK_MAX) return r;
+    const int R = r <= 4 ? 4 : 8;
+    *rank_padded = R;
+    const int offU = 0, offP = NSC * 2 * R, offL = offP + NSC * R * R, size = (offL + R + 3) & ~3;
+    t64.assign(size, 0.0);
+    for (int k = 0; k < NSC; ++k) {
+        double ur[8] = {0}, ui[8] = {0};
+        for (int j = 0; j < r; ++j) { ur[j] = V[2 * (k * NSC + idx[j])]; ui[j] = V[2 * (k * NSC + idx[j]) + 1]; }
+        double *U = &t64[offU + k * 2 * R], *P = &t64[offP + k * R * R];
+        for (int j = 0; j < R; ++j) { U[2 * j] = ur[j]; U[2 * j + 1] = ui[j]; P[j] = ur[j] * ur[j] + ui[j] * ui[j]; }
+        for (int i = 0; i < R; ++i)
+            for (int j = i + 1; j < R; ++j) {                       // conj(U_ki) U_kj
+                const int q = lr_pair(R, i, j);
+                P[R + 2 * q] = ur[i] * ur[j] + ui[i] * ui[j];
+                P[R + 2 * q + 1] = ur[i] * ui[j] - ui[i] * ur[j];
+            }
+    }
+    for (int j = 0; j < R; ++j) t64[offL + j] = j < r ? 1.0 / lam[idx[j]] : 1.0;      // padded directions: U = 0, S_jj = sigma2, t_j = 0 -> w_j = 0
+    t32.resize(size);
+    for (int e = 0; e < size; ++e) t32[e] = (float)t64[e];
+    return r;
+}
+
+}  // namespace wifi

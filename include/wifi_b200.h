@@ -172,6 +172,17 @@ int wifi_mmse_perframe_batch(wifi_ctx *ctx, wifi_dtype dt, const void *R, const 
 int wifi_mmse_eig_prepare(wifi_ctx *ctx, const void *R_f64, const double *absx2_f64);
 int wifi_mmse_perframe_eig_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                                  int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
+/* Per-frame case for a LOW-RANK covariance (a channel of L taps: rank L; numerical rank <= WIFI_LOWRANK_MAX), sigma2 AND the
+ * modulus pattern |tx_k|^2 free per frame (QAM): with R = U L U^H (FP64 Jacobi on the device, eigenvalues below 64 eps l_max
+ * dropped)  H = U (sigma2 L^-1 + U^H diag(|x|^2) U)^-1 U^H (conj(x) (.) rx)  -- the same H = R (R + sigma2 diag(1/|x|^2))^-1 (rx/tx)
+ * as wifi_mmse_perframe_batch (WiFi_channel_estimation_PS_MMSE.m:16-33) by the push-through identity, as an r x r solve per frame
+ * in ONE HBM-bound launch.  The r x r system is well conditioned, so WIFI_F32 runs in FP32 arithmetic and meets the 1e-4 bound.
+ * A bin with tx = 0 contributes nothing (the 53 x 53 solve yields NaN there).  R: 53x53 double2 (device); *rank_out (may be NULL)
+ * receives the numerical rank; rank 0 or > WIFI_LOWRANK_MAX -> WIFI_ERR_INVALID and no operands are installed. */
+#define WIFI_LOWRANK_MAX 8
+int wifi_mmse_lowrank_prepare(wifi_ctx *ctx, const void *R_f64, int *rank_out);
+int wifi_mmse_perframe_lowrank_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                                     int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
 /* C calling convention of main.c:148 batched: R_f = H_ls,f H_ls,f^H (main.c:186-189 intent),
  * tx/rx block vectors [n][53], ow2 [n] real, H_ls [n][53] -> H [n][53] */
 int wifi_mmse_cconv_batch(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
@@ -237,6 +248,8 @@ int wifi_mmse_perframe_host(wifi_ctx *ctx, wifi_dtype dt, const void *R, const v
                             int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames, int flags);
 int wifi_mmse_perframe_eig_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                                 int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
+int wifi_mmse_perframe_lowrank_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
+                                    int64_t frame_stride, const void *sigma2, void *H, int64_t n_frames);
 int wifi_mmse_cconv_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_symbols, const void *rx_symbols,
                          const void *ow2, const void *H_ls, void *H, int64_t n_frames);
 int wifi_mmse_matlab_host(wifi_ctx *ctx, wifi_dtype dt, const void *tx_frames, const void *rx_frames,

@@ -575,6 +575,61 @@ def test_mmse_eigen_domain_needs_prepare_and_one_null_bin(wifi):
         c.mmse_eig_prepare(synth.channel_covariance(), a)
 
 
+# ------------------------------------------------------------------ MMSE, per frame, low-rank covariance (push-through form)
+def _qam(tx, rx, seed):
+    """Per-frame, per-bin 16-QAM symbols on top of the BPSK frames: |tx_k|^2 now differs from bin to bin and frame to frame (x9 span)."""
+    rng = np.random.default_rng(seed)
+    lv = np.array([-3, -1, 1, 3]) / np.sqrt(10.0)
+    q = lv[rng.integers(0, 4, tx.shape)] + 1j * lv[rng.integers(0, 4, tx.shape)]
+    return (tx * q).astype(tx.dtype), (rx * q).astype(rx.dtype)
+
+
+@pytest.mark.parametrize("taps", [4, 7])
+@pytest.mark.parametrize("qam", [False, True])
+@pytest.mark.parametrize("prec,tol", [("f64", 1e-10), ("f32", 1e-4)])      # measured 2e-11 / 2e-5
+@pytest.mark.parametrize("n", [1, 45, 300])
+def test_mmse_perframe_lowrank(ctx, oracle, prec, tol, qam, taps, n):
+    """One-launch per-frame PS_MMSE for a rank-4 / rank-7 covariance against the oracle's long-double 53 x 53 solve of the same
+    R (R + sigma2 diag(1/|x|^2))^-1 (rx/tx), sigma2 in [1e-8, 1e-5] per frame, BPSK and per-frame 16-QAM moduli, ragged n, whole frames
+    in place and host pointers.  FP32 runs in FP32 ARITHMETIC here (the r x r system is well conditioned)."""
+    fr = synth.make_frames(n, seed=700 + n, sigma2="perframe", dtype=CDT[prec])
+    tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
+    if qam:
+        tx, rx = _qam(tx, rx, n)
+    s2 = fr["sigma2"].astype(np.float64 if prec == "f64" else np.float32)
+    R = synth.channel_covariance(taps)
+    assert ctx.mmse_lowrank_prepare(R) == taps
+    got = host(ctx.mmse_perframe_lowrank(dev(tx), dev(rx), dev(s2)))
+    pick = np.unique(np.r_[0, n - 1, np.random.default_rng(n).integers(0, n, 40)])
+    ref = oracle.mmse_perframe(R, tx[pick].astype(np.complex128), rx[pick].astype(np.complex128), s2[pick].astype(np.float64))
+    e = rel_err(got[pick], ref)
+    print("mmse_perframe_lowrank %s taps=%d qam=%d n=%d: %.3g" % (prec, taps, qam, n, e))
+    assert e < tol
+    assert np.isfinite(got).all()
+    if n == 300 and not qam:                                           # whole frames in place + host pointers
+        g2 = host(ctx.mmse_perframe_lowrank(dev(fr["tx_symb"]).reshape(-1), dev(fr["rx_symb"]).reshape(-1), dev(s2), frame_stride=15 * NSC, n_frames=n))
+        assert np.array_equal(g2, got)
+        assert np.array_equal(ctx.mmse_perframe_lowrank(tx, rx, s2), got)
+        if prec == "f64":                                              # the 53 x 53 device solve on the same frames: two algorithms, one estimator
+            assert rel_err(got, host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2)))) < 1e-9
+
+
+def test_mmse_lowrank_rank_gate(wifi):
+    c = wifi.WifiContext(0)
+    z = np.ones((1, NSC), np.complex128)
+    with pytest.raises(wifi.WifiError):                                # nothing installed
+        c.mmse_perframe_lowrank(dev(z), dev(z), dev(np.ones(1)))
+    with pytest.raises(wifi.WifiError, match="rank"):                  # full-rank covariance: not this path
+        c.mmse_lowrank_prepare(synth.random_hpd(np.random.default_rng(1)))
+    with pytest.raises(wifi.WifiError):
+        c.mmse_perframe_lowrank(dev(z), dev(z), dev(np.ones(1)))
+    assert c.mmse_lowrank_prepare(synth.channel_covariance(8)) == 8
+    assert c.mmse_perframe_lowrank(dev(z[:0]), dev(z[:0]), dev(np.ones(0))).shape[0] == 0
+    with pytest.raises(wifi.WifiError, match="rank"):
+        c.mmse_lowrank_prepare(synth.channel_covariance(9))
+    c.close()
+
+
 # ------------------------------------------------------------------ utils.h
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_utils_vs_reference(ctx, wifi, gold, prec):
