@@ -32,7 +32,6 @@ namespace wifi {
 
 constexpr int LR_WARPS = 8;
 template <typename T> struct LrSlab { static constexpr int W = sizeof(T) == 4 ? NSC : 27; };     // bins staged at a time
-template <typename T, int R> struct LrBatch { static constexpr int N = sizeof(T) == 4 ? 14 : (R > 4 ? 5 : 9); };   // element loads in flight per lane and array
 template <typename T, int R> struct LrUnroll { static constexpr int N = (sizeof(T) == 8 && R > 4) ? 1 : 2; };     // bins per trip of the accumulation loop (registers)
 // tables (in T): U[53][2 R] (re, im of U_kj) | P[53][R R] (|U_ki|^2, i < R; then re, im of conj(U_ki) U_kj, i < j) | 1 / l_j [R]
 template <int R> struct LrTab {
@@ -63,7 +62,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
     mmse_lowrank_kernel(const T *__restrict__ tab_g, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx, int64_t stride,
                         const T *__restrict__ sigma2, cx<T> *__restrict__ H, int64_t n, int aligned16)
 {
-    constexpr int SW = LrSlab<T>::W, NB = LrBatch<T, R>::N, UNR = LrUnroll<T, R>::N, NP = R * (R - 1) / 2;
+    constexpr int SW = LrSlab<T>::W, UNR = LrUnroll<T, R>::N, NP = R * (R - 1) / 2;
     using TB = LrTab<R>;
     extern __shared__ __align__(16) unsigned char lr_smem[];
     T *tab = reinterpret_cast<T *>(lr_smem);
@@ -74,12 +73,13 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
     __syncthreads();
 
     const int64_t n_chunks = (n + 31) / 32, cstep = (int64_t)gridDim.x * LR_WARPS;
-    const bool dense = stride == NSC && aligned16;
+    const bool dense = stride == NSC && (aligned16 & 1), out16 = (aligned16 & 2) != 0;
     constexpr uint32_t CHUNK_BYTES = 32 * NSC * sizeof(cx<T>);
     // chunks are dealt so that the whole grid sweeps HBM as one moving window: (round * gridDim + block) * 8 + warp
     for (int64_t chunk = (int64_t)blockIdx.x * LR_WARPS + warp; chunk < n_chunks; chunk += cstep) {
         const int64_t f0 = chunk * 32;
         const int valid = (int)min((int64_t)32, n - f0);
+        const bool fast = dense && valid == 32, fast_out = out16 && valid == 32;
         {
             const int64_t fn = (chunk + cstep) * 32;
             if (dense && lane == 0 && fn + 32 <= n) { lr_l2_prefetch(tx + fn * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fn * NSC, CHUNK_BYTES); }
@@ -93,32 +93,61 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
 #pragma unroll
         for (int s0 = 0; s0 < NSC; s0 += SW) {
             const int kw = NSC - s0 < SW ? NSC - s0 : SW;                  // compile-time after unrolling
-            const int total = 32 * kw;
             // ---- a. element-wise, coalesced: a = conj(x) rx, m = |x|^2 -> tile ----
-#pragma unroll 1
-            for (int base = lane; base < total; base += 32 * NB) {
-                cx<T> xv[NB], rv[NB];
+            if (sizeof(T) == 4 && fast) {
+                // FP32, dense 16-byte aligned rows, whole chunk: the chunk is one contiguous run of 848 float4 (two bins each); tile index =
+                // element index, no address arithmetic.  Four batches of 7 vectors per array in flight.
+                if constexpr (sizeof(T) == 4) {
+                    const float4 *px = reinterpret_cast<const float4 *>(tx + f0 * NSC) + lane, *pr = reinterpret_cast<const float4 *>(rx + f0 * NSC) + lane;
+                    float4 *A4 = reinterpret_cast<float4 *>(A) + lane;
+                    float2 *M2 = reinterpret_cast<float2 *>(M) + lane;
+                    constexpr int VB = 7;
+                    float4 xv[2][VB], rv[2][VB];
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int idx = base + 32 * j;
-                    xv[j] = rv[j] = mk<T>((T)0, (T)0);
-                    if (idx < total) {
-                        const int fr = idx / kw, kk = idx - fr * kw;
-                        if (fr < valid) {
-                            const int64_t off = (f0 + fr) * stride + s0 + kk;
-                            xv[j] = ld_stream(tx + off);
-                            rv[j] = ld_stream(rx + off);
+                    for (int j = 0; j < VB; ++j) { xv[0][j] = ld_stream(px + 32 * j); rv[0][j] = ld_stream(pr + 32 * j); }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (b < 3) {
+#pragma unroll
+                            for (int j = 0; j < VB; ++j) {
+                                const int i = (b + 1) * VB + j;
+                                if (i < 26 || (i == 26 && lane < 16)) { xv[(b + 1) & 1][j] = ld_stream(px + 32 * i); rv[(b + 1) & 1][j] = ld_stream(pr + 32 * i); }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < VB; ++j) {
+                            const int i = b * VB + j;
+                            if (i < 26 || (i == 26 && lane < 16)) {
+                                const float4 x = xv[b & 1][j], r = rv[b & 1][j];
+                                A4[32 * i] = make_float4(fmaf(x.x, r.x, x.y * r.y), fmaf(x.x, r.y, -(x.y * r.x)), fmaf(x.z, r.z, x.w * r.w), fmaf(x.z, r.w, -(x.w * r.z)));
+                                M2[32 * i] = make_float2(fmaf(x.x, x.x, x.y * x.y), fmaf(x.z, x.z, x.w * x.w));
+                            }
                         }
                     }
                 }
+            } else {
+                // row by row (FP64; strided, unaligned or ragged FP32): lane kk takes bin s0 + kk of the row, RB rows in flight
+                constexpr int RB = 8;
+#pragma unroll 1
+                for (int fr0 = 0; fr0 < 32; fr0 += RB) {
+#pragma unroll 1
+                    for (int kk = lane; kk < kw; kk += 32) {
+                        cx<T> xv[RB], rv[RB];
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int idx = base + 32 * j;
-                    if (idx < total) {
-                        const int fr = idx / kw, kk = idx - fr * kw;
-                        const cx<T> x = xv[j], r = rv[j];
-                        A[fr * SW + kk] = mk<T>(fma(x.x, r.x, x.y * r.y), fma(x.x, r.y, -(x.y * r.x)));
-                        M[fr * SW + kk] = fma(x.x, x.x, x.y * x.y);
+                        for (int j = 0; j < RB; ++j) {
+                            xv[j] = rv[j] = mk<T>((T)0, (T)0);
+                            if (fr0 + j < valid) {
+                                const int64_t off = (f0 + fr0 + j) * stride + s0 + kk;
+                                xv[j] = ld_stream(tx + off);
+                                rv[j] = ld_stream(rx + off);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < RB; ++j) {
+                            const cx<T> x = xv[j], r = rv[j];
+                            A[(fr0 + j) * SW + kk] = mk<T>(fma(x.x, r.x, x.y * r.y), fma(x.x, r.y, -(x.y * r.x)));
+                            M[(fr0 + j) * SW + kk] = fma(x.x, x.x, x.y * x.y);
+                        }
                     }
                 }
             }
@@ -189,7 +218,6 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
 #pragma unroll
         for (int s0 = 0; s0 < NSC; s0 += SW) {
             const int kw = NSC - s0 < SW ? NSC - s0 : SW;
-            const int total = 32 * kw;
             cx<T> *Ar = A + lane * SW;
 #pragma unroll 2
             for (int kk = 0; kk < kw; ++kk) {
@@ -204,9 +232,18 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
                 Ar[kk] = mk<T>(hr, hi);
             }
             __syncwarp();
-            for (int idx = lane; idx < total; idx += 32) {
-                const int fr = idx / kw, kk = idx - fr * kw;
-                if (fr < valid) st_stream(H + (f0 + fr) * NSC + s0 + kk, A[fr * SW + kk]);
+            if (sizeof(T) == 4 && fast_out) {
+                if constexpr (sizeof(T) == 4) {
+                    const float4 *A4 = reinterpret_cast<const float4 *>(A) + lane;
+                    float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC) + lane;
+#pragma unroll 9
+                    for (int i = 0; i < 27; ++i)
+                        if (i < 26 || lane < 16) st_stream(po + 32 * i, A4[32 * i]);
+                }
+            } else {
+#pragma unroll 4
+                for (int fr = 0; fr < valid; ++fr)
+                    for (int kk = lane; kk < kw; kk += 32) st_stream(H + (f0 + fr) * NSC + s0 + kk, A[fr * SW + kk]);
             }
             __syncwarp();
         }
@@ -227,7 +264,7 @@ static cudaError_t launch_lr(const void *tab, const void *tx, const void *rx, in
     if (e != cudaSuccess) return e;
     const int64_t n_chunks = (n + 31) / 32;
     const unsigned grid = (unsigned)std::min<int64_t>((n_chunks + LR_WARPS - 1) / LR_WARPS, 148);
-    const int aligned16 = ((((uintptr_t)tx) | ((uintptr_t)rx)) & 15) == 0;
+    const int aligned16 = (((((uintptr_t)tx) | ((uintptr_t)rx)) & 15) == 0 ? 1 : 0) | ((((uintptr_t)H) & 15) == 0 ? 2 : 0);
     kern<<<grid, LR_WARPS * 32, smem, s>>>((const T *)tab, (const cx<T> *)tx, (const cx<T> *)rx, stride, (const T *)sigma2, (cx<T> *)H, n, aligned16);
     return cudaGetLastError();
 }

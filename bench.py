@@ -347,6 +347,14 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
                *((37.2, mp["fp64_dmma_tflops"]) if prec == "f64" else (None, None)), config="configs[3]",
                note="per-frame sigma2 for frames that share |tx_k|^2: two shared 53x53 complex products (2 x 22 472 flop) + a per-frame scaling "
                     "instead of the 4.4e5-flop solve; hbm_frac is on the algorithmic 159 c + sigma2 per frame")
+        # low-rank per-frame MMSE (wifi_lowrank.cu): the synthetic covariance has rank 4 (4 channel taps), sigma2 per frame; one launch
+        rk = ctx.mmse_lowrank_prepare(R)
+        X.rate("mmse_perframe_lowrank_" + prec, lambda: ctx.mmse_perframe_lowrank(tx0, rx0, s2n, out=He), n, 159 * cbytes + cbytes // 2, 5874,
+               *((74.4, mp["fp32_fma_tflops"]) if prec == "f32" else (37.2, mp["fp64_fma_tflops"])), config="configs[3]", rank=rk,
+               arithmetic="FP32" if prec == "f32" else "FP64",
+               note="per-frame sigma2 (and per-frame |tx_k|^2) for a covariance of rank r <= 8: H = U (sigma2 L^-1 + U^H diag(|x|^2) U)^-1 U^H (conj(x) rx), "
+                    "an r x r solve per frame in registers, ONE launch on the frame's own 159 c + sigma2; flops at r = 4: 53 x (16 + 16 + 6) x 2 + 53 x 16 x 2 "
+                    "+ ~150 for the 4 x 4 solve = 5 874 (the 53 x 53 solve: 441 949)")
         del He
         if full:
             # receiver front-end: 15 x 64 packet samples + 128 lptot samples in, 15 x 53 + 53 values + ow2 out
@@ -390,6 +398,7 @@ def extras_block(wifi, ctx, torch, dist, world, shard_lo, peaks, mp, n_frames, s
     out = X.finish()
     for prec in ("f32", "f64"):
         out["mmse_perframe_eig_" + prec]["speedup_vs_direct_solve"] = out["mmse_perframe_eig_" + prec]["frames_per_s"] / out["mmse_perframe_hpd_" + prec]["frames_per_s"]
+        out["mmse_perframe_lowrank_" + prec]["speedup_vs_direct_solve"] = out["mmse_perframe_lowrank_" + prec]["frames_per_s"] / out["mmse_perframe_hpd_" + prec]["frames_per_s"]
     return out
 
 

@@ -34,6 +34,9 @@ def main():
             if want("eig") and rep == 0:
                 ctx.mmse_eig_prepare(R, (tx0[0].abs().to(torch.float64)) ** 2)
             if want("eig"): ctx.mmse_perframe_eig(tx0, rx0, fr["sigma2"], out=H)
+            if want("lowrank") and rep == 0:
+                ctx.mmse_lowrank_prepare(R)
+            if want("lowrank"): ctx.mmse_perframe_lowrank(tx0, rx0, fr["sigma2"], out=H)
             if want("rank1"): ctx.mmse_cconv(tx0, rx0, fr["sigma2"], outs["linear"], out=H)
             if want("frontend") and rep == 0:
                 m = 1 << 17
