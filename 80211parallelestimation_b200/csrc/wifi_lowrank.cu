@@ -30,10 +30,11 @@
 
 namespace wifi {
 
-constexpr int LR_WARPS = 8;
+// warps per CTA (one CTA per SM): as many 20 KB tiles as fit next to the tables
+template <typename T, int R> struct LrWarps { static constexpr int N = (sizeof(T) == 8 && R <= 4) ? 10 : 8; };
 template <typename T> struct LrSlab { static constexpr int W = sizeof(T) == 4 ? NSC : 27; };     // bins staged at a time
-template <typename T, int R> struct LrUnroll { static constexpr int N = (sizeof(T) == 8 && R > 4) ? 1 : 2; };     // bins per trip of the accumulation loop (registers)
-// tables (in T): U[53][2 R] (re, im of U_kj) | P[53][R R] (|U_ki|^2, i < R; then re, im of conj(U_ki) U_kj, i < j) | 1 / l_j [R]
+template <typename T, int R> struct LrUnroll { static constexpr int N = (sizeof(T) == 8 && R > 4) ? 1 : (sizeof(T) == 4 && R <= 4 ? 4 : 2); };     // bins per trip of the accumulation loop (registers)
+// tables (in T): U[53][2 R] (re of U_kj, j < R; then im: planar, so that FP32 pairs over j are adjacent) | P[53][R R] (|U_ki|^2, i < R; then re, im of conj(U_ki) U_kj, i < j) | 1 / l_j [R]
 template <int R> struct LrTab {
     static constexpr int U = 0, P = NSC * 2 * R, L = P + NSC * R * R, SIZE = (L + R + 3) & ~3;
 };
@@ -52,17 +53,29 @@ template <typename T, int N> __device__ __forceinline__ void lr_load(const T *p,
     }
 }
 
+// Packed FP32 pairs (FFMA2 on sm_100a: one issue slot for two FMAs -- this kernel is issue-bound, not FMA-pipe-bound)
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+template <int N> __device__ __forceinline__ void lr_load2(const float *p, f32x2 (&v)[N])          // N pairs = N / 2 16-byte vectors
+{
+    static_assert(N % 2 == 0, "whole 16-byte vectors");
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) { const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(p)[q]; v[2 * q] = w.x; v[2 * q + 1] = w.y; }
+}
+
 __device__ __forceinline__ void lr_l2_prefetch(const void *p, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 template <typename T, int R>
-__global__ void __launch_bounds__(LR_WARPS * 32, 1)
+__global__ void __launch_bounds__(LrWarps<T, R>::N * 32, 1)
     mmse_lowrank_kernel(const T *__restrict__ tab_g, const cx<T> *__restrict__ tx, const cx<T> *__restrict__ rx, int64_t stride,
                         const T *__restrict__ sigma2, cx<T> *__restrict__ H, int64_t n, int aligned16)
 {
-    constexpr int SW = LrSlab<T>::W, UNR = LrUnroll<T, R>::N, NP = R * (R - 1) / 2;
+    constexpr int LR_WARPS = LrWarps<T, R>::N, SW = LrSlab<T>::W, UNR = LrUnroll<T, R>::N, NP = R * (R - 1) / 2;
     using TB = LrTab<R>;
     extern __shared__ __align__(16) unsigned char lr_smem[];
     T *tab = reinterpret_cast<T *>(lr_smem);
@@ -80,23 +93,33 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
         const int64_t f0 = chunk * 32;
         const int valid = (int)min((int64_t)32, n - f0);
         const bool fast = dense && valid == 32, fast_out = out16 && valid == 32;
-        {
-            const int64_t fn = (chunk + cstep) * 32;
-            if (dense && lane == 0 && fn + 32 <= n) { lr_l2_prefetch(tx + fn * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fn * NSC, CHUNK_BYTES); }
-        }
+        // L2 prefetch, one slab ahead (a warp never has more than ~27 KB outstanding: 148 x 10 warps x 27 KB = 40 MB of the 126 MB L2; a
+        // whole FP64 chunk ahead -- 64 MB -- was evicted before use: ncu 3.22 GB read for 1.78 GB): lane r asks for row r's piece
+        auto prefetch_slab = [&](int64_t fb, int s0, int kw) {
+            if (!dense || fb + 32 > n) return;
+            if (SW == NSC) { if (lane == 0) { lr_l2_prefetch(tx + fb * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fb * NSC, CHUNK_BYTES); } }
+            else { lr_l2_prefetch(tx + (fb + lane) * NSC + s0, kw * (uint32_t)sizeof(cx<T>)); lr_l2_prefetch(rx + (fb + lane) * NSC + s0, kw * (uint32_t)sizeof(cx<T>)); }
+        };
         T tr[R], ti[R], gd[R], gor[NP > 0 ? NP : 1], goi[NP > 0 ? NP : 1];
 #pragma unroll
         for (int j = 0; j < R; ++j) tr[j] = ti[j] = gd[j] = (T)0;
 #pragma unroll
         for (int q = 0; q < NP; ++q) gor[q] = goi[q] = (T)0;
+        f32x2 trp[R / 2], tip[R / 2], gdp[R / 2], gop[NP];             // FP32: the same accumulators as packed pairs
+#pragma unroll
+        for (int h = 0; h < R / 2; ++h) trp[h] = tip[h] = gdp[h] = 0ull;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) gop[q] = 0ull;
 
 #pragma unroll
         for (int s0 = 0; s0 < NSC; s0 += SW) {
             const int kw = NSC - s0 < SW ? NSC - s0 : SW;                  // compile-time after unrolling
+            if (s0 + SW < NSC) prefetch_slab(f0, s0 + SW, NSC - s0 - SW < SW ? NSC - s0 - SW : SW);
+            else if (SW == NSC) prefetch_slab((chunk + cstep) * 32, 0, SW);
             // ---- a. element-wise, coalesced: a = conj(x) rx, m = |x|^2 -> tile ----
             if (sizeof(T) == 4 && fast) {
                 // FP32, dense 16-byte aligned rows, whole chunk: the chunk is one contiguous run of 848 float4 (two bins each); tile index =
-                // element index, no address arithmetic.  Four batches of 7 vectors per array in flight.
+                // element index, no address arithmetic.  Four batches of 7 vectors per array, two in flight.
                 if constexpr (sizeof(T) == 4) {
                     const float4 *px = reinterpret_cast<const float4 *>(tx + f0 * NSC) + lane, *pr = reinterpret_cast<const float4 *>(rx + f0 * NSC) + lane;
                     float4 *A4 = reinterpret_cast<float4 *>(A) + lane;
@@ -155,26 +178,53 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
             // ---- b. lane = frame: t += conj(U_k) a_k,  G += m_k P_k ----
             const cx<T> *Ar = A + lane * SW;
             const T *Mr = M + lane * SW;
+            if constexpr (sizeof(T) == 4) {
+                // FP32: pairs over j (t) and (re, im) pairs (G) as FFMA2 -- 16 instead of 32 FMA instructions per bin
 #pragma unroll UNR
-            for (int kk = 0; kk < kw; ++kk) {
-                const cx<T> a = Ar[kk];
-                const T m = Mr[kk];
-                T u[2 * R], p[R * R];
-                lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
-                lr_load<T, R * R>(tab + TB::P + (s0 + kk) * R * R, p);
+                for (int kk = 0; kk < kw; ++kk) {
+                    const float2 a = Ar[kk];
+                    const float m = Mr[kk];
+                    f32x2 u[R], p[R * R / 2];
+                    lr_load2<R>(tab + TB::U + (s0 + kk) * 2 * R, u);               // u[0 .. R/2) = re pairs, u[R/2 .. R) = im pairs
+                    lr_load2<R * R / 2>(tab + TB::P + (s0 + kk) * R * R, p);
+                    const f32x2 axx = pack2(a.x, a.x), ayy = pack2(a.y, a.y), nax = pack2(-a.x, -a.x), mm = pack2(m, m);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    tr[j] = fma(u[2 * j], a.x, tr[j]); tr[j] = fma(u[2 * j + 1], a.y, tr[j]);
-                    ti[j] = fma(u[2 * j], a.y, ti[j]); ti[j] = fma(-u[2 * j + 1], a.x, ti[j]);
-                    gd[j] = fma(m, p[j], gd[j]);
+                    for (int h = 0; h < R / 2; ++h) {
+                        trp[h] = ffma2(u[h], axx, trp[h]); trp[h] = ffma2(u[R / 2 + h], ayy, trp[h]);
+                        tip[h] = ffma2(u[h], ayy, tip[h]); tip[h] = ffma2(u[R / 2 + h], nax, tip[h]);
+                        gdp[h] = ffma2(mm, p[h], gdp[h]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) gop[q] = ffma2(mm, p[R / 2 + q], gop[q]);
                 }
+            } else {
+#pragma unroll UNR
+                for (int kk = 0; kk < kw; ++kk) {
+                    const cx<T> a = Ar[kk];
+                    const T m = Mr[kk];
+                    T u[2 * R], p[R * R];
+                    lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
+                    lr_load<T, R * R>(tab + TB::P + (s0 + kk) * R * R, p);
 #pragma unroll
-                for (int q = 0; q < NP; ++q) { gor[q] = fma(m, p[R + 2 * q], gor[q]); goi[q] = fma(m, p[R + 2 * q + 1], goi[q]); }
+                    for (int j = 0; j < R; ++j) {
+                        tr[j] = fma(u[j], a.x, tr[j]); tr[j] = fma(u[R + j], a.y, tr[j]);
+                        ti[j] = fma(u[j], a.y, ti[j]); ti[j] = fma(-u[R + j], a.x, ti[j]);
+                        gd[j] = fma(m, p[j], gd[j]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) { gor[q] = fma(m, p[R + 2 * q], gor[q]); goi[q] = fma(m, p[R + 2 * q + 1], goi[q]); }
+                }
             }
             __syncwarp();
         }
 
         // ---- c. S = G + sigma2 / l on the diagonal;  S w = t by Hermitian elimination (upper triangle stored), back-substitution ----
+        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int h = 0; h < R / 2; ++h) { unpack2(trp[h], tr[2 * h], tr[2 * h + 1]); unpack2(tip[h], ti[2 * h], ti[2 * h + 1]); unpack2(gdp[h], gd[2 * h], gd[2 * h + 1]); }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) unpack2(gop[q], gor[q], goi[q]);
+        }
         {
             const T s2 = lane < valid ? sigma2[f0 + lane] : (T)1;
             T dinv[R];
@@ -215,21 +265,44 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
         }
 
         // ---- d. H = U w through the tile, coalesced streaming store ----
+        if (SW < NSC) prefetch_slab((chunk + cstep) * 32, 0, SW);
 #pragma unroll
         for (int s0 = 0; s0 < NSC; s0 += SW) {
             const int kw = NSC - s0 < SW ? NSC - s0 : SW;
             cx<T> *Ar = A + lane * SW;
-#pragma unroll 2
-            for (int kk = 0; kk < kw; ++kk) {
-                T u[2 * R];
-                lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
-                T hr = (T)0, hi = (T)0;
+            if constexpr (sizeof(T) == 4) {
+                f32x2 wr2[R / 2], wi2[R / 2], nwi2[R / 2];
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    hr = fma(u[2 * j], tr[j], hr); hr = fma(-u[2 * j + 1], ti[j], hr);
-                    hi = fma(u[2 * j], ti[j], hi); hi = fma(u[2 * j + 1], tr[j], hi);
+                for (int h = 0; h < R / 2; ++h) {
+                    wr2[h] = pack2(tr[2 * h], tr[2 * h + 1]); wi2[h] = pack2(ti[2 * h], ti[2 * h + 1]); nwi2[h] = pack2(-ti[2 * h], -ti[2 * h + 1]);
                 }
-                Ar[kk] = mk<T>(hr, hi);
+#pragma unroll 4
+                for (int kk = 0; kk < kw; ++kk) {
+                    f32x2 u[R];
+                    lr_load2<R>(tab + TB::U + (s0 + kk) * 2 * R, u);
+                    f32x2 hr2 = 0ull, hi2 = 0ull;                                  // partial sums over even / odd j
+#pragma unroll
+                    for (int h = 0; h < R / 2; ++h) {
+                        hr2 = ffma2(u[h], wr2[h], hr2); hr2 = ffma2(u[R / 2 + h], nwi2[h], hr2);
+                        hi2 = ffma2(u[h], wi2[h], hi2); hi2 = ffma2(u[R / 2 + h], wr2[h], hi2);
+                    }
+                    float r0, r1, i0, i1;
+                    unpack2(hr2, r0, r1); unpack2(hi2, i0, i1);
+                    Ar[kk] = make_float2(r0 + r1, i0 + i1);
+                }
+            } else {
+#pragma unroll 2
+                for (int kk = 0; kk < kw; ++kk) {
+                    T u[2 * R];
+                    lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
+                    T hr = (T)0, hi = (T)0;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        hr = fma(u[j], tr[j], hr); hr = fma(-u[R + j], ti[j], hr);
+                        hi = fma(u[j], ti[j], hi); hi = fma(u[R + j], tr[j], hi);
+                    }
+                    Ar[kk] = mk<T>(hr, hi);
+                }
             }
             __syncwarp();
             if (sizeof(T) == 4 && fast_out) {
@@ -252,7 +325,7 @@ __global__ void __launch_bounds__(LR_WARPS * 32, 1)
 
 template <typename T, int R> static size_t lr_smem_bytes()
 {
-    return sizeof(T) * LrTab<R>::SIZE + (size_t)LR_WARPS * 32 * LrSlab<T>::W * (sizeof(cx<T>) + sizeof(T));
+    return sizeof(T) * LrTab<R>::SIZE + (size_t)LrWarps<T, R>::N * 32 * LrSlab<T>::W * (sizeof(cx<T>) + sizeof(T));
 }
 
 template <typename T, int R>
@@ -263,6 +336,7 @@ static cudaError_t launch_lr(const void *tab, const void *tx, const void *rx, in
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t n_chunks = (n + 31) / 32;
+    constexpr int LR_WARPS = LrWarps<T, R>::N;
     const unsigned grid = (unsigned)std::min<int64_t>((n_chunks + LR_WARPS - 1) / LR_WARPS, 148);
     const int aligned16 = (((((uintptr_t)tx) | ((uintptr_t)rx)) & 15) == 0 ? 1 : 0) | ((((uintptr_t)H) & 15) == 0 ? 2 : 0);
     kern<<<grid, LR_WARPS * 32, smem, s>>>((const T *)tab, (const cx<T> *)tx, (const cx<T> *)rx, stride, (const T *)sigma2, (cx<T> *)H, n, aligned16);
@@ -299,7 +373,7 @@ int lowrank_build_tables(const double *V /* re, im interleaved */, const double 
         double ur[8] = {0}, ui[8] = {0};
         for (int j = 0; j < r; ++j) { ur[j] = V[2 * (k * NSC + idx[j])]; ui[j] = V[2 * (k * NSC + idx[j]) + 1]; }
         double *U = &t64[offU + k * 2 * R], *P = &t64[offP + k * R * R];
-        for (int j = 0; j < R; ++j) { U[2 * j] = ur[j]; U[2 * j + 1] = ui[j]; P[j] = ur[j] * ur[j] + ui[j] * ui[j]; }
+        for (int j = 0; j < R; ++j) { U[j] = ur[j]; U[R + j] = ui[j]; P[j] = ur[j] * ur[j] + ui[j] * ui[j]; }
         for (int i = 0; i < R; ++i)
             for (int j = i + 1; j < R; ++j) {                       // conj(U_ki) U_kj
                 const int q = lr_pair(R, i, j);
