@@ -291,17 +291,18 @@ __global__ void __launch_bounds__(LrWarps<T, R>::N * 32, 1)
                     Ar[kk] = make_float2(r0 + r1, i0 + i1);
                 }
             } else {
+                // four independent chains per bin (the FP64 pipe's dependent-issue latency was the top 'wait' stall with two)
 #pragma unroll 2
                 for (int kk = 0; kk < kw; ++kk) {
                     T u[2 * R];
                     lr_load<T, 2 * R>(tab + TB::U + (s0 + kk) * 2 * R, u);
-                    T hr = (T)0, hi = (T)0;
+                    T hra = (T)0, hrb = (T)0, hia = (T)0, hib = (T)0;
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        hr = fma(u[j], tr[j], hr); hr = fma(-u[R + j], ti[j], hr);
-                        hi = fma(u[j], ti[j], hi); hi = fma(u[R + j], tr[j], hi);
+                        hra = fma(u[j], tr[j], hra); hrb = fma(-u[R + j], ti[j], hrb);
+                        hia = fma(u[j], ti[j], hia); hib = fma(u[R + j], tr[j], hib);
                     }
-                    Ar[kk] = mk<T>(hr, hi);
+                    Ar[kk] = mk<T>(hra + hrb, hia + hib);
                 }
             }
             __syncwarp();
