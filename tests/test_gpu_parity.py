@@ -610,6 +610,9 @@ def test_mmse_perframe_lowrank(ctx, oracle, prec, tol, qam, taps, n):
         g2 = host(ctx.mmse_perframe_lowrank(dev(fr["tx_symb"]).reshape(-1), dev(fr["rx_symb"]).reshape(-1), dev(s2), frame_stride=15 * NSC, n_frames=n))
         assert np.array_equal(g2, got)
         assert np.array_equal(ctx.mmse_perframe_lowrank(tx, rx, s2), got)
+        # views that start at frame 1: 8-byte aligned only (424-byte rows), 299 frames -> the row-wise path and a ragged last chunk
+        g4 = host(ctx.mmse_perframe_lowrank(dev(tx)[1:], dev(rx)[1:], dev(s2)[1:]))
+        assert rel_err(g4, got[1:]) < (1e-13 if prec == "f64" else 2e-6)
         if prec == "f64":                                              # the 53 x 53 device solve on the same frames: two algorithms, one estimator
             assert rel_err(got, host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2)))) < 1e-9
 
