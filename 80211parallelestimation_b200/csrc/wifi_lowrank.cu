@@ -103,45 +103,51 @@ __device__ __forceinline__ void lr_solve(T (&tr)[R], T (&ti)[R], T (&gd)[R], T (
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// FP32: 8 warps, chunk = 32 frames, lane = frame
-constexpr int LR32_WARPS = 8;
-constexpr int LR32_TILE = 32 * NSC;                 // complex values (a) and reals (m) per warp tile
+// Both kernels: chunk = 16 frames, lane = (frame f = lane & 15, half h = lane >> 4 of the bins: h = 0 -> bins 0..26, h = 1 -> bins
+// 27..52).  The tile holds 16 x 53 values (a: complex, m: real), the chunk is ONE contiguous run of 16-byte vectors in HBM and
+// staging is index-free; the two halves of a frame meet in one __shfl_xor(16) step per accumulator.  A 10 KB (FP32) / 20 KB (FP64)
+// tile per warp puts 16 / 10 warps on an SM.
+constexpr int LR_FR = 16, LR_TILE = LR_FR * NSC, LR_HB = 27;
+
+// FP32: 16 warps at rank <= 4 (128 registers), 12 beyond (168)
+template <int R> struct Lr32Warps { static constexpr int N = R <= 4 ? 16 : 12; };
 
 template <int R>
-__global__ void __launch_bounds__(LR32_WARPS * 32, 1)
+__global__ void __launch_bounds__(Lr32Warps<R>::N * 32, 1)
     mmse_lowrank_f32_kernel(const float *__restrict__ tab_g, const float2 *__restrict__ tx, const float2 *__restrict__ rx, int64_t stride,
                             const float *__restrict__ sigma2, float2 *__restrict__ H, int64_t n, int aligned16)
 {
-    constexpr int NP = R * (R - 1) / 2, UNR = R <= 4 ? 4 : 2;
+    constexpr int NP = R * (R - 1) / 2, UNR = 2, LR32_WARPS = Lr32Warps<R>::N;
     using TB = LrTab<R>;
     extern __shared__ __align__(16) unsigned char lr_smem[];
     float *tab = reinterpret_cast<float *>(lr_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 *A = reinterpret_cast<float2 *>(tab + TB::SIZE) + warp * LR32_TILE;                         // this warp's tile: a, later H
-    float *M = reinterpret_cast<float *>(reinterpret_cast<float2 *>(tab + TB::SIZE) + LR32_WARPS * LR32_TILE) + warp * LR32_TILE;
+    float2 *A = reinterpret_cast<float2 *>(tab + TB::SIZE) + warp * LR_TILE;                           // this warp's tile: a, later H
+    float *M = reinterpret_cast<float *>(reinterpret_cast<float2 *>(tab + TB::SIZE) + LR32_WARPS * LR_TILE) + warp * LR_TILE;
     for (int e = threadIdx.x; e < TB::SIZE; e += LR32_WARPS * 32) tab[e] = tab_g[e];
     __syncthreads();
 
-    const int64_t n_chunks = (n + 31) / 32, cstep = (int64_t)gridDim.x * LR32_WARPS;
+    const int64_t n_chunks = (n + LR_FR - 1) / LR_FR, cstep = (int64_t)gridDim.x * LR32_WARPS;
     const bool dense = stride == NSC && (aligned16 & 1), out16 = (aligned16 & 2) != 0;
-    constexpr uint32_t CHUNK_BYTES = 32 * NSC * sizeof(float2);
-    // chunks are dealt so that the whole grid sweeps HBM as one moving window: (round * gridDim + block) * 8 + warp
+    constexpr uint32_t CHUNK_BYTES = LR_TILE * sizeof(float2);
+    const int f = lane & 15, hb = lane >> 4, k0 = hb * LR_HB, nb = hb ? NSC - LR_HB : LR_HB;
+    // chunks are dealt so that the whole grid sweeps HBM as one moving window: (round * gridDim + block) * warps + warp
     for (int64_t chunk = (int64_t)blockIdx.x * LR32_WARPS + warp; chunk < n_chunks; chunk += cstep) {
-        const int64_t f0 = chunk * 32;
-        const int valid = (int)min((int64_t)32, n - f0);
-        const bool fast = dense && valid == 32, fast_out = out16 && valid == 32;
+        const int64_t f0 = chunk * LR_FR;
+        const int valid = (int)min((int64_t)LR_FR, n - f0);
+        const bool fast = dense && valid == LR_FR, fast_out = out16 && valid == LR_FR;
         {
-            const int64_t fn = (chunk + cstep) * 32;
-            if (dense && lane == 0 && fn + 32 <= n) { lr_l2_prefetch(tx + fn * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fn * NSC, CHUNK_BYTES); }
+            const int64_t fn = (chunk + cstep) * LR_FR;
+            if (dense && lane == 0 && fn + LR_FR <= n) { lr_l2_prefetch(tx + fn * NSC, CHUNK_BYTES); lr_l2_prefetch(rx + fn * NSC, CHUNK_BYTES); }
         }
         // ---- a. element-wise, coalesced: a = conj(x) rx, m = |x|^2 -> tile ----
         if (fast) {
-            // dense 16-byte aligned rows, whole chunk: one contiguous run of 848 float4 (two bins each); tile index = element index,
-            // no address arithmetic.  Four batches of 7 vectors per array, two in flight.
+            // dense 16-byte aligned rows, whole chunk: one contiguous run of 424 float4 (two bins each); tile index = element index,
+            // no address arithmetic.  Four batches of 4 vectors per array, two in flight.
             const float4 *px = reinterpret_cast<const float4 *>(tx + f0 * NSC) + lane, *pr = reinterpret_cast<const float4 *>(rx + f0 * NSC) + lane;
             float4 *A4 = reinterpret_cast<float4 *>(A) + lane;
             float2 *M2 = reinterpret_cast<float2 *>(M) + lane;
-            constexpr int VB = 7;
+            constexpr int VB = 4;
             float4 xv[2][VB], rv[2][VB];
 #pragma unroll
             for (int j = 0; j < VB; ++j) { xv[0][j] = ld_stream(px + 32 * j); rv[0][j] = ld_stream(pr + 32 * j); }
@@ -151,13 +157,13 @@ __global__ void __launch_bounds__(LR32_WARPS * 32, 1)
 #pragma unroll
                     for (int j = 0; j < VB; ++j) {
                         const int i = (b + 1) * VB + j;
-                        if (i < 26 || (i == 26 && lane < 16)) { xv[(b + 1) & 1][j] = ld_stream(px + 32 * i); rv[(b + 1) & 1][j] = ld_stream(pr + 32 * i); }
+                        if (i < 13 || (i == 13 && lane < 8)) { xv[(b + 1) & 1][j] = ld_stream(px + 32 * i); rv[(b + 1) & 1][j] = ld_stream(pr + 32 * i); }
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < VB; ++j) {
                     const int i = b * VB + j;
-                    if (i < 26 || (i == 26 && lane < 16)) {
+                    if (i < 13 || (i == 13 && lane < 8)) {
                         const float4 x = xv[b & 1][j], r = rv[b & 1][j];
                         A4[32 * i] = make_float4(fmaf(x.x, r.x, x.y * r.y), fmaf(x.x, r.y, -(x.y * r.x)), fmaf(x.z, r.z, x.w * r.w), fmaf(x.z, r.w, -(x.w * r.z)));
                         M2[32 * i] = make_float2(fmaf(x.x, x.x, x.y * x.y), fmaf(x.z, x.z, x.w * x.w));
@@ -165,10 +171,10 @@ __global__ void __launch_bounds__(LR32_WARPS * 32, 1)
                 }
             }
         } else {
-            // row by row (strided, 8-byte aligned or ragged): lane kk takes bins kk and kk + 32 of the row, 8 rows in flight
-            constexpr int RB = 8;
+            // row by row (strided, 8-byte aligned or ragged): lane kk takes bins kk and kk + 32 of the row, 4 rows in flight
+            constexpr int RB = 4;
 #pragma unroll 1
-            for (int fr0 = 0; fr0 < 32; fr0 += RB) {
+            for (int fr0 = 0; fr0 < LR_FR; fr0 += RB) {
 #pragma unroll 1
                 for (int kk = lane; kk < NSC; kk += 32) {
                     float2 xv[RB], rv[RB];
@@ -191,22 +197,26 @@ __global__ void __launch_bounds__(LR32_WARPS * 32, 1)
             }
         }
         __syncwarp();
-        // ---- b. lane = frame: t += conj(U_k) a_k, G += m_k P_k as FFMA2: pairs over j (t) and (re, im) pairs (G) -- 16 instead of 32
-        //         FMA instructions per bin ----
+        // ---- b. lane = (frame, half): t += conj(U_k) a_k, G += m_k P_k over this half's bins as FFMA2 -- pairs over j (t) and
+        //         (re, im) pairs (G): 16 instead of 32 FMA instructions per bin ----
         f32x2 trp[R / 2], tip[R / 2], gdp[R / 2], gop[NP];
 #pragma unroll
         for (int h = 0; h < R / 2; ++h) trp[h] = tip[h] = gdp[h] = 0ull;
 #pragma unroll
         for (int q = 0; q < NP; ++q) gop[q] = 0ull;
-        float2 *Ar = A + lane * NSC;
-        const float *Mr = M + lane * NSC;
+        float2 *Ar = A + f * NSC + k0;
+        const float *Mr = M + f * NSC + k0;
+        const float *Uh = tab + TB::U + k0 * 2 * R, *Ph = tab + TB::P + k0 * R * R;
 #pragma unroll UNR
-        for (int kk = 0; kk < NSC; ++kk) {
-            const float2 a = Ar[kk];
-            const float m = Mr[kk];
+        for (int kk = 0; kk < LR_HB; ++kk) {
+            const bool on = kk < nb;                                           // the upper half has 26 bins
+            const int kc = on ? kk : 0;
+            float2 a = Ar[kc];
+            float m = Mr[kc];
+            if (!on) { a = make_float2(0.f, 0.f); m = 0.f; }
             f32x2 u[R], p[R * R / 2];
-            lr_load2<R>(tab + TB::U + kk * 2 * R, u);                              // u[0 .. R/2) = re pairs, u[R/2 .. R) = im pairs
-            lr_load2<R * R / 2>(tab + TB::P + kk * R * R, p);
+            lr_load2<R>(Uh + kc * 2 * R, u);                                   // u[0 .. R/2) = re pairs, u[R/2 .. R) = im pairs
+            lr_load2<R * R / 2>(Ph + kc * R * R, p);
             const f32x2 axx = pack2(a.x, a.x), ayy = pack2(a.y, a.y), nax = pack2(-a.x, -a.x), mm = pack2(m, m);
 #pragma unroll
             for (int h = 0; h < R / 2; ++h) {
@@ -217,45 +227,52 @@ __global__ void __launch_bounds__(LR32_WARPS * 32, 1)
 #pragma unroll
             for (int q = 0; q < NP; ++q) gop[q] = ffma2(mm, p[R / 2 + q], gop[q]);
         }
-        __syncwarp();
-        // ---- c. the r x r solve ----
+        // ---- c. the other half of the frame lives 16 lanes away; the r x r solve (both halves, redundantly) ----
         float tr[R], ti[R], gd[R], gor[NP], goi[NP];
 #pragma unroll
         for (int h = 0; h < R / 2; ++h) { unpack2(trp[h], tr[2 * h], tr[2 * h + 1]); unpack2(tip[h], ti[2 * h], ti[2 * h + 1]); unpack2(gdp[h], gd[2 * h], gd[2 * h + 1]); }
 #pragma unroll
         for (int q = 0; q < NP; ++q) unpack2(gop[q], gor[q], goi[q]);
-        lr_solve<float, R>(tr, ti, gd, gor, goi, lane < valid ? sigma2[f0 + lane] : 1.f, tab + TB::L);
-        // ---- d. H = U w through the tile (pairs over j, one final add), coalesced streaming store ----
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            tr[j] += __shfl_xor_sync(0xffffffffu, tr[j], 16); ti[j] += __shfl_xor_sync(0xffffffffu, ti[j], 16); gd[j] += __shfl_xor_sync(0xffffffffu, gd[j], 16);
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { gor[q] += __shfl_xor_sync(0xffffffffu, gor[q], 16); goi[q] += __shfl_xor_sync(0xffffffffu, goi[q], 16); }
+        __syncwarp();
+        lr_solve<float, R>(tr, ti, gd, gor, goi, f < valid ? sigma2[f0 + f] : 1.f, tab + TB::L);
+        // ---- d. H = U w for this half's bins through the tile (pairs over j, one final add), coalesced streaming store ----
         {
             f32x2 wr2[R / 2], wi2[R / 2], nwi2[R / 2];
 #pragma unroll
             for (int h = 0; h < R / 2; ++h) {
                 wr2[h] = pack2(tr[2 * h], tr[2 * h + 1]); wi2[h] = pack2(ti[2 * h], ti[2 * h + 1]); nwi2[h] = pack2(-ti[2 * h], -ti[2 * h + 1]);
             }
-#pragma unroll 4
-            for (int kk = 0; kk < NSC; ++kk) {
-                f32x2 u[R];
-                lr_load2<R>(tab + TB::U + kk * 2 * R, u);
-                f32x2 hr2 = 0ull, hi2 = 0ull;
+#pragma unroll 3
+            for (int kk = 0; kk < LR_HB; ++kk) {
+                if (kk < nb) {
+                    f32x2 u[R];
+                    lr_load2<R>(Uh + kk * 2 * R, u);
+                    f32x2 hr2 = 0ull, hi2 = 0ull;
 #pragma unroll
-                for (int h = 0; h < R / 2; ++h) {
-                    hr2 = ffma2(u[h], wr2[h], hr2); hr2 = ffma2(u[R / 2 + h], nwi2[h], hr2);
-                    hi2 = ffma2(u[h], wi2[h], hi2); hi2 = ffma2(u[R / 2 + h], wr2[h], hi2);
+                    for (int h = 0; h < R / 2; ++h) {
+                        hr2 = ffma2(u[h], wr2[h], hr2); hr2 = ffma2(u[R / 2 + h], nwi2[h], hr2);
+                        hi2 = ffma2(u[h], wi2[h], hi2); hi2 = ffma2(u[R / 2 + h], wr2[h], hi2);
+                    }
+                    float r0, r1, i0, i1;
+                    unpack2(hr2, r0, r1); unpack2(hi2, i0, i1);
+                    Ar[kk] = make_float2(r0 + r1, i0 + i1);
                 }
-                float r0, r1, i0, i1;
-                unpack2(hr2, r0, r1); unpack2(hi2, i0, i1);
-                Ar[kk] = make_float2(r0 + r1, i0 + i1);
             }
         }
         __syncwarp();
         if (fast_out) {
             const float4 *A4 = reinterpret_cast<const float4 *>(A) + lane;
             float4 *po = reinterpret_cast<float4 *>(H + f0 * NSC) + lane;
-#pragma unroll 9
-            for (int i = 0; i < 27; ++i)
-                if (i < 26 || lane < 16) st_stream(po + 32 * i, A4[32 * i]);
+#pragma unroll 7
+            for (int i = 0; i < 14; ++i)
+                if (i < 13 || lane < 8) st_stream(po + 32 * i, A4[32 * i]);
         } else {
-#pragma unroll 4
             for (int fr = 0; fr < valid; ++fr)
                 for (int kk = lane; kk < NSC; kk += 32) st_stream(H + (f0 + fr) * NSC + kk, A[fr * NSC + kk]);
         }
@@ -264,13 +281,11 @@ __global__ void __launch_bounds__(LR32_WARPS * 32, 1)
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// FP64: chunk = 16 frames, lane = (frame f = lane & 15, half h = lane >> 4 of the bins: h = 0 -> bins 0..26, h = 1 -> bins 27..52).
-// The tile holds 16 x 53 values exactly like the FP32 one, so the chunk is again ONE contiguous run of 16-byte vectors in HBM (a
-// complex128 value each) and staging is index-free; the two halves of a frame meet in one __shfl_xor(16) step per accumulator.
+// FP64: 10 warps (8 at rank > 4), one complex128 value per 16-byte vector.
 // (First version: 32 frames per warp in two slabs of 27 / 26 bins, staged row by row with 27 of 32 lanes: 0.732 ms per 1 Mi frames,
-// ncu long_scoreboard 28 % of the samples in the staging loads.)
+// ncu long_scoreboard 28 % of the samples in the staging loads; this one: 0.614 ms.)
 template <int R> struct Lr64Warps { static constexpr int N = R <= 4 ? 10 : 8; };
-constexpr int LR64_FR = 16, LR64_TILE = LR64_FR * NSC, LR64_HB = 27;
+constexpr int LR64_FR = LR_FR, LR64_TILE = LR_TILE, LR64_HB = LR_HB;
 
 template <int R>
 __global__ void __launch_bounds__(Lr64Warps<R>::N * 32, 1)
@@ -423,11 +438,12 @@ __global__ void __launch_bounds__(Lr64Warps<R>::N * 32, 1)
 template <int R>
 static cudaError_t launch_lr32(const void *tab, const void *tx, const void *rx, int64_t stride, const void *sigma2, void *H, int64_t n, int aligned16, cudaStream_t s)
 {
-    const size_t smem = sizeof(float) * LrTab<R>::SIZE + (size_t)LR32_WARPS * LR32_TILE * (sizeof(float2) + sizeof(float));
+    constexpr int LR32_WARPS = Lr32Warps<R>::N;
+    const size_t smem = sizeof(float) * LrTab<R>::SIZE + (size_t)LR32_WARPS * LR_TILE * (sizeof(float2) + sizeof(float));
     auto kern = mmse_lowrank_f32_kernel<R>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int64_t n_chunks = (n + 31) / 32;
+    const int64_t n_chunks = (n + LR_FR - 1) / LR_FR;
     const unsigned grid = (unsigned)std::min<int64_t>((n_chunks + LR32_WARPS - 1) / LR32_WARPS, 148);
     kern<<<grid, LR32_WARPS * 32, smem, s>>>((const float *)tab, (const float2 *)tx, (const float2 *)rx, stride, (const float *)sigma2, (float2 *)H, n, aligned16);
     return cudaGetLastError();
