@@ -8,21 +8,20 @@
 //     G = U^H diag(|x|^2) U                          r x r Hermitian
 //     S = sigma2 L^-1 + G,   S w = t                 r x r Hermitian positive definite solve in registers
 //     H = U w
-// -- 8 kflop per frame at r = 4 instead of the 442 kflop of the 53 x 53 solve (wifi_solve_hpd.cu), on the frame's own 159 complex
+// -- 6 kflop per frame at r = 4 instead of the 442 kflop of the 53 x 53 solve (wifi_solve_hpd.cu), on the frame's own 159 complex
 // values of traffic.  Both sigma2 AND the modulus pattern |x_k|^2 may differ per frame (QAM), which the eigen-domain path
 // (wifi_eig.cu: shared |x_k|^2 only) cannot do; a bin without transmit energy (the DC bin) simply contributes nothing.
 // S is well conditioned (G ~ |x|^2 I, sigma2/l tiny), so FP32 ARITHMETIC meets the 1e-4 bound here, where FP32 elimination of
 // the 53 x 53 matrix R + D (condition 1e7) cannot.
 //
-// Kernels: one persistent CTA per SM; a warp owns a chunk of frames at a time (a 20 KB private shared-memory tile per warp).
+// Kernels: one persistent CTA per SM; a warp owns a chunk of 16 frames at a time (a 10 / 20 KB private shared-memory tile per warp),
+// lane = (frame, half of the bins); the two halves of a frame are summed by one shuffle step.
 //   a. coalesced element-wise pass over the chunk (a contiguous run of 16-byte vectors: tile index = element index):
 //      a = conj(x) rx and m = |x|^2 into the tile;
 //   b. t and G accumulated over the bins from the tile (conflict-free row strides) and the shared tables U_k, P_k = conj(U_ki) U_kj
 //      (broadcast 16-byte loads);   c. S w = t by Hermitian elimination with static register indices;
 //   d. H = U w written back through the tile, coalesced streaming store.
-// FP32: chunk = 32 frames, lane = frame, accumulations as packed FFMA2 pairs.  FP64: chunk = 16 frames, lane = (frame, half of
-// the bins) -- the tile holds 16 x 53 values like the FP32 one, the two halves of a frame are summed by one shuffle step.
-// The next chunk of the warp is pulled into L2 (cp.async.bulk.prefetch.L2) while the current one is processed.
+// FP32 accumulations are packed FFMA2 pairs.  The next chunk of the warp is pulled into L2 (cp.async.bulk.prefetch.L2) while the current one is processed.
 #include <algorithm>
 #include <cmath>
 #include <type_traits>
