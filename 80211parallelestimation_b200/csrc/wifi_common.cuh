@@ -70,6 +70,15 @@ __device__ __forceinline__ double2 ld_gather(const double2 *p)
     return v;
 }
 
+// Packed FP32 pairs (sm_100a: FFMA2 / FADD2 -- one issue slot for two operations; the FMA *rate* is not higher than FFMA's, so this
+// pays where a kernel is issue- or latency-bound, not FMA-pipe-bound).  A pair lives in a 64-bit register: a float2 read as one word.
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpack2(f32x2 v, uint32_t &lo, uint32_t &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 fsub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // main.c:69-72 as written: c = Re(tx) - Im(tx) (a real scalar), H = (c*rx)/(c*tx).  Re(tx) == Im(tx)
 // gives 0/0 = NaN exactly like the reference.
 template <typename T> __device__ __forceinline__ cx<T> lt_ls_one(cx<T> tx, cx<T> rx)

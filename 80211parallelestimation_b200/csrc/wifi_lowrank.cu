@@ -38,11 +38,6 @@ template <int R> struct LrTab {
 };
 __host__ __device__ constexpr int lr_pair(int R, int i, int j) { return i * R - i * (i + 1) / 2 + (j - i - 1); }     // i < j
 
-// Packed FP32 pairs (FFMA2 on sm_100a: one issue slot for two FMAs -- the FP32 kernel is issue-bound, not FMA-pipe-bound)
-using f32x2 = unsigned long long;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 template <int N> __device__ __forceinline__ void lr_load2(const float *p, f32x2 (&v)[N])          // N pairs = N / 2 16-byte vectors
 {
     static_assert(N % 2 == 0, "whole 16-byte vectors");
