@@ -9,11 +9,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "80211parallelestimation_b200", "libwifi_b200.so")
-KEEP = ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "DMMA", "HMMA", "FFMA", "DFMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "MUFU", "CREDUX", "REDUX", "LDL", "STL")
+KEEP = ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "DMMA", "HMMA", "FFMA2", "FADD2", "FFMA", "DFMA", "LDG", "STG", "LDS", "STS", "SHFL", "BAR", "MUFU", "CREDUX", "REDUX", "LDL", "STL")
 
 HEADER = """SASS evidence (cuobjdump -sass libwifi_b200.so, sm_100a): per kernel, counts of the mnemonics that show which hardware path it uses.
 UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st (tensor memory), UBLKCP = cp.async.bulk (TMA bulk copy), UBLKPF = cp.async.bulk.prefetch.L2,
-SYNCS = mbarrier, DMMA = FP64 tensor-core mma.sync, HMMA = warp-level mma.sync (here: TF32 m16n8k8 of the batched inverse).  (B200_PROFILING.md: the PTX names never appear in SASS.)
+SYNCS = mbarrier, DMMA = FP64 tensor-core mma.sync, HMMA = warp-level mma.sync (here: TF32 m16n8k8 of the batched inverse), FFMA2 = fma.rn.f32x2 (packed FP32 pairs: the low-rank per-frame MMSE).  (B200_PROFILING.md: the PTX names never appear in SASS.)
 """
 
 
