@@ -617,6 +617,22 @@ def test_mmse_perframe_lowrank(ctx, oracle, prec, tol, qam, taps, n):
             assert rel_err(got, host(ctx.mmse_perframe(dev(R), dev(tx), dev(rx), dev(s2)))) < 1e-9
 
 
+def test_mmse_lowrank_equals_the_shared_filter_when_sigma2_is_shared(ctx, oracle):
+    """With one sigma2 and one modulus pattern for every frame the per-frame estimator IS the shared filter W = R (R + D)^-1: the
+    low-rank one-launch form (FP64) against the DMMA GEMM with the double-double filter and against the oracle, 1e-10."""
+    n = 200
+    fr = synth.make_frames(n, seed=77)
+    tx, rx = fr["tx_symb"][:, 0, :].copy(), fr["rx_symb"][:, 0, :].copy()
+    R = synth.channel_covariance()
+    d = synth.OW2 / np.abs(tx[0]) ** 2
+    W = host(ctx.mmse_filter_form(dev(R), dev(d)))
+    shared = host(ctx.mmse_shared(dev(tx), dev(rx)))
+    assert ctx.mmse_lowrank_prepare(R) == synth.TAPS
+    low = host(ctx.mmse_perframe_lowrank(dev(tx), dev(rx), dev(np.full(n, synth.OW2))))
+    assert rel_err(low, shared) < 1e-10
+    assert rel_err(low, oracle.mmse_apply(W, rx / tx)) < 1e-10
+
+
 def test_mmse_lowrank_rank_gate(wifi):
     c = wifi.WifiContext(0)
     z = np.ones((1, NSC), np.complex128)
