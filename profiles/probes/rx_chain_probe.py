@@ -4,6 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 wifi = importlib.import_module("80211parallelestimation_b200")
+if len(sys.argv) > 1:                      # A/B builds of the library
+    wifi._lib.LIB_PATH = os.path.abspath(sys.argv[1]); print("library:", wifi._lib.LIB_PATH)
 ctx = wifi.WifiContext(0)
 n = int(os.environ.get("N", 1 << 18))
 
