@@ -227,6 +227,21 @@ def cpu_estimator_baselines(seconds_each=1.5):
             e["reference_openmp_build_as_is"] = dict(timed(lambda x, y: romp.estimate(w, x, y), a, b, per_o),
                                                      note="main_openmp.c: num_threads(53) team per call, frames one after the other")
         out[w] = e
+    # configs[3]: the per-frame 53 x 53 solve.  The reference's own PS_MMSE returns NaN after 278 s per frame, so this
+    # row is the oracle's long-double LU restatement of WiFi_channel_estimation_PS_MMSE.m:16-33 on ONE core -- a port, stated as such
+    try:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
+        frp = synth.make_frames(256, seed=7, sigma2="perframe")
+        txp, rxp, R = frp["tx_symb"][:, 0, :].copy(), frp["rx_symb"][:, 0, :].copy(), synth.channel_covariance()
+        t0 = time.perf_counter(); o.mmse_perframe(R, txp[:16], rxp[:16], frp["sigma2"][:16]); per = (time.perf_counter() - t0) / 16
+        n = int(max(16, min(256, seconds_each / per)))
+        t0 = time.perf_counter(); o.mmse_perframe(R, txp[:n], rxp[:n], frp["sigma2"][:n]); dt = time.perf_counter() - t0
+        out["mmse_perframe"] = {"oracle_port_long_double_1core": {"value": n / dt, "sample": "%d frames, %.2f s" % (n, dt), "kind": "port", "cores": 1,
+                                                                  "note": "53 x 53 complex LU + back-substitution per frame in long double "
+                                                                          "(oracle/wifi_oracle.c); the reference's PS_MMSE: 278 s per frame, NaN"}}
+    except Exception as exc:                                          # the checker library is test infrastructure: never fail the bench on it
+        out["mmse_perframe"] = {"unavailable": str(exc)[:120]}
     return out
 
 
